@@ -1,0 +1,158 @@
+/*
+ * s2vt.h -- C ABI of the B200-native S2VT caption hot path (libs2vt_b200.so).
+ *
+ * The reference (adwardlee/multitask-end-to-end-video-captioning, TensorFlow 1.1 scripts) has no FFI or plugin
+ * interface: its seam is the feed/fetch contract of the graphs built by class Video_Caption_Generator and the
+ * host helpers around them.  Every entry point below replaces one such contract; the citation names the
+ * reference lines it stands in for (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C types, raw DEVICE pointers unless a parameter says "host"; the caller owns every buffer
+ *     (persistent state block and scratch workspace are sized by the library and allocated by the caller --
+ *     PyTorch in this repo); nothing is allocated after s2vt_create.
+ *   - every call is asynchronous on the given cudaStream_t and never synchronises;
+ *   - return 0 on success, a negative S2VT_E* code otherwise; s2vt_last_error() gives the text;
+ *   - one handle per GPU / process; a handle is not thread-safe; distinct handles are independent;
+ *   - rows are "sample-major" like the reference's np.vstack (reinforcement_multisampling_tf_s2vt.py:764-782):
+ *     row n of an [N, ...] tensor belongs to video n % B.
+ */
+#ifndef S2VT_H_
+#define S2VT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s2vt_handle s2vt_handle;
+typedef void* s2vt_stream; /* cudaStream_t */
+
+enum {
+    S2VT_OK = 0,
+    S2VT_EINVAL = -1,     /* bad argument / shape */
+    S2VT_ENOTFOUND = -2,  /* unknown variable name (optimistic_restore skips these silently) */
+    S2VT_ESHAPE = -3,     /* variable known, shape differs (also skipped by optimistic_restore) */
+    S2VT_ECUDA = -4,      /* CUDA runtime error, see s2vt_last_error */
+    S2VT_ENOSPACE = -5,   /* bound state / workspace block too small */
+    S2VT_ESTATE = -6      /* call order violated (e.g. backward without forward) */
+};
+
+enum { S2VT_PREC_BF16 = 0, S2VT_PREC_FP32 = 1 };
+enum { S2VT_GEMM_AUTO = 0, S2VT_GEMM_MMA_SYNC = 1, S2VT_GEMM_TCGEN05 = 2 };
+
+/* Model dimensions: the "Train Parameters" constants of reinforcement_multisampling_tf_s2vt.py:505-511
+ * (dim_image, word_dim, lstm_dim, n_video_lstm_step, n_caption_lstm_step) and n_words = len(wordtoix) (:617). */
+typedef struct s2vt_config {
+    int32_t dim_image;       /* 1536 */
+    int32_t word_dim;        /* 500  */
+    int32_t lstm_dim;        /* 1000 */
+    int32_t n_words;         /* 9972 */
+    int32_t n_video_steps;   /* T_v  */
+    int32_t n_caption_steps; /* 35   */
+    int32_t n_attributes;    /* 0, or 400 for the attribute head (reinforce_multitask_e2e_attribute_loss.py:112-114) */
+    int32_t precision;       /* S2VT_PREC_* : compute dtype of the GEMM operands (accumulation is always fp32) */
+    int32_t gemm_backend;    /* S2VT_GEMM_* for the large batched GEMMs */
+    float dropout_keep;      /* DropoutWrapper(output_keep_prob), 0.9 in the reference (:66,85-87); 1 disables */
+} s2vt_config;
+
+int s2vt_create(const s2vt_config* cfg, s2vt_handle** out);
+void s2vt_destroy(s2vt_handle* h);
+const char* s2vt_last_error(const s2vt_handle* h);
+
+/* ---- memory: Video_Caption_Generator.__init__ (:64-98) creates the variables; here the caller provides the block.
+ * state block  = fp32 parameters | fp32 gradients | Adam m | Adam v | compute-dtype weight copies | embedding table.
+ * workspace    = scratch for the largest call with at most n_videos videos / n_rows caption rows / beam k. */
+size_t s2vt_num_params(const s2vt_handle* h); /* floats in the flat fp32 parameter (= gradient = Adam slot) vector */
+size_t s2vt_state_bytes(const s2vt_handle* h);
+size_t s2vt_workspace_bytes(const s2vt_handle* h, int n_videos, int n_rows, int beam);
+int s2vt_bind(s2vt_handle* h, void* state, size_t state_bytes, void* workspace, size_t workspace_bytes);
+float* s2vt_params(const s2vt_handle* h);    /* device pointers into the state block (flat, TF layouts) */
+float* s2vt_grads(const s2vt_handle* h);
+float* s2vt_adam_m(const s2vt_handle* h);
+float* s2vt_adam_v(const s2vt_handle* h);
+
+/* Variable table keyed by the TF checkpoint names (:79-98; "s2vt/LSTM{1,2}/basic_lstm_cell/{weights,biases}" and
+ * their TF>=1.2 / TF<=0.12 aliases).  offset is in floats inside the flat vector. */
+int s2vt_num_variables(const s2vt_handle* h);
+int s2vt_variable_info(const s2vt_handle* h, int index, const char** tf_name, int64_t* offset, int64_t shape[2], int* ndim);
+/* optimistic_restore (:47-61): copy iff name and shape match.  src is a HOST pointer to fp32 data. */
+int s2vt_load_param(s2vt_handle* h, const char* tf_name, const float* src_host, const int64_t* shape, int ndim, s2vt_stream st);
+/* Re-derive the compute-dtype copies and the Wemb.W2[emb rows] gate table from the fp32 master parameters.
+ * Must follow any direct write to s2vt_params(); s2vt_optimizer_step calls it itself. */
+int s2vt_refresh(s2vt_handle* h, s2vt_stream st);
+
+/* ---- decoding -------------------------------------------------------------------------------------------------
+ * build_sampler (:342-391): greedy argmax decode, no early stop.   video fp32 [B, T_v, dim_image] -> ids int32 [B, T_c] */
+int s2vt_greedy(s2vt_handle* h, const float* video, int B, int32_t* ids_out, s2vt_stream st);
+/* build_multinomial_sampler (:294-339) called K times (:743-753) + build_sampler, fused: the frames are encoded once.
+ * sampled int32 [K*B, T_c] (row k*B+j = sample k of video j), greedy int32 [B, T_c] (nullable).
+ * Categorical draws use Philox4x32-10(seed; row_base + row, step, vocab index) Gumbel-max (tf.multinomial [lib]). */
+int s2vt_rollout(s2vt_handle* h, const float* video, int B, int K, uint64_t seed, uint32_t row_base, int32_t* sampled_out,
+                 int32_t* greedy_out, s2vt_stream st);
+/* decode_captions_masks (cider_evaluation.py:145-172), the mask half: 1 through the first <eos>. lengths nullable. */
+int s2vt_caption_masks(s2vt_handle* h, const int32_t* ids, int N, float* mask_out, int32_t* lengths_out, s2vt_stream st);
+
+/* ---- training ---------------------------------------------------------------------------------------------------
+ * build_loss (:227-292) / build_model (:100-177) forward, teacher forced, with DropoutWrapper masks drawn from
+ * Philox(drop_seed; row_base + n, step, unit) (drop_seed == 0 or dropout_keep == 1: no dropout).
+ * video fp32 [B, T_v, D]; captions int32 [N, T_c]; row n uses video n % B (B == N: one video per row, the literal feed).
+ * logp_out   fp32 [N, T_c]  log_softmax(logits)[n, t, captions[n,t]]      (un-masked; nullable)
+ * logits_out fp32 [T_c, N, n_words] the `probs` list of build_model (:157)  (nullable, debugging / parity only) */
+int s2vt_teacher_forward(s2vt_handle* h, const float* video, int B, const int32_t* captions, int N, uint64_t drop_seed,
+                         uint32_t row_base, float* logp_out, float* logits_out, s2vt_stream st);
+/* REINFORCE objective and its gradient (:643-650): sum_loss = -sum(logp*mask*(rewards-base_line)) / norm.
+ * norm <= 0 means sum(mask) of this call; pass the global sum for data-parallel runs.  Overwrites s2vt_grads()
+ * (scaled by grad_scale, 1 for the plain objective, (1-lambda) for the stage-3 mixes) and writes loss_out[0] (device). */
+int s2vt_rl_backward(s2vt_handle* h, const float* video, int B, const int32_t* captions, const float* mask, const float* rewards,
+                     const float* base_line, int N, float norm, float grad_scale, int accumulate, uint64_t drop_seed, uint32_t row_base,
+                     float* loss_out, s2vt_stream st);
+/* build_model XE objective (:153-166 = tf_s2vt.py:143-166): label-smoothed batch-mean CE, /sum(mask), + decay * L2.
+ * loss_out[0] = total loss, loss_out[1] = weight-decay part. */
+int s2vt_xe_backward(s2vt_handle* h, const float* video, int B, const int32_t* captions, const float* mask, int N, float label_smoothing,
+                     float decay, float norm, float grad_scale, int accumulate, uint64_t drop_seed, uint32_t row_base, float* loss_out,
+                     s2vt_stream st);
+/* Attribute head (reinforce_multitask_e2e_attribute_loss.py:375-380): sigmoid CE of mean_t(video) . attr_W + attr_b
+ * against labels fp32 {0,1} [B, n_attributes], / (n_attributes * B).  Adds grad_scale * gradient to attr_W / attr_b. */
+int s2vt_attribute_backward(s2vt_handle* h, const float* video, int B, const float* labels, float grad_scale, float* loss_out,
+                            s2vt_stream st);
+/* tf.clip_by_global_norm + AdamOptimizer.apply_gradients (:650-652; tf_s2vt.py:446-448), TF-1.1 Adam arithmetic.
+ * step = 1-based Adam time step; lr already includes exponential_decay.  wemb_slice_norm != 0 uses the
+ * IndexedSlices norm of the Wemb gradient.  gnorm_out (device, nullable) receives the global norm. */
+int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int wemb_slice_norm, float* gnorm_out, s2vt_stream st);
+
+/* ---- beam search: beam_probability + the host loop of final_beam_search.py:202-294 / e2e_beam_search.py:235-344,
+ * batched over B videos on the device, semantics B1-B7 of SURVEY.md.
+ * sentences int32 [B, T_c] (0-padded after the final token), lengths int32 [B], logprob / score fp32 [B]. */
+int s2vt_beam_search(s2vt_handle* h, const float* video, int B, int beam_size, float length_normalization_factor, int32_t* sentences_out,
+                     int32_t* lengths_out, float* logprob_out, float* score_out, s2vt_stream st);
+/* The single-hypothesis contracts of the reference, for drop-in callers of beam_probability:
+ * beam_init: encode one video -> state1, state2 ([1, 2*lstm_dim] = concat(c, h), state_is_tuple=False)
+ * beam_step: (state2, state1, word) -> top-k ids, probs, state2', state1'. */
+int s2vt_beam_init(s2vt_handle* h, const float* video, float* state1_out, float* state2_out, s2vt_stream st);
+int s2vt_beam_step(s2vt_handle* h, const float* state2, const float* state1, const int32_t* word, int beam_size, int32_t* idx_out,
+                   float* prob_out, float* state2_out, float* state1_out, s2vt_stream st);
+
+/* ---- CIDEr-D reward: CiderD_scorer.compute_score behind evaluate_captions_cider (cider_evaluation.py:33-39, 60-87).
+ * Tokens are int32 ids (ids >= n_words may be used for out-of-vocabulary reference words); n-grams are exact 64-bit
+ * keys of <= 4 ids of 16 bits.  Build (host, once per corpus): */
+typedef struct ciderd_corpus ciderd_corpus;
+/* ref_tokens: concatenated reference sentences; ref_offsets[n_refs+1]; video_ref_offsets[n_videos+1] indexes refs.
+ * Document frequencies are counted over these videos (CiderD df corpus); ref_len = ln(n_videos). */
+int ciderd_corpus_create(const int32_t* ref_tokens, const int64_t* ref_offsets, int64_t n_refs, const int64_t* video_ref_offsets,
+                         int64_t n_videos, ciderd_corpus** out);
+void ciderd_corpus_destroy(ciderd_corpus* c);
+size_t ciderd_corpus_device_bytes(const ciderd_corpus* c);
+/* Serialise the tables into a caller-allocated HOST buffer of ciderd_corpus_device_bytes(); the caller copies it to
+ * the device and passes that device pointer to ciderd_score. */
+int ciderd_corpus_serialize(const ciderd_corpus* c, void* host_buffer);
+/* Score N hypotheses: hyp int32 [N, T_c] (tokens before the first 0 count, R2), video_of_row int32 [N] indexes the
+ * corpus videos.  scores_out float64 [N].  counts_out (nullable) uint64 [N, 140, 2] (key, count) n-gram tables. */
+int ciderd_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, double* scores_out,
+                 unsigned long long* counts_out, s2vt_stream st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2VT_H_ */

@@ -1,0 +1,89 @@
+"""ctypes binding of libs2vt_b200.so (the C ABI of include/s2vt.h).
+
+There is no CPU fallback: if the shared library is missing or a symbol cannot be resolved, importing this
+module raises.  Build it with `python -m __graft_entry__` / `__graft_entry__.build()`.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libs2vt_b200.so')
+
+
+class S2vtConfig(C.Structure):
+    _fields_ = [('dim_image', C.c_int32), ('word_dim', C.c_int32), ('lstm_dim', C.c_int32), ('n_words', C.c_int32),
+                ('n_video_steps', C.c_int32), ('n_caption_steps', C.c_int32), ('n_attributes', C.c_int32),
+                ('precision', C.c_int32), ('gemm_backend', C.c_int32), ('dropout_keep', C.c_float)]
+
+
+PREC_BF16, PREC_FP32 = 0, 1
+GEMM_AUTO, GEMM_MMA_SYNC, GEMM_TCGEN05 = 0, 1, 2
+S2VT_OK, S2VT_EINVAL, S2VT_ENOTFOUND, S2VT_ESHAPE, S2VT_ECUDA, S2VT_ENOSPACE, S2VT_ESTATE = 0, -1, -2, -3, -4, -5, -6
+
+_vp, _i32, _i64, _u32, _u64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/s2vt.h declares
+SIGNATURES = {
+    's2vt_create': (_i32, [C.POINTER(S2vtConfig), C.POINTER(_vp)]),
+    's2vt_destroy': (None, [_vp]),
+    's2vt_last_error': (C.c_char_p, [_vp]),
+    's2vt_num_params': (_sz, [_vp]),
+    's2vt_state_bytes': (_sz, [_vp]),
+    's2vt_workspace_bytes': (_sz, [_vp, _i32, _i32, _i32]),
+    's2vt_bind': (_i32, [_vp, _vp, _sz, _vp, _sz]),
+    's2vt_params': (_vp, [_vp]),
+    's2vt_grads': (_vp, [_vp]),
+    's2vt_adam_m': (_vp, [_vp]),
+    's2vt_adam_v': (_vp, [_vp]),
+    's2vt_num_variables': (_i32, [_vp]),
+    's2vt_variable_info': (_i32, [_vp, _i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.POINTER(_i64 * 2), C.POINTER(_i32)]),
+    's2vt_load_param': (_i32, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i32, _vp]),
+    's2vt_refresh': (_i32, [_vp, _vp]),
+    's2vt_greedy': (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    's2vt_rollout': (_i32, [_vp, _vp, _i32, _i32, _u64, _u32, _vp, _vp, _vp]),
+    's2vt_caption_masks': (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
+    's2vt_teacher_forward': (_i32, [_vp, _vp, _i32, _vp, _i32, _u64, _u32, _vp, _vp, _vp]),
+    's2vt_rl_backward': (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _u64, _u32, _vp, _vp]),
+    's2vt_xe_backward': (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _i32, _u64, _u32, _vp, _vp]),
+    's2vt_attribute_backward': (_i32, [_vp, _vp, _i32, _vp, _f32, _vp, _vp]),
+    's2vt_optimizer_step': (_i32, [_vp, _f32, _f32, _i64, _i32, _vp, _vp]),
+    's2vt_beam_search': (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    's2vt_beam_init': (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    's2vt_beam_step': (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    'ciderd_corpus_create': (_i32, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_vp)]),
+    'ciderd_corpus_destroy': (None, [_vp]),
+    'ciderd_corpus_device_bytes': (_sz, [_vp]),
+    'ciderd_corpus_serialize': (_i32, [_vp, _vp]),
+    'ciderd_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once and attach the prototypes.  Raises if it is absent -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('%s is missing: run `python -c "import __graft_entry__ as g; g.build()"` first '
+                          '(there is no CPU fallback)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class S2vtError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, 's2vt error %d: %s' % (code, msg))
+        self.code = code
+
+
+def check(handle, code):
+    if code != 0:
+        msg = load().s2vt_last_error(handle)
+        raise S2vtError(code, msg.decode() if msg else '')

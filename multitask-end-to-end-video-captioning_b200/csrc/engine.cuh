@@ -1,0 +1,70 @@
+// Handle layout and helpers shared by the translation units of libs2vt_b200.so.
+#pragma once
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/s2vt.h"
+#include "common.cuh"
+
+struct Var {
+    std::string name;
+    std::vector<std::string> aliases;
+    int64_t rows, cols;  // cols == 0 -> 1-D
+    size_t off;          // floats
+    size_t count() const { return (size_t)rows * (cols ? cols : 1); }
+};
+
+// Bump allocator over a caller-owned block; with base == nullptr it only measures.
+struct Arena {
+    char* base;
+    size_t cap, used;
+    bool overflow;
+    Arena(void* b, size_t c) : base((char*)b), cap(c), used(0), overflow(false) {}
+    template <typename U> U* take(size_t n) {
+        size_t bytes = ru64(n * sizeof(U), 256);
+        size_t o = used;
+        used += bytes;
+        if (base && used > cap) { overflow = true; return nullptr; }
+        return base ? reinterpret_cast<U*>(base + o) : nullptr;
+    }
+};
+
+struct s2vt_handle {
+    s2vt_config cfg;
+    int D, E, H, V, Tv, Tc, A, T;        // logical dims, T = Tv + Tc
+    int Dp, Ep, Hp, Vp, Gp, Ap;          // padded dims, Gp = 4*Hp
+    size_t esz;                           // sizeof(compute dtype)
+    std::vector<Var> vars;
+    size_t P;                             // floats in the flat parameter vector
+    // state block
+    char* state; size_t state_bytes;
+    char* ws; size_t ws_bytes;
+    float *params, *grads, *adam_m, *adam_v;
+    double* sq;                           // [0] dense grad sumsq, [1] dense Wemb sumsq, [2] Wemb slice sumsq, [3] scratch
+    float* scal;                          // small fp32 scratch (loss parts, norm)
+    void *WeT, *W1xT, *W1hT, *W1h, *W1x, *W2xT, *W2x, *W2eT, *W2e, *W2hT, *W2h, *WoT, *Wo, *WembC, *attrWT;
+    float *be_p, *b1_p, *b2_p, *bo_p, *Etab;
+    bool bound, fresh;
+    // variable indices
+    int iWemb, iWe, ibe, iWo, ibo, iW1, ib1, iW2, ib2, iAW, iAb;
+    mutable std::string err;
+    int fail(int code, const char* fmt, ...) const {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf;
+        return code;
+    }
+    float* P_(int i) const { return params + vars[i].off; }
+    float* G_(int i) const { return grads + vars[i].off; }
+};
+
+#define CUDA_TRY(h, expr)                                                                                        \
+    do {                                                                                                         \
+        cudaError_t _e = (expr);                                                                                 \
+        if (_e != cudaSuccess) return (h)->fail(S2VT_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define KCHECK(h) CUDA_TRY(h, cudaGetLastError())

@@ -1,0 +1,365 @@
+// GEMM building blocks: C[M,N] = A[M,K] . B[N,K]^T  (both operands K-major, N and K multiples of 128,
+// M guarded), accumulators handed to an epilogue functor through a shared-memory tile.
+//
+// Mainloops:
+//   * Mainloop<bf16,...>  : mma.sync.m16n8k16 bf16 -> fp32, cp.async 3-stage pipeline (warp-level tensor path; the
+//                           recurrent-step kernels use it and it is the fallback/checker for the tcgen05 GEMM).
+//   * Mainloop<float,...> : SIMT fp32 FMA (the 1e-5 "fp32 mode" of BASELINE.json; also the on-device checker).
+//   * gemm_tcgen05.cuh    : tcgen05.mma + TMA + TMEM for the large batched GEMMs.
+// Epilogues (all read the fp32 tile Cs[BM][LDC] that the mainloop leaves in shared memory):
+//   EpiStore, EpiGradStore, EpiLstmFwd, EpiLstmBwd.
+#pragma once
+#include "common.cuh"
+
+// -----------------------------------------------------------------------------------------------------------------
+// tile configurations
+// -----------------------------------------------------------------------------------------------------------------
+template <int BM_, int BN_, int WM_, int WN_>
+struct TileCfg {
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_;
+    static constexpr int NWARPS = (BM / WM) * (BN / WN);
+    static constexpr int NTHREADS = NWARPS * 32;
+    static constexpr int LDC = BN + 8;  // fp32 epilogue tile row stride
+    static constexpr int BK = 32, STAGES = 3, LDS = BK + 8;
+    static constexpr size_t PIPE_BYTES = (size_t)STAGES * (BM + BN) * LDS * 2;
+    static constexpr size_t SIMT_BYTES = (size_t)16 * (BM + 4 + BN + 4) * 4;
+    static constexpr size_t EPI_BYTES = (size_t)BM * LDC * 4;
+    static constexpr size_t SMEM_BYTES =
+        (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) > SIMT_BYTES ? (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) : SIMT_BYTES;
+};
+typedef TileCfg<128, 128, 64, 32> CfgBig;    // batched GEMMs: 8 warps, warp tile 64x32
+typedef TileCfg<64, 32, 16, 32> CfgStep;     // recurrent-step GEMMs: 4 warps, many CTAs for small M
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename T, class Cfg> struct Mainloop;
+
+// ---- bf16 tensor-core mainloop (mma.sync) ---------------------------------------------------------------------
+template <class Cfg>
+struct Mainloop<bf16, Cfg> {
+    __device__ static void run(const bf16* __restrict__ A, int lda, const bf16* __restrict__ B, int ldb, int M, int K, int m0, int n0,
+                               unsigned char* smem, float* Cs) {
+        constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, LDS = Cfg::LDS, ST = Cfg::STAGES;
+        constexpr int MT = WM / 16, NT = WN / 8;
+        static_assert(NT % 2 == 0, "warp tile N must cover pairs of n8 tiles");
+        bf16* sA = reinterpret_cast<bf16*>(smem);
+        bf16* sB = sA + ST * BM * LDS;
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        const int wm = warp / (BN / WN), wn = warp % (BN / WN);
+        const int KT = K / Cfg::BK;
+
+        auto load_stage = [&](int s, int kt) {
+            bf16* a = sA + s * BM * LDS;
+            bf16* b = sB + s * BN * LDS;
+            for (int c = tid; c < BM * 4; c += Cfg::NTHREADS) {
+                int r = c >> 2, ch = c & 3, gr = m0 + r;
+                bool ok = gr < M;
+                cp_async16(a + r * LDS + ch * 8, A + (size_t)(ok ? gr : 0) * lda + kt * 32 + ch * 8, ok ? 16 : 0);
+            }
+            for (int c = tid; c < BN * 4; c += Cfg::NTHREADS) {
+                int r = c >> 2, ch = c & 3;
+                cp_async16(b + r * LDS + ch * 8, B + (size_t)(n0 + r) * ldb + kt * 32 + ch * 8, 16);
+            }
+        };
+
+        float acc[MT][NT][4];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+#pragma unroll
+        for (int s = 0; s < ST - 1; ++s) {
+            if (s < KT) load_stage(s, s);
+            cp_async_commit();
+        }
+        for (int kt = 0; kt < KT; ++kt) {
+            cp_async_wait<ST - 2>();
+            __syncthreads();
+            if (kt + ST - 1 < KT) load_stage((kt + ST - 1) % ST, kt + ST - 1);
+            cp_async_commit();
+            const bf16* a = sA + (kt % ST) * BM * LDS;
+            const bf16* b = sB + (kt % ST) * BN * LDS;
+#pragma unroll
+            for (int kk = 0; kk < 32; kk += 16) {
+                uint32_t af[MT][4];
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+                    ldmatrix_x4(af[i][0], af[i][1], af[i][2], af[i][3], a + (wm * WM + i * 16 + (lane & 15)) * LDS + kk + (lane >> 4) * 8);
+#pragma unroll
+                for (int j = 0; j < NT; j += 2) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4(b0, b1, b2, b3, b + (wn * WN + j * 8 + (lane & 7) + (lane >> 4) * 8) * LDS + kk + ((lane >> 3) & 1) * 8);
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        mma_bf16_16816(acc[i][j], af[i], b0, b1);
+                        mma_bf16_16816(acc[i][j + 1], af[i], b2, b3);
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();  // every warp is done with the pipeline buffers; Cs aliases them
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                int r = wm * WM + i * 16 + (lane >> 2), c = wn * WN + j * 8 + (lane & 3) * 2;
+                *reinterpret_cast<float2*>(Cs + r * Cfg::LDC + c) = make_float2(acc[i][j][0], acc[i][j][1]);
+                *reinterpret_cast<float2*>(Cs + (r + 8) * Cfg::LDC + c) = make_float2(acc[i][j][2], acc[i][j][3]);
+            }
+        __syncthreads();
+    }
+};
+
+// ---- fp32 SIMT mainloop ----------------------------------------------------------------------------------------
+template <class Cfg>
+struct Mainloop<float, Cfg> {
+    __device__ static void run(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K, int m0, int n0,
+                               unsigned char* smem, float* Cs) {
+        constexpr int BM = Cfg::BM, BN = Cfg::BN, NTH = Cfg::NTHREADS, BK = 16;
+        constexpr int TGN = BN / 4, TGM = NTH / TGN, TM = BM / TGM;
+        static_assert(TGM * TM == BM && TGN * 4 == BN, "bad SIMT thread grid");
+        constexpr int LDA = BM + 4, LDB = BN + 4;
+        float* As = reinterpret_cast<float*>(smem);  // [BK][LDA]
+        float* Bs = As + BK * LDA;                   // [BK][LDB]
+        const int tid = threadIdx.x, tx = tid % TGN, ty = tid / TGN;
+        float acc[TM][4];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+        for (int k0 = 0; k0 < K; k0 += BK) {
+            for (int c = tid; c < BM * (BK / 4); c += NTH) {
+                int r = c % BM, ch = c / BM, gr = m0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gr < M) v = *reinterpret_cast<const float4*>(A + (size_t)gr * lda + k0 + ch * 4);
+                As[(ch * 4 + 0) * LDA + r] = v.x; As[(ch * 4 + 1) * LDA + r] = v.y;
+                As[(ch * 4 + 2) * LDA + r] = v.z; As[(ch * 4 + 3) * LDA + r] = v.w;
+            }
+            for (int c = tid; c < BN * (BK / 4); c += NTH) {
+                int r = c % BN, ch = c / BN;
+                float4 v = *reinterpret_cast<const float4*>(B + (size_t)(n0 + r) * ldb + k0 + ch * 4);
+                Bs[(ch * 4 + 0) * LDB + r] = v.x; Bs[(ch * 4 + 1) * LDB + r] = v.y;
+                Bs[(ch * 4 + 2) * LDB + r] = v.z; Bs[(ch * 4 + 3) * LDB + r] = v.w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                float4 b = *reinterpret_cast<const float4*>(Bs + k * LDB + tx * 4);
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    float a = As[k * LDA + ty + i * TGM];
+                    acc[i][0] = fmaf(a, b.x, acc[i][0]); acc[i][1] = fmaf(a, b.y, acc[i][1]);
+                    acc[i][2] = fmaf(a, b.z, acc[i][2]); acc[i][3] = fmaf(a, b.w, acc[i][3]);
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+            *reinterpret_cast<float4*>(Cs + (ty + i * TGM) * Cfg::LDC + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        __syncthreads();
+    }
+};
+
+// -----------------------------------------------------------------------------------------------------------------
+// epilogues
+// -----------------------------------------------------------------------------------------------------------------
+// out = acc (+ bias[col]) (+ old out if accumulate); written as fp32 and/or compute dtype.
+template <typename T>
+struct EpiStore {
+    struct Params {
+        float* outF; T* outT; int ldo; const float* bias; int M; int accumulate;
+    };
+    template <class Cfg>
+    __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
+        for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN / 4; idx += Cfg::NTHREADS) {
+            int r = idx / (Cfg::BN / 4), c = (idx % (Cfg::BN / 4)) * 4, gr = m0 + r, gc = n0 + c;
+            if (gr >= p.M) continue;
+            float4 v = *reinterpret_cast<const float4*>(Cs + r * Cfg::LDC + c);
+            if (p.bias) { float4 b = *reinterpret_cast<const float4*>(p.bias + gc); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+            size_t o = (size_t)gr * p.ldo + gc;
+            if (p.outF) {
+                if (p.accumulate) { float4 w = *reinterpret_cast<const float4*>(p.outF + o); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+                *reinterpret_cast<float4*>(p.outF + o) = v;
+            }
+            if (p.outT) { p.outT[o] = from_f32<T>(v.x); p.outT[o + 1] = from_f32<T>(v.y); p.outT[o + 2] = from_f32<T>(v.z); p.outT[o + 3] = from_f32<T>(v.w); }
+        }
+    }
+};
+
+// Weight-gradient store into the fp32 TF-layout gradient block:  grad[(row0 + r) * ldg + colmap(c)] += scale * acc.
+// gate_h > 0 : columns are in packed gate order (c = 4u+g) and map to the TF order g*gate_h + u (u < gate_h).
+// gate_h == 0: identity columns, valid while c < ncols.   Rows valid while r < nrows.
+struct EpiGradStore {
+    struct Params {
+        float* grad; int ldg; int nrows; int ncols; int gate_h; float scale;
+    };
+    template <class Cfg>
+    __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
+        if (p.gate_h > 0) {
+            // thread -> (row, gate, unit): consecutive threads take consecutive units of one gate (coalesced stores)
+            constexpr int UN = Cfg::BN / 4;
+            for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::NTHREADS) {
+                int r = idx / Cfg::BN, rem = idx % Cfg::BN, g = rem / UN, ul = rem % UN;
+                int gr = m0 + r, u = n0 / 4 + ul;
+                if (gr >= p.nrows || u >= p.gate_h) continue;
+                float* dst = p.grad + (size_t)gr * p.ldg + (size_t)g * p.gate_h + u;
+                *dst += p.scale * Cs[r * Cfg::LDC + ul * 4 + g];
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::NTHREADS) {
+                int r = idx / Cfg::BN, c = idx % Cfg::BN, gr = m0 + r, gc = n0 + c;
+                if (gr >= p.nrows || gc >= p.ncols) continue;
+                float* dst = p.grad + (size_t)gr * p.ldg + gc;
+                *dst += p.scale * Cs[r * Cfg::LDC + c];
+            }
+        }
+    }
+};
+
+// Fused BasicLSTMCell forward (Q7).  acc = h_prev . Wh (packed gate columns 4u+g);
+//   pre = acc + bias + add0[row0(row)] + add1[tok[row]] ; i,j,f,o -> c' = c*sig(f+1) + sig(i)*tanh(j) ; h' = tanh(c')*sig(o)
+template <typename T>
+struct EpiLstmFwd {
+    struct Params {
+        int M; int Hp;
+        const float* bias;                 // [4Hp] packed
+        const float* add0; int add0_mod;   // [*, 4Hp] input-side pre-activations; row = add0_mod > 0 ? row % add0_mod : row
+        const float* add1; const int* tok; // embedding table [V, 4Hp] gathered by tok[row] (nullable)
+        const float* c_prev; float* c_out; // [M, Hp]
+        T* h_out;                          // [M, Hp] compute dtype (next step's A operand / batched GEMM operand)
+        float* h_outF;                     // optional fp32 copy
+        float* gates_out;                  // optional [M, 4Hp] saved activations (si, tj, sf, so) for BPTT
+        T* hdrop_out;                      // optional dropout-applied output (DropoutWrapper, Q2)
+        unsigned long long seed; uint32_t stream; uint32_t step; uint32_t row_base; float keep;
+    };
+    template <class Cfg>
+    __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
+        constexpr int UN = Cfg::BN / 4;
+        const int G = 4 * p.Hp;
+        for (int idx = threadIdx.x; idx < Cfg::BM * UN; idx += Cfg::NTHREADS) {
+            int r = idx / UN, ul = idx % UN, gr = m0 + r;
+            if (gr >= p.M) continue;
+            int gc = n0 + ul * 4, u = gc >> 2;
+            float4 v = *reinterpret_cast<const float4*>(Cs + r * Cfg::LDC + ul * 4);
+            float4 b = *reinterpret_cast<const float4*>(p.bias + gc);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            if (p.add0) {
+                int ar = p.add0_mod > 0 ? gr % p.add0_mod : gr;
+                float4 a = *reinterpret_cast<const float4*>(p.add0 + (size_t)ar * G + gc);
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            if (p.add1) {
+                float4 a = *reinterpret_cast<const float4*>(p.add1 + (size_t)p.tok[gr] * G + gc);
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            float si = sigmoidf_(v.x), tj = tanhf(v.y), sf = sigmoidf_(v.z + 1.0f), so = sigmoidf_(v.w);
+            size_t o = (size_t)gr * p.Hp + u;
+            float c = p.c_prev[o] * sf + si * tj;
+            float h = tanhf(c) * so;
+            p.c_out[o] = c;
+            p.h_out[o] = from_f32<T>(h);
+            if (p.h_outF) p.h_outF[o] = h;
+            if (p.gates_out) *reinterpret_cast<float4*>(p.gates_out + (size_t)gr * G + gc) = make_float4(si, tj, sf, so);
+            if (p.hdrop_out) {
+                float m = p.keep < 1.0f ? dropout_mult(p.seed, p.stream, p.row_base + gr, p.step, u, p.keep) : 1.0f;
+                p.hdrop_out[o] = from_f32<T>(h * m);
+            }
+        }
+    }
+};
+
+// BasicLSTMCell backward for one time step.  dh = dh_rec + dh_ext * dropout ; produces the pre-activation gate
+// gradients (packed order) and dc for the previous step.
+struct LstmBwdArgs {
+    int M; int Hp;
+    const float* dh_ext;     // [M, Hp] nullable: gradient arriving from the layer above at this step
+    const float* gates;      // [M, 4Hp] (si, tj, sf, so)
+    const float* c_prev;     // [M, Hp]
+    const float* c_new;      // [M, Hp]
+    float* dc;               // [M, Hp] in: dc from step t+1, out: dc for step t-1
+    unsigned long long seed; uint32_t stream; uint32_t step; uint32_t row_base; float keep;  // dropout on dh_ext (keep>=1: none)
+};
+template <typename T>
+__device__ __forceinline__ void lstm_bwd_unit(const LstmBwdArgs& p, T* dg_out, int gr, int u, float dh_rec) {
+    const int G = 4 * p.Hp;
+    size_t o = (size_t)gr * p.Hp + u;
+    float dh = dh_rec;
+    if (p.dh_ext) {
+        float m = p.keep < 1.0f ? dropout_mult(p.seed, p.stream, p.row_base + gr, p.step, u, p.keep) : 1.0f;
+        dh += p.dh_ext[o] * m;
+    }
+    float4 g = *reinterpret_cast<const float4*>(p.gates + (size_t)gr * G + 4 * u);
+    float si = g.x, tj = g.y, sf = g.z, so = g.w;
+    float tc = tanhf(p.c_new[o]);
+    float d_o = dh * tc;
+    float dc = p.dc[o] + dh * so * (1.0f - tc * tc);
+    float di = dc * tj, dj = dc * si, df = dc * p.c_prev[o];
+    p.dc[o] = dc * sf;
+    T* d = dg_out + (size_t)gr * G + 4 * u;
+    d[0] = from_f32<T>(di * si * (1.0f - si));
+    d[1] = from_f32<T>(dj * (1.0f - tj * tj));
+    d[2] = from_f32<T>(df * sf * (1.0f - sf));
+    d[3] = from_f32<T>(d_o * so * (1.0f - so));
+}
+// GEMM form: acc[row, u] = dG(t+1)[row, :] . Wh[u, :]   (N dimension = hidden units)
+template <typename T>
+struct EpiLstmBwd {
+    struct Params {
+        LstmBwdArgs a; T* dg_out;
+    };
+    template <class Cfg>
+    __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
+        for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::NTHREADS) {
+            int r = idx / Cfg::BN, c = idx % Cfg::BN, gr = m0 + r;
+            if (gr >= p.a.M) continue;
+            lstm_bwd_unit<T>(p.a, p.dg_out, gr, n0 + c, Cs[r * Cfg::LDC + c]);
+        }
+    }
+};
+
+template <typename T, class Cfg, class Epi>
+__global__ void __launch_bounds__(Cfg::NTHREADS) gemm_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, int M, int K,
+                                                             typename Epi::Params ep) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int m0 = blockIdx.y * Cfg::BM, n0 = blockIdx.x * Cfg::BN;
+    float* Cs = reinterpret_cast<float*>(smem);
+    Mainloop<T, Cfg>::run(A, lda, B, ldb, M, K, m0, n0, smem, Cs);
+    Epi::template apply<Cfg>(ep, Cs, m0, n0);
+}
+
+// Host launcher.  N, K are padded sizes (multiples of 128).
+template <typename T, class Cfg, class Epi>
+inline cudaError_t launch_gemm(cudaStream_t st, const T* A, int lda, const T* B, int ldb, int M, int N, int K, const typename Epi::Params& ep) {
+    if (M <= 0) return cudaSuccess;
+    auto kern = gemm_kernel<T, Cfg, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid(N / Cfg::BN, (M + Cfg::BM - 1) / Cfg::BM);
+    kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(A, lda, B, ldb, M, K, ep);
+    return cudaGetLastError();
+}

@@ -1,0 +1,749 @@
+// libs2vt_b200.so -- model entry points of the C ABI declared in include/s2vt.h.
+//
+// Data flow (one REINFORCE iteration; B videos, K samples, N = K*B rows, T = T_v + T_c steps):
+//   frontend : video -> Xc (time-major, compute dtype) -> img = Xc.We + be -> G1x = img.W1x            [batched GEMMs]
+//   LSTM1    : T recurrent steps over B rows only -- LSTM1 never sees a word (decoder input is `padding`,
+//              reinforcement_multisampling_tf_s2vt.py:327-328), so it is shared by every sample of a video
+//   G2x      : (dropout(h1)) . W2[out1 rows]  for all T steps at once                                   [batched GEMM]
+//   LSTM2    : T recurrent steps, per row: h2.W2[h rows] + G2x + Etab[prev word] (Etab = Wemb.W2[emb rows])
+//   logits   : out2 . embed_word_W + b                      [per step in rollouts, batched when teacher forced]
+//   backward : mirror image; weight gradients as batched GEMMs over the stashed per-step gate gradients.
+#include "engine.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+template <typename T>
+__global__ void lstm_bwd_elem_kernel(LstmBwdArgs a, T* dg_out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.M * a.Hp) return;
+    lstm_bwd_unit<T>(a, dg_out, idx / a.Hp, idx % a.Hp, 0.f);
+}
+
+// out[r, :] = in[r % B, :]  (replicate the per-video encoder state over the K+1 decode rows)
+template <typename U>
+__global__ void tile_rows_kernel(const U* __restrict__ in, int B, int R, int ld, U* __restrict__ out) {
+    int r = blockIdx.x;
+    const U* s = in + (size_t)(r % B) * ld;
+    U* d = out + (size_t)r * ld;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) d[c] = s[c];
+}
+
+// mean over frames of the fp32 feed: pooled[b, d] = mean_t video[b, t, d]  -> compute dtype [B, Dp]
+template <typename T>
+__global__ void mean_frames_kernel(const float* __restrict__ video, int Tv, int D, int Dp, T* __restrict__ out) {
+    int b = blockIdx.x;
+    for (int d = threadIdx.x; d < Dp; d += blockDim.x) {
+        float acc = 0.f;
+        if (d < D) for (int t = 0; t < Tv; ++t) acc += video[((size_t)b * Tv + t) * D + d];
+        out[(size_t)b * Dp + d] = from_f32<T>(acc / (float)Tv);
+    }
+}
+
+// sigmoid cross entropy with logits (tf.nn.sigmoid_cross_entropy_with_logits [lib]) / (A*B); dz in compute dtype
+template <typename T>
+__global__ void sigmoid_ce_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ y, int B, int A, int Ap, float scale, T* __restrict__ dz,
+                                  float* __restrict__ loss) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int idx = threadIdx.x; idx < B * Ap; idx += blockDim.x) {
+        int b = idx / Ap, a = idx % Ap;
+        float d = 0.f;
+        if (a < A) {
+            float zz = z[(size_t)b * ldz + a], yy = y[(size_t)b * A + a];
+            acc += fmaxf(zz, 0.f) - zz * yy + log1pf(expf(-fabsf(zz)));
+            d = scale * (sigmoidf_(zz) - yy) / (float)(A * B);
+        }
+        dz[(size_t)b * Ap + a] = from_f32<T>(d);
+    }
+    acc = block_reduce(acc, [](float a, float b) { return a + b; }, red);
+    if (threadIdx.x == 0) loss[0] = acc / (float)(A * B);
+}
+
+__global__ void add_scaled_scalar_kernel(float* dst, const float* src, float scale) { dst[0] += scale * src[0]; }
+__global__ void copy_slice_norm_kernel(const float* src, double* dst) { dst[0] = (double)src[0]; }
+__global__ void xe_total_kernel(float* out, const double* sq, float decay, float scale) {
+    float wd = decay * 0.5f * (float)sq[3];
+    out[1] = wd;
+    out[0] += scale * wd;
+}
+
+// =================================================================================================================
+// handle / memory
+// =================================================================================================================
+static void add_var(s2vt_handle* h, const char* name, std::vector<std::string> aliases, int64_t rows, int64_t cols) {
+    Var v; v.name = name; v.aliases = aliases; v.rows = rows; v.cols = cols; v.off = h->P;
+    h->P += ru64(v.count(), 4);
+    h->vars.push_back(v);
+}
+
+template <typename F> static void layout_state(s2vt_handle* h, Arena& a, F assign) {
+    const size_t e = h->esz;
+    const int Dp = h->Dp, Ep = h->Ep, Hp = h->Hp, Vp = h->Vp, Gp = h->Gp, Ap = h->Ap;
+    float* params = a.take<float>(h->P);
+    float* grads = a.take<float>(h->P + 8);
+    float* m = a.take<float>(h->P);
+    float* v = a.take<float>(h->P);
+    double* sq = a.take<double>(8);
+    float* scal = a.take<float>(64);
+    size_t copies_begin = a.used;
+    char* WeT = a.take<char>((size_t)Ep * Dp * e);
+    char* W1xT = a.take<char>((size_t)Gp * Ep * e);
+    char* W1hT = a.take<char>((size_t)Gp * Hp * e);
+    char* W1h = a.take<char>((size_t)Hp * Gp * e);
+    char* W1x = a.take<char>((size_t)Ep * Gp * e);
+    char* W2xT = a.take<char>((size_t)Gp * Hp * e);
+    char* W2x = a.take<char>((size_t)Hp * Gp * e);
+    char* W2eT = a.take<char>((size_t)Gp * Ep * e);
+    char* W2e = a.take<char>((size_t)Ep * Gp * e);
+    char* W2hT = a.take<char>((size_t)Gp * Hp * e);
+    char* W2h = a.take<char>((size_t)Hp * Gp * e);
+    char* WoT = a.take<char>((size_t)Vp * Hp * e);
+    char* Wo = a.take<char>((size_t)Hp * Vp * e);
+    char* WembC = a.take<char>((size_t)Vp * Ep * e);
+    char* attrWT = a.take<char>((size_t)(Ap ? Ap : 1) * Dp * e);
+    float* be_p = a.take<float>(Ep);
+    float* b1_p = a.take<float>(Gp);
+    float* b2_p = a.take<float>(Gp);
+    float* bo_p = a.take<float>(Vp);
+    size_t copies_end = a.used;
+    float* Etab = a.take<float>((size_t)Vp * Gp);
+    assign(params, grads, m, v, sq, scal, WeT, W1xT, W1hT, W1h, W1x, W2xT, W2x, W2eT, W2e, W2hT, W2h, WoT, Wo, WembC, attrWT, be_p, b1_p, b2_p, bo_p, Etab,
+           copies_begin, copies_end);
+}
+
+extern "C" int s2vt_create(const s2vt_config* cfg, s2vt_handle** out) {
+    if (!cfg || !out) return S2VT_EINVAL;
+    if (cfg->dim_image <= 0 || cfg->word_dim <= 0 || cfg->lstm_dim <= 0 || cfg->n_words <= 2 || cfg->n_video_steps <= 0 || cfg->n_caption_steps <= 0)
+        return S2VT_EINVAL;
+    if (cfg->n_words > ROW_THREADS * ROW_MAXV4 * 4 || cfg->n_words > 65534) return S2VT_EINVAL;
+    if (cfg->precision != S2VT_PREC_BF16 && cfg->precision != S2VT_PREC_FP32) return S2VT_EINVAL;
+    s2vt_handle* h = new s2vt_handle();
+    h->cfg = *cfg;
+    if (!(h->cfg.dropout_keep > 0.f) || h->cfg.dropout_keep > 1.f) h->cfg.dropout_keep = 1.f;
+    h->D = cfg->dim_image; h->E = cfg->word_dim; h->H = cfg->lstm_dim; h->V = cfg->n_words;
+    h->Tv = cfg->n_video_steps; h->Tc = cfg->n_caption_steps; h->A = cfg->n_attributes > 0 ? cfg->n_attributes : 0;
+    h->T = h->Tv + h->Tc;
+    h->Dp = ru(h->D, S2VT_PAD); h->Ep = ru(h->E, S2VT_PAD); h->Hp = ru(h->H, S2VT_PAD); h->Vp = ru(h->V, S2VT_PAD);
+    h->Gp = 4 * h->Hp; h->Ap = h->A ? ru(h->A, S2VT_PAD) : 0;
+    h->esz = cfg->precision == S2VT_PREC_BF16 ? 2 : 4;
+    h->P = 0;
+    const int64_t E = h->E, H = h->H, V = h->V, D = h->D;
+    h->iWemb = 0; add_var(h, "Wemb", {}, V, E);
+    h->iWe = 1; add_var(h, "encode_image_W", {}, D, E);
+    h->ibe = 2; add_var(h, "encode_image_b", {}, E, 0);
+    h->iWo = 3; add_var(h, "embed_word_W", {}, H, V);
+    h->ibo = 4; add_var(h, "embed_word_b", {}, V, 0);
+    h->iW1 = 5; add_var(h, "s2vt/LSTM1/basic_lstm_cell/weights", {"s2vt/LSTM1/basic_lstm_cell/kernel", "s2vt/LSTM1/BasicLSTMCell/Linear/Matrix"}, E + H, 4 * H);
+    h->ib1 = 6; add_var(h, "s2vt/LSTM1/basic_lstm_cell/biases", {"s2vt/LSTM1/basic_lstm_cell/bias", "s2vt/LSTM1/BasicLSTMCell/Linear/Bias"}, 4 * H, 0);
+    h->iW2 = 7; add_var(h, "s2vt/LSTM2/basic_lstm_cell/weights", {"s2vt/LSTM2/basic_lstm_cell/kernel", "s2vt/LSTM2/BasicLSTMCell/Linear/Matrix"}, H + E + H, 4 * H);
+    h->ib2 = 8; add_var(h, "s2vt/LSTM2/basic_lstm_cell/biases", {"s2vt/LSTM2/basic_lstm_cell/bias", "s2vt/LSTM2/BasicLSTMCell/Linear/Bias"}, 4 * H, 0);
+    h->iAW = h->iAb = -1;
+    if (h->A) {
+        h->iAW = 9; add_var(h, "attr_W", {}, D, h->A);
+        h->iAb = 10; add_var(h, "attr_b", {}, h->A, 0);
+    }
+    Arena a(nullptr, 0);
+    layout_state(h, a, [](auto...) {});
+    h->state_bytes = a.used;
+    h->state = nullptr; h->ws = nullptr; h->ws_bytes = 0; h->bound = false; h->fresh = false;
+    *out = h;
+    return S2VT_OK;
+}
+
+extern "C" void s2vt_destroy(s2vt_handle* h) { delete h; }
+extern "C" const char* s2vt_last_error(const s2vt_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" size_t s2vt_num_params(const s2vt_handle* h) { return h->P; }
+extern "C" size_t s2vt_state_bytes(const s2vt_handle* h) { return h->state_bytes; }
+extern "C" float* s2vt_params(const s2vt_handle* h) { return h->params; }
+extern "C" float* s2vt_grads(const s2vt_handle* h) { return h->grads; }
+extern "C" float* s2vt_adam_m(const s2vt_handle* h) { return h->adam_m; }
+extern "C" float* s2vt_adam_v(const s2vt_handle* h) { return h->adam_v; }
+extern "C" int s2vt_num_variables(const s2vt_handle* h) { return (int)h->vars.size(); }
+extern "C" int s2vt_variable_info(const s2vt_handle* h, int index, const char** tf_name, int64_t* offset, int64_t shape[2], int* ndim) {
+    if (index < 0 || index >= (int)h->vars.size()) return S2VT_EINVAL;
+    const Var& v = h->vars[index];
+    if (tf_name) *tf_name = v.name.c_str();
+    if (offset) *offset = (int64_t)v.off;
+    if (shape) { shape[0] = v.rows; shape[1] = v.cols; }
+    if (ndim) *ndim = v.cols ? 2 : 1;
+    return S2VT_OK;
+}
+
+extern "C" int s2vt_bind(s2vt_handle* h, void* state, size_t state_bytes, void* workspace, size_t workspace_bytes) {
+    if (!h || !state) return S2VT_EINVAL;
+    if (state_bytes < h->state_bytes) return h->fail(S2VT_ENOSPACE, "state block %zu < %zu bytes", state_bytes, h->state_bytes);
+    if (((uintptr_t)state & 255) || ((uintptr_t)workspace & 255)) return h->fail(S2VT_EINVAL, "blocks must be 256-byte aligned");
+    Arena a(state, state_bytes);
+    layout_state(h, a, [&](float* params, float* grads, float* m, float* v, double* sq, float* scal, char* WeT, char* W1xT, char* W1hT, char* W1h, char* W1x,
+                           char* W2xT, char* W2x, char* W2eT, char* W2e, char* W2hT, char* W2h, char* WoT, char* Wo, char* WembC, char* attrWT, float* be_p,
+                           float* b1_p, float* b2_p, float* bo_p, float* Etab, size_t, size_t) {
+        h->params = params; h->grads = grads; h->adam_m = m; h->adam_v = v; h->sq = sq; h->scal = scal;
+        h->WeT = WeT; h->W1xT = W1xT; h->W1hT = W1hT; h->W1h = W1h; h->W1x = W1x; h->W2xT = W2xT; h->W2x = W2x; h->W2eT = W2eT; h->W2e = W2e;
+        h->W2hT = W2hT; h->W2h = W2h; h->WoT = WoT; h->Wo = Wo; h->WembC = WembC; h->attrWT = attrWT;
+        h->be_p = be_p; h->b1_p = b1_p; h->b2_p = b2_p; h->bo_p = bo_p; h->Etab = Etab;
+    });
+    h->state = (char*)state;
+    h->ws = (char*)workspace; h->ws_bytes = workspace_bytes;
+    h->bound = true; h->fresh = false;
+    return S2VT_OK;
+}
+
+extern "C" int s2vt_load_param(s2vt_handle* h, const char* tf_name, const float* src_host, const int64_t* shape, int ndim, s2vt_stream st) {
+    if (!h || !h->bound) return S2VT_ESTATE;
+    for (const Var& v : h->vars) {
+        bool match = v.name == tf_name;
+        for (const auto& al : v.aliases) match |= (al == tf_name);
+        if (!match) continue;
+        int vnd = v.cols ? 2 : 1;
+        if (ndim != vnd || shape[0] != v.rows || (vnd == 2 && shape[1] != v.cols)) return h->fail(S2VT_ESHAPE, "shape mismatch for %s", tf_name);
+        CUDA_TRY(h, cudaMemcpyAsync(h->params + v.off, src_host, v.count() * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)st));
+        h->fresh = false;
+        return S2VT_OK;
+    }
+    return h->fail(S2VT_ENOTFOUND, "no variable named %s", tf_name);
+}
+
+// =================================================================================================================
+// refresh: fp32 master -> compute copies
+// =================================================================================================================
+template <typename T>
+static int pack(s2vt_handle* h, cudaStream_t st, const float* src, int lds, int R, int C, void* dst, int ldd, int gate_h, int transpose) {
+    dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+    pack_matrix_kernel<T><<<grid, block, 0, st>>>(src, lds, R, C, (T*)dst, ldd, gate_h, transpose);
+    KCHECK(h);
+    return 0;
+}
+
+template <typename T, class Cfg, class Epi>
+static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const typename Epi::Params& ep) {
+    CUDA_TRY(h, (launch_gemm<T, Cfg, Epi>(st, (const T*)A, lda, (const T*)B, ldb, M, N, K, ep)));
+    return 0;
+}
+#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+template <typename T>
+static int refresh_impl(s2vt_handle* h, cudaStream_t st) {
+    const int E = h->E, H = h->H, V = h->V, D = h->D, Dp = h->Dp, Ep = h->Ep, Hp = h->Hp, Vp = h->Vp, Gp = h->Gp;
+    // zero all compute copies (pads must be zero)
+    size_t begin = 0, end = 0;
+    {
+        Arena a(nullptr, 0);
+        layout_state(h, a, [&](float*, float*, float*, float*, double*, float*, char*, char*, char*, char*, char*, char*, char*, char*, char*, char*, char*,
+                               char*, char*, char*, char*, float*, float*, float*, float*, float*, size_t b, size_t e) { begin = b; end = e; });
+    }
+    CUDA_TRY(h, cudaMemsetAsync(h->state + begin, 0, end - begin, st));
+    const float* W1 = h->P_(h->iW1); const float* W2 = h->P_(h->iW2);
+    const int G = 4 * H;
+    TRY(pack<T>(h, st, h->P_(h->iWe), E, D, E, h->WeT, Dp, 0, 1));                         // WeT [Ep, Dp]
+    TRY(pack<T>(h, st, W1, G, E, G, h->W1xT, Ep, H, 1));                                   // W1xT [Gp, Ep]
+    TRY(pack<T>(h, st, W1, G, E, G, h->W1x, Gp, H, 0));                                    // W1x  [Ep, Gp]
+    TRY(pack<T>(h, st, W1 + (size_t)E * G, G, H, G, h->W1hT, Hp, H, 1));                   // W1hT [Gp, Hp]
+    TRY(pack<T>(h, st, W1 + (size_t)E * G, G, H, G, h->W1h, Gp, H, 0));                    // W1h  [Hp, Gp]
+    TRY(pack<T>(h, st, W2, G, H, G, h->W2xT, Hp, H, 1));                                   // rows [0,H): out1
+    TRY(pack<T>(h, st, W2, G, H, G, h->W2x, Gp, H, 0));
+    TRY(pack<T>(h, st, W2 + (size_t)H * G, G, E, G, h->W2eT, Ep, H, 1));                   // rows [H,H+E): word embedding
+    TRY(pack<T>(h, st, W2 + (size_t)H * G, G, E, G, h->W2e, Gp, H, 0));
+    TRY(pack<T>(h, st, W2 + (size_t)(H + E) * G, G, H, G, h->W2hT, Hp, H, 1));             // rows [H+E, 2H+E): h2
+    TRY(pack<T>(h, st, W2 + (size_t)(H + E) * G, G, H, G, h->W2h, Gp, H, 0));
+    TRY(pack<T>(h, st, h->P_(h->iWo), V, H, V, h->WoT, Hp, 0, 1));                         // WoT [Vp, Hp]
+    TRY(pack<T>(h, st, h->P_(h->iWo), V, H, V, h->Wo, Vp, 0, 0));                          // Wo  [Hp, Vp]
+    TRY(pack<T>(h, st, h->P_(h->iWemb), E, V, E, h->WembC, Ep, 0, 0));                     // Wemb [Vp, Ep]
+    if (h->A) TRY(pack<T>(h, st, h->P_(h->iAW), h->A, D, h->A, h->attrWT, Dp, 0, 1));      // attrWT [Ap, Dp]
+    pack_vector_kernel<<<(E + 255) / 256, 256, 0, st>>>(h->P_(h->ibe), E, h->be_p, 0); KCHECK(h);
+    pack_vector_kernel<<<(G + 255) / 256, 256, 0, st>>>(h->P_(h->ib1), G, h->b1_p, H); KCHECK(h);
+    pack_vector_kernel<<<(G + 255) / 256, 256, 0, st>>>(h->P_(h->ib2), G, h->b2_p, H); KCHECK(h);
+    pack_vector_kernel<<<(V + 255) / 256, 256, 0, st>>>(h->P_(h->ibo), V, h->bo_p, 0); KCHECK(h);
+    // Etab[v, :] = Wemb[v, :] . W2[emb rows]  (packed gate order) -- the word-embedding contribution to LSTM2's gates
+    typename EpiStore<T>::Params ep = {h->Etab, nullptr, Gp, nullptr, Vp, 0};
+    TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, h->WembC, Ep, h->W2eT, Ep, Vp, Gp, Ep, ep)));
+    h->fresh = true;
+    return 0;
+}
+
+extern "C" int s2vt_refresh(s2vt_handle* h, s2vt_stream st) {
+    if (!h || !h->bound) return S2VT_ESTATE;
+    return h->cfg.precision == S2VT_PREC_BF16 ? refresh_impl<bf16>(h, (cudaStream_t)st) : refresh_impl<float>(h, (cudaStream_t)st);
+}
+
+// =================================================================================================================
+// forward plans
+// =================================================================================================================
+template <typename T>
+struct Front {   // per-video part: frame projection + LSTM1 over all T steps
+    T* Xc; T* img; float* G1x; T* h1_all; float* c1_all; float* gates1;
+};
+template <typename T>
+static void plan_front(const s2vt_handle* h, Arena& a, int B, bool train, Front<T>& f) {
+    f.Xc = a.take<T>((size_t)h->Tv * B * h->Dp);
+    f.img = a.take<T>((size_t)h->Tv * B * h->Ep);
+    f.G1x = a.take<float>((size_t)h->Tv * B * h->Gp);
+    f.h1_all = a.take<T>((size_t)(h->T + 1) * B * h->Hp);
+    f.c1_all = a.take<float>((size_t)(h->T + 1) * B * h->Hp);
+    f.gates1 = train ? a.take<float>((size_t)h->T * B * h->Gp) : nullptr;
+}
+
+template <typename T>
+static int run_front(s2vt_handle* h, cudaStream_t st, const float* video, int B, Front<T>& f) {
+    const int Tv = h->Tv, T_ = h->T, Dp = h->Dp, Ep = h->Ep, Hp = h->Hp, Gp = h->Gp;
+    convert_video_kernel<T><<<Tv * B, 256, 0, st>>>(video, nullptr, B, Tv, h->D, Dp, f.Xc); KCHECK(h);
+    {   // img = Xc . We + be   (:107-111 tf.nn.xw_plus_b)
+        typename EpiStore<T>::Params ep = {nullptr, f.img, Ep, h->be_p, Tv * B, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, f.Xc, Dp, h->WeT, Dp, Tv * B, Ep, Dp, ep)));
+    }
+    {   // G1x = img . W1[x rows]  (the input half of LSTM1's concat([x, h]) W, all frames at once)
+        typename EpiStore<T>::Params ep = {f.G1x, nullptr, Gp, nullptr, Tv * B, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, f.img, Ep, h->W1xT, Ep, Tv * B, Gp, Ep, ep)));
+    }
+    CUDA_TRY(h, cudaMemsetAsync(f.h1_all, 0, (size_t)B * Hp * sizeof(T), st));
+    CUDA_TRY(h, cudaMemsetAsync(f.c1_all, 0, (size_t)B * Hp * sizeof(float), st));
+    for (int t = 0; t < T_; ++t) {   // :128-129 / :148-149 LSTM1; decoder steps get `padding` -> no input term (Q8)
+        typename EpiLstmFwd<T>::Params ep;
+        memset(&ep, 0, sizeof ep);
+        ep.M = B; ep.Hp = Hp; ep.bias = h->b1_p;
+        ep.add0 = t < Tv ? f.G1x + (size_t)t * B * Gp : nullptr;
+        ep.c_prev = f.c1_all + (size_t)t * B * Hp; ep.c_out = f.c1_all + (size_t)(t + 1) * B * Hp;
+        ep.h_out = f.h1_all + (size_t)(t + 1) * B * Hp;
+        ep.gates_out = f.gates1 ? f.gates1 + (size_t)t * B * Gp : nullptr;
+        ep.keep = 1.f;
+        TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, f.h1_all + (size_t)t * B * Hp, Hp, h->W1hT, Hp, B, Gp, Hp, ep)));
+    }
+    return 0;
+}
+
+// ---- rollout (greedy + K samples), also the front half of beam search --------------------------------------------
+template <typename T>
+struct Roll {
+    Front<T> f; float* G2x; T* h2e[2]; float* c2e[2]; T* h2r[2]; float* c2r[2]; float* logits; int* tok[2]; int* ids;
+};
+template <typename T>
+static void plan_roll(const s2vt_handle* h, Arena& a, int B, int R, Roll<T>& r) {
+    plan_front<T>(h, a, B, false, r.f);
+    r.G2x = a.take<float>((size_t)h->T * B * h->Gp);
+    for (int i = 0; i < 2; ++i) { r.h2e[i] = a.take<T>((size_t)B * h->Hp); r.c2e[i] = a.take<float>((size_t)B * h->Hp); }
+    for (int i = 0; i < 2; ++i) { r.h2r[i] = a.take<T>((size_t)R * h->Hp); r.c2r[i] = a.take<float>((size_t)R * h->Hp); }
+    r.logits = a.take<float>((size_t)R * h->Vp);
+    r.tok[0] = a.take<int>(R); r.tok[1] = a.take<int>(R);
+    r.ids = a.take<int>((size_t)R * h->Tc);
+}
+
+// frames -> (LSTM1 all steps, G2x all steps, LSTM2 encoder steps).  Leaves the encoder state in h2e[Tv&1], c2e[Tv&1].
+template <typename T>
+static int run_encoder(s2vt_handle* h, cudaStream_t st, const float* video, int B, Roll<T>& r) {
+    const int Tv = h->Tv, T_ = h->T, Hp = h->Hp, Gp = h->Gp;
+    TRY(run_front<T>(h, st, video, B, r.f));
+    {   // G2x = h1 . W2[out1 rows] for every step (bare cells: no dropout in the samplers, Q2)
+        typename EpiStore<T>::Params ep = {r.G2x, nullptr, Gp, nullptr, T_ * B, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, r.f.h1_all + (size_t)B * Hp, Hp, h->W2xT, Hp, T_ * B, Gp, Hp, ep)));
+    }
+    CUDA_TRY(h, cudaMemsetAsync(r.h2e[0], 0, (size_t)B * Hp * sizeof(T), st));
+    CUDA_TRY(h, cudaMemsetAsync(r.c2e[0], 0, (size_t)B * Hp * sizeof(float), st));
+    for (int t = 0; t < Tv; ++t) {   // :131-132 LSTM2 on concat([output1, padding]) -> the embedding rows see zeros (Q8)
+        typename EpiLstmFwd<T>::Params ep;
+        memset(&ep, 0, sizeof ep);
+        ep.M = B; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp;
+        ep.c_prev = r.c2e[t & 1]; ep.c_out = r.c2e[(t + 1) & 1]; ep.h_out = r.h2e[(t + 1) & 1]; ep.keep = 1.f;
+        TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, r.h2e[t & 1], Hp, h->W2hT, Hp, B, Gp, Hp, ep)));
+    }
+    return 0;
+}
+
+template <typename T>
+static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B, int K, uint64_t seed, uint32_t row_base, int32_t* sampled_out,
+                        int32_t* greedy_out) {
+    const int Tv = h->Tv, Tc = h->Tc, Hp = h->Hp, Gp = h->Gp, Vp = h->Vp;
+    const bool want_greedy = greedy_out != nullptr;
+    const int R = (K + (want_greedy ? 1 : 0)) * B;
+    if (R <= 0) return h->fail(S2VT_EINVAL, "nothing to decode");
+    Arena a(h->ws, h->ws_bytes);
+    Roll<T> r;
+    plan_roll<T>(h, a, B, R, r);
+    if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small: need %zu bytes", a.used);
+    TRY(run_encoder<T>(h, st, video, B, r));
+    tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2e[Tv & 1], B, R, Hp, r.h2r[0]); KCHECK(h);
+    tile_rows_kernel<float><<<R, 256, 0, st>>>(r.c2e[Tv & 1], B, R, Hp, r.c2r[0]); KCHECK(h);
+    fill_int_kernel<<<(R + 255) / 256, 256, 0, st>>>(r.tok[0], R, 1); KCHECK(h);   // <bos> = 1 (:321-323)
+    for (int i = 0; i < Tc; ++i) {
+        const int t = Tv + i;
+        typename EpiLstmFwd<T>::Params ep;
+        memset(&ep, 0, sizeof ep);
+        ep.M = R; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp; ep.add0_mod = B;
+        ep.add1 = h->Etab; ep.tok = r.tok[i & 1];
+        ep.c_prev = r.c2r[i & 1]; ep.c_out = r.c2r[(i + 1) & 1]; ep.h_out = r.h2r[(i + 1) & 1]; ep.keep = 1.f;
+        TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, r.h2r[i & 1], Hp, h->W2hT, Hp, R, Gp, Hp, ep)));
+        typename EpiStore<T>::Params el = {r.logits, nullptr, Vp, h->bo_p, R, 0};   // :332 logit_words
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, r.h2r[(i + 1) & 1], Hp, h->WoT, Hp, R, Vp, Hp, el)));
+        sample_rows_kernel<<<R, ROW_THREADS, 0, st>>>(r.logits, Vp, h->V, K * B, seed, (uint32_t)i, row_base, r.tok[(i + 1) & 1], r.ids, Tc);
+        KCHECK(h);
+    }
+    if (K > 0 && sampled_out)
+        CUDA_TRY(h, cudaMemcpyAsync(sampled_out, r.ids, (size_t)K * B * Tc * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (want_greedy)
+        CUDA_TRY(h, cudaMemcpyAsync(greedy_out, r.ids + (size_t)K * B * Tc, (size_t)B * Tc * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+static int check_ready(s2vt_handle* h) {
+    if (!h) return S2VT_EINVAL;
+    if (!h->bound) return h->fail(S2VT_ESTATE, "s2vt_bind has not been called");
+    if (!h->fresh) return h->fail(S2VT_ESTATE, "parameters changed: call s2vt_refresh first");
+    return 0;
+}
+
+extern "C" int s2vt_rollout(s2vt_handle* h, const float* video, int B, int K, uint64_t seed, uint32_t row_base, int32_t* sampled_out, int32_t* greedy_out,
+                            s2vt_stream st) {
+    TRY(check_ready(h));
+    if (B <= 0 || K < 0 || !video) return h->fail(S2VT_EINVAL, "bad rollout arguments");
+    return h->cfg.precision == S2VT_PREC_BF16 ? rollout_impl<bf16>(h, (cudaStream_t)st, video, B, K, seed, row_base, sampled_out, greedy_out)
+                                              : rollout_impl<float>(h, (cudaStream_t)st, video, B, K, seed, row_base, sampled_out, greedy_out);
+}
+extern "C" int s2vt_greedy(s2vt_handle* h, const float* video, int B, int32_t* ids_out, s2vt_stream st) {
+    if (!ids_out) return S2VT_EINVAL;
+    return s2vt_rollout(h, video, B, 0, 0, 0, nullptr, ids_out, st);
+}
+extern "C" int s2vt_caption_masks(s2vt_handle* h, const int32_t* ids, int N, float* mask_out, int32_t* lengths_out, s2vt_stream st) {
+    if (!h || N <= 0) return S2VT_EINVAL;
+    caption_mask_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)st>>>(ids, N, h->Tc, mask_out, lengths_out);
+    KCHECK(h);
+    return 0;
+}
+
+// =================================================================================================================
+// teacher-forced forward / backward
+// =================================================================================================================
+template <typename T>
+struct Train {
+    Front<T> f;
+    T* out1d; float* G2x; T* h2_all; float* c2_all; float* gates2; T* out2d; float* logits;
+    int *prev_tok, *target; float *ca, *cb, *cc, *logp, *sumlsm;
+    // backward
+    T* dlogits; float* dout2; T* dG2; float* dc2; float* dout1; float* dEmb; float* dh1; T* dG1; float* dc1; float* dimgF; T* dimgT_src;
+    T *tA, *tB;   // transposed operand scratch (largest: [Vp, Mp])
+    T* emb;
+};
+
+template <typename T>
+static void plan_train(const s2vt_handle* h, Arena& a, int B, int N, bool backward, bool want_logits_only, Train<T>& p) {
+    const int T_ = h->T, Tv = h->Tv, Tc = h->Tc, Hp = h->Hp, Gp = h->Gp, Vp = h->Vp, Ep = h->Ep, Dp = h->Dp;
+    plan_front<T>(h, a, B, backward, p.f);
+    p.out1d = a.take<T>((size_t)T_ * N * Hp);
+    p.G2x = a.take<float>((size_t)T_ * N * Gp);
+    p.h2_all = a.take<T>((size_t)(T_ + 1) * N * Hp);
+    p.c2_all = a.take<float>((size_t)(T_ + 1) * N * Hp);
+    p.gates2 = backward ? a.take<float>((size_t)T_ * N * Gp) : nullptr;
+    p.out2d = a.take<T>((size_t)Tc * N * Hp);
+    p.logits = a.take<float>((size_t)Tc * N * Vp);
+    p.prev_tok = a.take<int>((size_t)Tc * N); p.target = a.take<int>((size_t)Tc * N);
+    p.ca = a.take<float>((size_t)Tc * N); p.cb = a.take<float>((size_t)Tc * N); p.cc = a.take<float>((size_t)Tc * N);
+    p.logp = a.take<float>((size_t)Tc * N); p.sumlsm = a.take<float>((size_t)Tc * N);
+    if (!backward) return;
+    const size_t MpD = ru(Tc * N, S2VT_PAD), Mp2 = ru(T_ * N, S2VT_PAD), Mp1 = ru(T_ * B, S2VT_PAD);
+    p.dlogits = a.take<T>((size_t)Tc * N * Vp);
+    p.dout2 = a.take<float>((size_t)Tc * N * Hp);
+    p.dG2 = a.take<T>((size_t)T_ * N * Gp);
+    p.dc2 = a.take<float>((size_t)N * Hp);
+    p.dout1 = a.take<float>((size_t)T_ * N * Hp);
+    p.dEmb = a.take<float>((size_t)Tc * N * Ep);
+    p.dh1 = a.take<float>((size_t)T_ * B * Hp);
+    p.dG1 = a.take<T>((size_t)T_ * B * Gp);
+    p.dc1 = a.take<float>((size_t)B * Hp);
+    p.dimgF = a.take<float>((size_t)Tv * B * Ep);
+    p.dimgT_src = a.take<T>((size_t)Tv * B * Ep);
+    p.emb = a.take<T>((size_t)Tc * N * Ep);
+    size_t ta = (size_t)Hp * Mp2;                       // activations^T : at most [max(Hp,Ep,Dp), Mp2]
+    if ((size_t)Dp * Mp1 > ta) ta = (size_t)Dp * Mp1;
+    if ((size_t)Ep * MpD > ta) ta = (size_t)Ep * MpD;
+    size_t tb = (size_t)Vp * MpD;                       // gradients^T  : [Vp, MpD] or [Gp, Mp2]
+    if ((size_t)Gp * Mp2 > tb) tb = (size_t)Gp * Mp2;
+    p.tA = a.take<T>(ta + 256);
+    p.tB = a.take<T>(tb + 256);
+}
+
+template <typename T>
+static int transpose(s2vt_handle* h, cudaStream_t st, const T* src, int lds, int R, int C, T* dst, int ldd, int rows_dst_padded) {
+    // zero the destination (pads along the contraction dimension must be zero), then transpose the valid part
+    CUDA_TRY(h, cudaMemsetAsync(dst, 0, (size_t)rows_dst_padded * ldd * sizeof(T), st));
+    dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+    transpose_kernel<T><<<grid, block, 0, st>>>(src, lds, R, C, dst, ldd);
+    KCHECK(h);
+    return 0;
+}
+
+// mode 0: REINFORCE (needs rewards/base), mode 1: XE, mode 2: forward only
+template <typename T>
+static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* video, int B, const int32_t* captions, const float* mask, const float* rewards,
+                      const float* base_line, int N, float norm, float grad_scale, int accumulate, float ls, float decay, uint64_t drop_seed,
+                      uint32_t row_base, float* loss_out, float* logp_out, float* logits_out) {
+    const int Tv = h->Tv, Tc = h->Tc, T_ = h->T, Hp = h->Hp, Gp = h->Gp, Vp = h->Vp, Ep = h->Ep, Dp = h->Dp;
+    const int H = h->H, E = h->E, V = h->V, D = h->D, G = 4 * h->H;
+    const bool backward = mode != 2;
+    const float keep = (drop_seed == 0) ? 1.f : h->cfg.dropout_keep;
+    if (N % B != 0) return h->fail(S2VT_EINVAL, "N (%d) must be a multiple of B (%d): row n uses video n %% B", N, B);
+    Arena a(h->ws, h->ws_bytes);
+    Train<T> p;
+    plan_train<T>(h, a, B, N, backward, false, p);
+    if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small: need %zu bytes", a.used);
+
+    // ---------------- forward ----------------
+    TRY(run_front<T>(h, st, video, B, p.f));
+    expand_dropout_kernel<T><<<T_ * N, 256, 0, st>>>(p.f.h1_all + (size_t)B * Hp, B, N, Hp, H, p.out1d, drop_seed, S2VT_STREAM_DROP1, row_base, keep);
+    KCHECK(h);
+    {
+        typename EpiStore<T>::Params ep = {p.G2x, nullptr, Gp, nullptr, T_ * N, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.out1d, Hp, h->W2xT, Hp, T_ * N, Gp, Hp, ep)));
+    }
+    caption_tables_kernel<<<(Tc * N + 255) / 256, 256, 0, st>>>(captions, N, Tc, p.prev_tok, p.target); KCHECK(h);
+    CUDA_TRY(h, cudaMemsetAsync(p.h2_all, 0, (size_t)N * Hp * sizeof(T), st));
+    CUDA_TRY(h, cudaMemsetAsync(p.c2_all, 0, (size_t)N * Hp * sizeof(float), st));
+    for (int t = 0; t < T_; ++t) {
+        typename EpiLstmFwd<T>::Params ep;
+        memset(&ep, 0, sizeof ep);
+        ep.M = N; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = p.G2x + (size_t)t * N * Gp;
+        if (t >= Tv) { ep.add1 = h->Etab; ep.tok = p.prev_tok + (size_t)(t - Tv) * N; ep.hdrop_out = p.out2d + (size_t)(t - Tv) * N * Hp; }
+        ep.c_prev = p.c2_all + (size_t)t * N * Hp; ep.c_out = p.c2_all + (size_t)(t + 1) * N * Hp;
+        ep.h_out = p.h2_all + (size_t)(t + 1) * N * Hp;
+        ep.gates_out = p.gates2 ? p.gates2 + (size_t)t * N * Gp : nullptr;
+        ep.seed = drop_seed; ep.stream = S2VT_STREAM_DROP2; ep.step = (uint32_t)t; ep.row_base = row_base; ep.keep = keep;
+        TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, p.h2_all + (size_t)t * N * Hp, Hp, h->W2hT, Hp, N, Gp, Hp, ep)));
+    }
+    {   // logits for all decode steps at once (:163 / :286)
+        typename EpiStore<T>::Params ep = {p.logits, nullptr, Vp, h->bo_p, Tc * N, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.out2d, Hp, h->WoT, Hp, Tc * N, Vp, Hp, ep)));
+    }
+    if (logits_out)
+        CUDA_TRY(h, cudaMemcpy2DAsync(logits_out, (size_t)V * sizeof(float), p.logits, (size_t)Vp * sizeof(float), (size_t)V * sizeof(float), (size_t)Tc * N,
+                                      cudaMemcpyDeviceToDevice, st));
+    if (!backward) {
+        softmax_rows_kernel<T><<<Tc * N, ROW_THREADS, 0, st>>>(p.logits, Vp, V, Vp, p.target, nullptr, nullptr, nullptr, p.logp, p.sumlsm, (T*)nullptr, logp_out,
+                                                               N, Tc);
+        KCHECK(h);
+        return 0;
+    }
+    // ---------------- loss coefficients ----------------
+    float* nrm = h->scal;   // scal[0] = norm
+    if (norm > 0.f) { CUDA_TRY(h, cudaMemcpyAsync(nrm, &norm, sizeof(float), cudaMemcpyHostToDevice, st)); }
+    else { sum_kernel<<<1, 256, 0, st>>>(mask, N * Tc, nrm); KCHECK(h); }
+    if (!accumulate) CUDA_TRY(h, cudaMemsetAsync(h->grads, 0, (h->P + 8) * sizeof(float), st));
+    loss_coef_kernel<<<(Tc * N + 255) / 256, 256, 0, st>>>(mode, mask, rewards, base_line, N, Tc, nrm, grad_scale, ls, V, p.ca, p.cb, p.cc); KCHECK(h);
+    softmax_rows_kernel<T><<<Tc * N, ROW_THREADS, 0, st>>>(p.logits, Vp, V, Vp, p.target, p.ca, p.cb, p.cc, p.logp, p.sumlsm, p.dlogits, logp_out, N, Tc);
+    KCHECK(h);
+    loss_reduce_kernel<<<1, 256, 0, st>>>(mode, p.logp, p.sumlsm, mask, rewards, base_line, N, Tc, nrm, ls, V, h->scal + 4, nullptr); KCHECK(h);
+    if (loss_out) {
+        if (accumulate) { add_scaled_scalar_kernel<<<1, 1, 0, st>>>(loss_out, h->scal + 4, grad_scale); KCHECK(h); }
+        else CUDA_TRY(h, cudaMemcpyAsync(loss_out, h->scal + 4, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    add_scaled_scalar_kernel<<<1, 1, 0, st>>>(h->grads + h->P + 1, h->scal + 4, grad_scale); KCHECK(h);   // aux[1] = loss (summed by the DP allreduce)
+
+    // ---------------- backward ----------------
+    const int MD = Tc * N, M2 = T_ * N, M1 = T_ * B, ME = Tv * B;
+    const int MpD = ru(MD, S2VT_PAD), Mp2 = ru(M2, S2VT_PAD), Mp1 = ru(M1, S2VT_PAD), MpE = ru(ME, S2VT_PAD);
+    {   // dout2 = dlogits . embed_word_W^T
+        typename EpiStore<T>::Params ep = {p.dout2, nullptr, Hp, nullptr, MD, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dlogits, Vp, h->Wo, Vp, MD, Hp, Vp, ep)));
+    }
+    {   // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums
+        TRY(transpose<T>(h, st, p.out2d, Hp, MD, Hp, p.tA, MpD, Hp));
+        TRY(transpose<T>(h, st, p.dlogits, Vp, MD, Vp, p.tB, MpD, Vp));
+        EpiGradStore::Params ep = {h->G_(h->iWo), V, H, V, 0, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Hp, Vp, MpD, ep)));
+        rowsum_grad_kernel<T><<<Vp, 256, 0, st>>>(p.tB, MpD, MD, V, 0, h->G_(h->ibo)); KCHECK(h);
+    }
+    // LSTM2 BPTT
+    CUDA_TRY(h, cudaMemsetAsync(p.dc2, 0, (size_t)N * Hp * sizeof(float), st));
+    for (int t = T_ - 1; t >= 0; --t) {
+        LstmBwdArgs b;
+        memset(&b, 0, sizeof b);
+        b.M = N; b.Hp = Hp;
+        b.dh_ext = t >= Tv ? p.dout2 + (size_t)(t - Tv) * N * Hp : nullptr;
+        b.gates = p.gates2 + (size_t)t * N * Gp; b.c_prev = p.c2_all + (size_t)t * N * Hp; b.c_new = p.c2_all + (size_t)(t + 1) * N * Hp;
+        b.dc = p.dc2; b.seed = drop_seed; b.stream = S2VT_STREAM_DROP2; b.step = (uint32_t)t; b.row_base = row_base; b.keep = keep;
+        T* dg = p.dG2 + (size_t)t * N * Gp;
+        if (t == T_ - 1) {
+            lstm_bwd_elem_kernel<T><<<(N * Hp + 255) / 256, 256, 0, st>>>(b, dg); KCHECK(h);
+        } else {
+            typename EpiLstmBwd<T>::Params ep = {b, dg};
+            TRY((gemm<T, CfgStep, EpiLstmBwd<T>>(h, st, p.dG2 + (size_t)(t + 1) * N * Gp, Gp, h->W2h, Gp, N, Hp, Gp, ep)));
+        }
+    }
+    {   // gradient flowing into LSTM1's (dropped) output and into the word embeddings
+        typename EpiStore<T>::Params ep = {p.dout1, nullptr, Hp, nullptr, M2, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2, Gp, h->W2x, Gp, M2, Hp, Gp, ep)));
+        typename EpiStore<T>::Params ee = {p.dEmb, nullptr, Ep, nullptr, MD, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2 + (size_t)Tv * N * Gp, Gp, h->W2e, Gp, MD, Ep, Gp, ee)));
+        scatter_emb_grad_kernel<<<MD, 128, 0, st>>>(p.dEmb, Ep, p.prev_tok, MD, E, h->G_(h->iWemb), h->grads + h->P); KCHECK(h);   // aux[0] = slice square norm (R6)
+    }
+    {   // LSTM2 kernel / bias gradients: [out1 ; emb ; h2]^T . dG2
+        float* gW2 = h->G_(h->iW2);
+        TRY(transpose<T>(h, st, p.dG2, Gp, M2, Gp, p.tB, Mp2, Gp));
+        rowsum_grad_kernel<T><<<Gp, 256, 0, st>>>(p.tB, Mp2, M2, 0, H, h->G_(h->ib2)); KCHECK(h);
+        TRY(transpose<T>(h, st, p.out1d, Hp, M2, Hp, p.tA, Mp2, Hp));
+        EpiGradStore::Params e1 = {gW2, G, H, G, H, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp2, p.tB, Mp2, Hp, Gp, Mp2, e1)));
+        TRY(transpose<T>(h, st, p.h2_all, Hp, M2, Hp, p.tA, Mp2, Hp));       // h2 before step t = h2_all[t]
+        EpiGradStore::Params e3 = {gW2 + (size_t)(H + E) * G, G, H, G, H, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp2, p.tB, Mp2, Hp, Gp, Mp2, e3)));
+        // embedding rows: decode steps only
+        TRY(transpose<T>(h, st, p.dG2 + (size_t)Tv * N * Gp, Gp, MD, Gp, p.tB, MpD, Gp));
+        gather_rows_kernel<T><<<MD, 128, 0, st>>>((const T*)h->WembC, Ep, p.prev_tok, MD, p.emb); KCHECK(h);
+        TRY(transpose<T>(h, st, p.emb, Ep, MD, Ep, p.tA, MpD, Ep));
+        EpiGradStore::Params e2 = {gW2 + (size_t)H * G, G, E, G, H, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Ep, Gp, MpD, e2)));
+    }
+    // LSTM1 BPTT over the B shared rows
+    reduce_dropout_kernel<<<M1, 256, 0, st>>>(p.dout1, B, N, Hp, p.dh1, drop_seed, S2VT_STREAM_DROP1, row_base, keep); KCHECK(h);
+    CUDA_TRY(h, cudaMemsetAsync(p.dc1, 0, (size_t)B * Hp * sizeof(float), st));
+    for (int t = T_ - 1; t >= 0; --t) {
+        LstmBwdArgs b;
+        memset(&b, 0, sizeof b);
+        b.M = B; b.Hp = Hp; b.dh_ext = p.dh1 + (size_t)t * B * Hp;
+        b.gates = p.f.gates1 + (size_t)t * B * Gp; b.c_prev = p.f.c1_all + (size_t)t * B * Hp; b.c_new = p.f.c1_all + (size_t)(t + 1) * B * Hp;
+        b.dc = p.dc1; b.keep = 1.f;
+        T* dg = p.dG1 + (size_t)t * B * Gp;
+        if (t == T_ - 1) {
+            lstm_bwd_elem_kernel<T><<<(B * Hp + 255) / 256, 256, 0, st>>>(b, dg); KCHECK(h);
+        } else {
+            typename EpiLstmBwd<T>::Params ep = {b, dg};
+            TRY((gemm<T, CfgStep, EpiLstmBwd<T>>(h, st, p.dG1 + (size_t)(t + 1) * B * Gp, Gp, h->W1h, Gp, B, Hp, Gp, ep)));
+        }
+    }
+    {   // LSTM1 kernel / bias gradients
+        float* gW1 = h->G_(h->iW1);
+        TRY(transpose<T>(h, st, p.dG1, Gp, M1, Gp, p.tB, Mp1, Gp));
+        rowsum_grad_kernel<T><<<Gp, 256, 0, st>>>(p.tB, Mp1, M1, 0, H, h->G_(h->ib1)); KCHECK(h);
+        TRY(transpose<T>(h, st, p.f.h1_all, Hp, M1, Hp, p.tA, Mp1, Hp));
+        EpiGradStore::Params e2 = {gW1 + (size_t)E * G, G, H, G, H, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp1, p.tB, Mp1, Hp, Gp, Mp1, e2)));
+        // frame-embedding rows: encoder steps only
+        TRY(transpose<T>(h, st, p.dG1, Gp, ME, Gp, p.tB, MpE, Gp));
+        TRY(transpose<T>(h, st, p.f.img, Ep, ME, Ep, p.tA, MpE, Ep));
+        EpiGradStore::Params e1 = {gW1, G, E, G, H, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpE, p.tB, MpE, Ep, Gp, MpE, e1)));
+    }
+    {   // frame projection gradients: dimg = dG1[enc] . W1[x rows]^T ; dWe = X^T . dimg ; dbe = column sums
+        typename EpiStore<T>::Params ep = {p.dimgF, p.dimgT_src, Ep, nullptr, ME, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG1, Gp, h->W1x, Gp, ME, Ep, Gp, ep)));
+        TRY(transpose<T>(h, st, p.dimgT_src, Ep, ME, Ep, p.tB, MpE, Ep));
+        rowsum_grad_kernel<T><<<Ep, 256, 0, st>>>(p.tB, MpE, ME, E, 0, h->G_(h->ibe)); KCHECK(h);
+        TRY(transpose<T>(h, st, p.f.Xc, Dp, ME, Dp, p.tA, MpE, Dp));
+        EpiGradStore::Params e = {h->G_(h->iWe), E, D, E, 0, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpE, p.tB, MpE, Dp, Ep, MpE, e)));
+    }
+    if (mode == 1 && decay > 0.f) {   // Q4: L2 on every variable without 'bias' in its name (the LSTM '/biases' only)
+        CUDA_TRY(h, cudaMemsetAsync(h->sq + 3, 0, sizeof(double), st));
+        for (size_t i = 0; i < h->vars.size(); ++i) {
+            if ((int)i == h->ib1 || (int)i == h->ib2) continue;
+            if ((int)i == h->iAW || (int)i == h->iAb) continue;   // attribute head is not part of build_model's graph here
+            const Var& v = h->vars[i];
+            add_decay_kernel<<<148 * 4, 256, 0, st>>>(h->grads + v.off, h->params + v.off, v.count(), decay * grad_scale); KCHECK(h);
+            sumsq_kernel<<<148 * 2, 256, 0, st>>>(h->params + v.off, v.count(), h->sq + 3); KCHECK(h);
+        }
+        if (loss_out) { xe_total_kernel<<<1, 1, 0, st>>>(loss_out, h->sq, decay, grad_scale); KCHECK(h); }
+    }
+    return 0;
+}
+
+#define DISPATCH(h, call_bf16, call_f32) ((h)->cfg.precision == S2VT_PREC_BF16 ? (call_bf16) : (call_f32))
+
+extern "C" int s2vt_teacher_forward(s2vt_handle* h, const float* video, int B, const int32_t* captions, int N, uint64_t drop_seed, uint32_t row_base,
+                                    float* logp_out, float* logits_out, s2vt_stream st) {
+    TRY(check_ready(h));
+    if (!video || !captions || B <= 0 || N <= 0) return h->fail(S2VT_EINVAL, "bad teacher_forward arguments");
+    cudaStream_t s = (cudaStream_t)st;
+    return DISPATCH(h, (train_impl<bf16>(h, s, 2, video, B, captions, nullptr, nullptr, nullptr, N, 0.f, 1.f, 0, 0.f, 0.f, drop_seed, row_base, nullptr, logp_out, logits_out)),
+                    (train_impl<float>(h, s, 2, video, B, captions, nullptr, nullptr, nullptr, N, 0.f, 1.f, 0, 0.f, 0.f, drop_seed, row_base, nullptr, logp_out, logits_out)));
+}
+
+extern "C" int s2vt_rl_backward(s2vt_handle* h, const float* video, int B, const int32_t* captions, const float* mask, const float* rewards,
+                                const float* base_line, int N, float norm, float grad_scale, int accumulate, uint64_t drop_seed, uint32_t row_base,
+                                float* loss_out, s2vt_stream st) {
+    TRY(check_ready(h));
+    if (!video || !captions || !mask || !rewards || !base_line || B <= 0 || N <= 0) return h->fail(S2VT_EINVAL, "bad rl_backward arguments");
+    cudaStream_t s = (cudaStream_t)st;
+    return DISPATCH(h, (train_impl<bf16>(h, s, 0, video, B, captions, mask, rewards, base_line, N, norm, grad_scale, accumulate, 0.f, 0.f, drop_seed, row_base, loss_out, nullptr, nullptr)),
+                    (train_impl<float>(h, s, 0, video, B, captions, mask, rewards, base_line, N, norm, grad_scale, accumulate, 0.f, 0.f, drop_seed, row_base, loss_out, nullptr, nullptr)));
+}
+
+extern "C" int s2vt_xe_backward(s2vt_handle* h, const float* video, int B, const int32_t* captions, const float* mask, int N, float label_smoothing,
+                                float decay, float norm, float grad_scale, int accumulate, uint64_t drop_seed, uint32_t row_base, float* loss_out,
+                                s2vt_stream st) {
+    TRY(check_ready(h));
+    if (!video || !captions || !mask || B <= 0 || N <= 0) return h->fail(S2VT_EINVAL, "bad xe_backward arguments");
+    cudaStream_t s = (cudaStream_t)st;
+    return DISPATCH(h, (train_impl<bf16>(h, s, 1, video, B, captions, mask, nullptr, nullptr, N, norm, grad_scale, accumulate, label_smoothing, decay, drop_seed, row_base, loss_out, nullptr, nullptr)),
+                    (train_impl<float>(h, s, 1, video, B, captions, mask, nullptr, nullptr, N, norm, grad_scale, accumulate, label_smoothing, decay, drop_seed, row_base, loss_out, nullptr, nullptr)));
+}
+
+// ---- attribute head (config 4) --------------------------------------------------------------------------------------
+template <typename T>
+static int attribute_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B, const float* labels, float grad_scale, float* loss_out) {
+    const int A = h->A, Ap = h->Ap, D = h->D, Dp = h->Dp, Bp = ru(B, S2VT_PAD);
+    Arena a(h->ws, h->ws_bytes);
+    T* pooled = a.take<T>((size_t)B * Dp);
+    float* z = a.take<float>((size_t)B * Ap);
+    T* dz = a.take<T>((size_t)B * Ap);
+    T* pooledT = a.take<T>((size_t)Dp * Bp);
+    T* dzT = a.take<T>((size_t)Ap * Bp);
+    float* battr = a.take<float>(Ap);
+    if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small: need %zu bytes", a.used);
+    mean_frames_kernel<T><<<B, 256, 0, st>>>(video, h->Tv, D, Dp, pooled); KCHECK(h);
+    CUDA_TRY(h, cudaMemsetAsync(battr, 0, Ap * sizeof(float), st));
+    CUDA_TRY(h, cudaMemcpyAsync(battr, h->P_(h->iAb), A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    typename EpiStore<T>::Params ep = {z, nullptr, Ap, battr, B, 0};
+    TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, pooled, Dp, h->attrWT, Dp, B, Ap, Dp, ep)));
+    sigmoid_ce_kernel<T><<<1, 256, 0, st>>>(z, Ap, labels, B, A, Ap, grad_scale, dz, h->scal + 8); KCHECK(h);
+    if (loss_out) CUDA_TRY(h, cudaMemcpyAsync(loss_out, h->scal + 8, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRY(transpose<T>(h, st, pooled, Dp, B, Dp, pooledT, Bp, Dp));
+    TRY(transpose<T>(h, st, dz, Ap, B, Ap, dzT, Bp, Ap));
+    EpiGradStore::Params eg = {h->G_(h->iAW), A, D, A, 0, 1.f};
+    TRY((gemm<T, CfgBig, EpiGradStore>(h, st, pooledT, Bp, dzT, Bp, Dp, Ap, Bp, eg)));
+    rowsum_grad_kernel<T><<<Ap, 256, 0, st>>>(dzT, Bp, B, A, 0, h->G_(h->iAb)); KCHECK(h);
+    return 0;
+}
+
+extern "C" int s2vt_attribute_backward(s2vt_handle* h, const float* video, int B, const float* labels, float grad_scale, float* loss_out, s2vt_stream st) {
+    TRY(check_ready(h));
+    if (!h->A) return h->fail(S2VT_ESTATE, "handle was created without an attribute head");
+    if (!video || !labels || B <= 0) return h->fail(S2VT_EINVAL, "bad attribute_backward arguments");
+    return DISPATCH(h, attribute_impl<bf16>(h, (cudaStream_t)st, video, B, labels, grad_scale, loss_out),
+                    attribute_impl<float>(h, (cudaStream_t)st, video, B, labels, grad_scale, loss_out));
+}
+
+// ---- optimiser ----------------------------------------------------------------------------------------------------
+extern "C" int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int wemb_slice_norm, float* gnorm_out, s2vt_stream st_) {
+    if (!h || !h->bound) return S2VT_ESTATE;
+    if (step < 1) return h->fail(S2VT_EINVAL, "Adam step is 1-based");
+    cudaStream_t st = (cudaStream_t)st_;
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    CUDA_TRY(h, cudaMemsetAsync(h->sq, 0, 3 * sizeof(double), st));
+    sumsq_kernel<<<148 * 4, 256, 0, st>>>(h->grads, h->P, h->sq); KCHECK(h);
+    const Var& we = h->vars[h->iWemb];
+    sumsq_kernel<<<148, 256, 0, st>>>(h->grads + we.off, we.count(), h->sq + 1); KCHECK(h);
+    copy_slice_norm_kernel<<<1, 1, 0, st>>>(h->grads + h->P, h->sq + 2); KCHECK(h);
+    double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step));
+    adam_kernel<<<148 * 8, 256, 0, st>>>(h->params, h->grads, h->adam_m, h->adam_v, h->P, h->sq, wemb_slice_norm, clip_norm, (float)lr_t, b1, b2, eps, gnorm_out);
+    KCHECK(h);
+    h->fresh = false;
+    return s2vt_refresh(h, st_);
+}
+
+// ---- workspace sizing ---------------------------------------------------------------------------------------------
+template <typename T>
+static size_t ws_bytes_impl(const s2vt_handle* h, int nv, int nr, int beam) {
+    size_t best = 0;
+    {   // rollout: K*B + B rows
+        Arena a(nullptr, 0); Roll<T> r; plan_roll<T>(h, a, nv, nr + nv, r); if (a.used > best) best = a.used;
+    }
+    {   // training with de-duplicated videos, and with one video per row (the literal reference feed)
+        Arena a(nullptr, 0); Train<T> p; plan_train<T>(h, a, nv, nr, true, false, p); if (a.used > best) best = a.used;
+    }
+    if (beam > 0) {
+        Arena a(nullptr, 0); Roll<T> r; plan_roll<T>(h, a, nv, nv * beam, r);
+        a.take<float>((size_t)8 * nv * beam * 64);   // beam bookkeeping, see beam.cuh
+        if (a.used > best) best = a.used;
+    }
+    return best + 4096;
+}
+extern "C" size_t s2vt_workspace_bytes(const s2vt_handle* h, int n_videos, int n_rows, int beam) {
+    if (!h || n_videos <= 0) return 0;
+    if (n_rows < n_videos) n_rows = n_videos;
+    return h->cfg.precision == S2VT_PREC_BF16 ? ws_bytes_impl<bf16>(h, n_videos, n_rows, beam) : ws_bytes_impl<float>(h, n_videos, n_rows, beam);
+}
