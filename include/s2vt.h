@@ -139,9 +139,11 @@ int s2vt_beam_step(s2vt_handle* h, const float* state2, const float* state1, con
  * keys of <= 4 ids of 16 bits.  Build (host, once per corpus): */
 typedef struct ciderd_corpus ciderd_corpus;
 /* ref_tokens: concatenated reference sentences; ref_offsets[n_refs+1]; video_ref_offsets[n_videos+1] indexes refs.
- * Document frequencies are counted over these videos (CiderD df corpus); ref_len = ln(n_videos). */
+ * Document frequencies are counted over the videos with video_in_df[v] != 0 (all when NULL) -- the CiderD df corpus
+ * (`CiderD(df='msvd')`, cider_evaluation.py:12); ref_len = ln(#df videos).  Videos outside the df corpus can still be
+ * scored against (e.g. test-set references). */
 int ciderd_corpus_create(const int32_t* ref_tokens, const int64_t* ref_offsets, int64_t n_refs, const int64_t* video_ref_offsets,
-                         int64_t n_videos, ciderd_corpus** out);
+                         int64_t n_videos, const uint8_t* video_in_df, ciderd_corpus** out);
 void ciderd_corpus_destroy(ciderd_corpus* c);
 size_t ciderd_corpus_device_bytes(const ciderd_corpus* c);
 /* Serialise the tables into a caller-allocated HOST buffer of ciderd_corpus_device_bytes(); the caller copies it to

@@ -50,7 +50,7 @@ SIGNATURES = {
     's2vt_beam_search': (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     's2vt_beam_init': (_i32, [_vp, _vp, _vp, _vp, _vp]),
     's2vt_beam_step': (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
-    'ciderd_corpus_create': (_i32, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_vp)]),
+    'ciderd_corpus_create': (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, C.POINTER(_vp)]),
     'ciderd_corpus_destroy': (None, [_vp]),
     'ciderd_corpus_device_bytes': (_sz, [_vp]),
     'ciderd_corpus_serialize': (_i32, [_vp, _vp]),

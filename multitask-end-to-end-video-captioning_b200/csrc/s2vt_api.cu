@@ -747,3 +747,5 @@ extern "C" size_t s2vt_workspace_bytes(const s2vt_handle* h, int n_videos, int n
     if (n_rows < n_videos) n_rows = n_videos;
     return h->cfg.precision == S2VT_PREC_BF16 ? ws_bytes_impl<bf16>(h, n_videos, n_rows, beam) : ws_bytes_impl<float>(h, n_videos, n_rows, beam);
 }
+
+#include "beam.cuh"
