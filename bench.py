@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- REINFORCE train videos/s (BASELINE.json metric) of the S2VT caption hot path on B200.
+
+One step = one iteration of the reference's RL hot loop (reinforcement_multisampling_tf_s2vt.py:734-829) on a batch of
+synthetic MSVD-shaped features: K sampled captions + greedy baseline per video, CIDEr-D rewards against the real
+MSVD training references, teacher-forced forward with output dropout, BPTT, global-norm clip, Adam.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     the reference algorithm on the host CPU (NumPy oracle)
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import gzip
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+DIMS = dict(D=1536, E=500, H=1000, V=9972)
+METRIC = 'reinforce_train_videos_per_s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--videos', type=int, default=64, help='videos per GPU per step (BASELINE config 2: batch 64)')
+    ap.add_argument('--samples', type=int, default=5, help='K sampled captions per video')
+    ap.add_argument('--frames', type=int, default=80, help='T_v (BASELINE features [64, 80, 1536]; the reference literal is 5)')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--ref-videos', type=int, default=8, help='videos per step of the CPU reference arm / cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# shared synthetic workload
+# ------------------------------------------------------------------------------------------------------------------
+def load_corpus():
+    def rd(name):
+        with gzip.open(os.path.join(GOLD, name), 'rt') as f:
+            return [l.rstrip('\n') for l in f]
+    vocab = [l.rstrip() for l in rd('msvd_vocabulary1.txt.gz')]
+    by, order = {}, []
+    for line in rd('msvd_sents_train_noval_lc_nopunc.txt.gz'):
+        vid, sent = line.strip().split('\t')[:2]
+        if vid not in by:
+            by[vid] = []; order.append(vid)
+        by[vid].append(sent)
+    return vocab, by, order
+
+
+def peaked_bias(vocab, by):
+    """'set B' of SURVEY 8(d): embed_word_b = ln(unigram count + 1) (the reference's bias_init_vector hook, :95-96)."""
+    w2i = {'<eos>': 0, '<bos>': 1}
+    w2i.update((w, i + 2) for i, w in enumerate(vocab))
+    counts = np.zeros(len(w2i))
+    for sents in by.values():
+        for s in sents:
+            for w in s.split(' '):
+                counts[w2i.get(w, 2)] += 1
+            counts[0] += 1
+    return w2i, np.log(counts + 1.0)
+
+
+def features(B, Tv, seed):
+    rng = np.random.RandomState(seed)
+    return np.maximum(0.0, rng.normal(0.25, 0.5, size=(B, Tv, DIMS['D']))).astype(np.float32)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU reference arm: the reference's algorithm (NumPy oracle restatement -- TF 1.1 / py2 cannot run here)
+# ------------------------------------------------------------------------------------------------------------------
+class OracleIteration(object):
+    """reinforcement_multisampling_tf_s2vt.py:734-829 statement by statement on the host: K separate multinomial sampler
+    runs + one greedy run (each re-encoding the frames), host CIDEr-D, build_loss forward at K*B rows with dropout,
+    BPTT, clip 5, Adam.  fp32, BLAS-threaded NumPy."""
+
+    def __init__(self, args, vocab, by, order, bias):
+        from oracle import s2vt_numpy as M, ciderd, philox
+        self.M, self.philox = M, philox
+        self.K, self.Tv, self.B = args.samples, args.frames, args.ref_videos
+        self.p = M.init_params(seed=4, dtype=np.float32, peaked_bias=bias, logit_scale=3.0, **DIMS)
+        self.opt = M.TFAdam(self.p)
+        self.scorer = ciderd.CiderD([by[v] for v in order])
+        self.i2w = {0: '<eos>', 1: '<bos>'}
+        self.i2w.update((i + 2, w) for i, w in enumerate(vocab))
+        self.refs = [by[order[j % len(order)]] for j in range(self.B)]
+        self.video = features(self.B, self.Tv, 1234)
+        self.step_no = 0
+
+    def step(self):
+        from oracle import text, ciderd
+        M, K, B = self.M, self.K, self.B
+        it = self.step_no
+        samples = [M.multinomial_sampler(self.p, self.video, 2024 + it, np.arange(k * B, (k + 1) * B)) for k in range(K)]
+        greedy = M.greedy_sampler(self.p, self.video)
+        samples = np.vstack(samples)
+        vid_rows = np.concatenate([self.video] * K, 0)
+        mask, multi_decoded = text.decode_captions_masks(samples, self.i2w)
+        _, greedy_decoded = text.decode_captions_masks(greedy, self.i2w)
+        ref = {i: self.refs[i % B] for i in range(K * B)}
+        b = ciderd.evaluate_captions_cider(self.scorer, ref, greedy_decoded)
+        b = np.tile(b, K)
+        r = ciderd.evaluate_captions_cider(self.scorer, ref, multi_decoded)
+        T = self.Tv + samples.shape[1]
+        rows = np.arange(K * B)
+        d1 = np.stack([self.philox.dropout_mask(7 + it, self.philox.STREAM_DROP1, rows, t, DIMS['H'], 0.9) for t in range(T)])
+        d2 = np.stack([self.philox.dropout_mask(7 + it, self.philox.STREAM_DROP2, rows, t, DIMS['H'], 0.9) for t in range(T)])
+        loss, grads, aux = M.rl_objective(self.p, vid_rows, samples, np.asarray(mask, np.float32), r.astype(np.float32), b.astype(np.float32), d1, d2)
+        clipped, gn = M.clip_by_global_norm(grads, 5.0, emb_slice_sqnorm=aux['emb_slice_sqnorm'])
+        self.p = self.opt.apply(self.p, clipped, M.exponential_decay(1e-6, it, 1000))
+        self.step_no += 1
+        return float(loss)
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get('num_threads') for i in threadpool_info() if i.get('user_api') == 'blas']
+        return int(max(n)) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vocab, by, order = load_corpus()
+    w2i, bias = peaked_bias(vocab, by)
+    o = OracleIteration(args, vocab, by, order, bias)
+    for _ in range(args.warmup):
+        o.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.step()
+    dt = time.perf_counter() - t0
+    val = args.steps * args.ref_videos / dt
+    sample = '%d steps of the full iteration on %d videos x K=%d, T_v=%d, fp32 NumPy/OpenBLAS' % (args.steps, args.ref_videos, args.samples, args.frames)
+    out = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'videos/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+           'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': workload_config(args, args.ref_videos, 1),
+           'cpu_baseline': {'value': val, 'unit': 'videos/s', 'cores': cpu_threads(), 'kind': 'port', 'sample': sample},
+           'e2e': {'value': val, 'unit': 'videos/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, videos_per_gpu, world):
+    return {'workload': 'REINFORCE iteration (rollout K+1, CIDEr-D reward, teacher-forced fwd+bwd with dropout 0.9, clip 5, Adam); '
+                        'BASELINE config 2 on MSVD-shaped features',
+            'videos_per_gpu': videos_per_gpu, 'global_videos': videos_per_gpu * world, 'K': args.samples, 'T_v': args.frames, 'T_c': 35,
+            'dim_image': DIMS['D'], 'word_dim': DIMS['E'], 'lstm_dim': DIMS['H'], 'n_words': DIMS['V'], 'parallelism': 'dp%d' % world,
+            'weights': 'random init seed 4, embed_word_b = ln(unigram count+1), embed_word_W x3 (SURVEY 8d set B)',
+            'references': 'MSVD train sentences (1200 videos, 48 774 refs)',
+            'l2': 'per-step working set (~3 GB of activations / gradients) is >> the 126 MB L2; no explicit flush'}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import s2vt_b200
+    vocab, by, order = load_corpus()
+    w2i, bias = peaked_bias(vocab, by)
+    B, K, Tv = args.videos, args.samples, args.frames
+    model = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=B,
+                                              n_video_lstm_step=Tv, n_caption_lstm_step=35, bias_init_vector=bias, dropout_rate=0.9,
+                                              precision=args.precision, max_videos=B, max_rows=K * B, seed=4)
+    model.variable('embed_word_W').mul_(3.0)
+    model.refresh()
+    scorer = s2vt_b200.cider.CiderD([by[v] for v in order], w2i)
+    trainer = s2vt_b200.trainer.ReinforceTrainer(model, scorer, n_samples=K, start_learning_rate=1e-6, decay_steps=1000, clip_norm=5.0, seed=2024)
+    feats_host = torch.from_numpy(features(B, Tv, 1234 + rank)).pin_memory()
+    feats_dev = feats_host.cuda(non_blocking=True)
+    vidx_host = torch.from_numpy(((rank * B + np.arange(B)) % len(order)).astype(np.int32)).pin_memory()
+    vidx_dev = vidx_host.cuda(non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(n, fn):
+        """n steps bracketed by barrier + synchronize; device time via CUDA events; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    step_dev = lambda: trainer.step(feats_dev, vidx_dev)
+
+    def step_e2e():
+        out = trainer.step(feats_host, vidx_host)          # H2D of the step's features inside the step
+        return out.cpu()                                   # D2H of [grad norm, loss]
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.3)
+    l0 = model.launch_count()
+    ms = timed(args.steps, step_dev)
+    launches = model.launch_count() - l0 + 2 * args.steps          # + 2 CIDEr-D kernels per step (launched outside the handle)
+    clocks = sampler.stop() if sampler else None
+    value = world * B * args.steps / (ms / 1e3)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(args.steps, step_e2e)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    # roofline pass: the same steps with CUDA-event brackets around every GEMM launch (separate from the timed region
+    # above so the brackets do not perturb `value`)
+    model.profile(True)
+    barrier()
+    for _ in range(args.steps):
+        step_dev()
+    prof = model.profile_read()
+    model.profile(False)
+    loss = float(trainer.step(feats_dev, vidx_dev)[1].item())
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+    bms, bfl, bn = prof['batched']
+    sms, sfl, sn = prof['step']
+    ach = bfl / (bms * 1e-3) / 1e12 if bms > 0 else 0.0
+    H, Tall = DIMS['H'], Tv + 35
+    step_bytes = sn and (sn * (H * 4 * H * 2.0) + 0.0)            # bf16 recurrent weights touched once per launch
+    out = {'metric': METRIC, 'value': value, 'unit': 'videos/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+           'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': workload_config(args, B, world),
+           'clocks': clocks, 'e2e': {'value': e2e, 'unit': 'videos/s', 'h2d_bytes_per_step': int(feats_host.numel() * 4 + vidx_host.numel() * 4),
+                                     'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps},
+           'gpu_launches': int(launches), 'loss': loss,
+           'roofline': {'kernel': 'gemm_kernel<bf16, 128x128x32 tiles> (batched GEMMs: projections, vocab logits, weight gradients)',
+                        'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf if peak_tf else None,
+                        'traffic': None, 'peak_source': peak_src, 'launches_per_step': bn / args.steps, 'ms_per_step': bms / args.steps,
+                        'algorithmic_gflop_per_step': bfl / args.steps / 1e9,
+                        'pass': 'separate instrumented pass of the same %d steps (events around each launch)' % args.steps},
+           'roofline_recurrent_step': {'kernel': 'gemm_kernel<bf16, 64x32 tiles> + fused LSTM cell (one launch per time step)', 'bound': 'hbm',
+                                       'achieved': (step_bytes / (sms * 1e-3) / 1e9) if sms > 0 else None, 'peak': peaks.get('hbm_gbs', 6650.0),
+                                       'unit': 'GB/s', 'launches_per_step': sn / args.steps, 'ms_per_step': sms / args.steps,
+                                       'us_per_launch': 1e3 * sms / sn if sn else None,
+                                       'bytes_model': 'bf16 recurrent weights 1000x4000x2 B = 8.0 MB read once per launch'}}
+    if out['roofline_recurrent_step']['achieved']:
+        out['roofline_recurrent_step']['frac'] = out['roofline_recurrent_step']['achieved'] / out['roofline_recurrent_step']['peak']
+    if world == 1 and not args.no_cpu_baseline:
+        o = OracleIteration(args, vocab, by, order, bias)
+        o.step()
+        t0 = time.perf_counter(); o.step(); dt = time.perf_counter() - t0
+        out['cpu_baseline'] = {'value': args.ref_videos / dt, 'unit': 'videos/s', 'cores': cpu_threads(), 'kind': 'port',
+                               'sample': '1 full iteration (after 1 warm-up) on %d videos x K=%d, T_v=%d, fp32 NumPy/OpenBLAS oracle' % (args.ref_videos, K, Tv)}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

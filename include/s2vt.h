@@ -118,9 +118,20 @@ int s2vt_xe_backward(s2vt_handle* h, const float* video, int B, const int32_t* c
 int s2vt_attribute_backward(s2vt_handle* h, const float* video, int B, const float* labels, float grad_scale, float* loss_out,
                             s2vt_stream st);
 /* tf.clip_by_global_norm + AdamOptimizer.apply_gradients (:650-652; tf_s2vt.py:446-448), TF-1.1 Adam arithmetic.
- * step = 1-based Adam time step; lr already includes exponential_decay.  wemb_slice_norm != 0 uses the
- * IndexedSlices norm of the Wemb gradient.  gnorm_out (device, nullable) receives the global norm. */
-int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int wemb_slice_norm, float* gnorm_out, s2vt_stream st);
+ * step = 1-based Adam time step; lr already includes exponential_decay.
+ * flags: S2VT_OPT_WEMB_SLICE_NORM uses the IndexedSlices norm of the Wemb gradient;
+ *        S2VT_OPT_NORMALIZE divides the gradients (accumulated with norm = 1 and summed over ranks) by the global
+ *        sum(mask) that s2vt_rl_backward left in the gradient block's aux slot -- the data-parallel form of `/ norm`.
+ * out (device, nullable, 2 floats): out[0] = global gradient norm, out[1] = loss (aux slot, normalised likewise). */
+enum { S2VT_OPT_WEMB_SLICE_NORM = 1, S2VT_OPT_NORMALIZE = 2 };
+int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int flags, float* out, s2vt_stream st);
+
+/* ---- instrumentation used by bench.py: kernels launched by this handle so far; CUDA-event brackets around every GEMM
+ * launch (class 0 = batched GEMMs, class 1 = recurrent-step GEMMs) with their algorithmic FLOPs.  profile_read
+ * synchronises the device, fills ms/flops/launches [2] and clears the records. */
+long long s2vt_launch_count(const s2vt_handle* h);
+int s2vt_profile(s2vt_handle* h, int enable);
+int s2vt_profile_read(s2vt_handle* h, double* ms_out, double* flops_out, long long* launches_out);
 
 /* ---- beam search: beam_probability + the host loop of final_beam_search.py:202-294 / e2e_beam_search.py:235-344,
  * batched over B videos on the device, semantics B1-B7 of SURVEY.md.

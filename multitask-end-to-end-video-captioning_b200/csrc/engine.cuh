@@ -49,6 +49,12 @@ struct s2vt_handle {
     void *WeT, *W1xT, *W1hT, *W1h, *W1x, *W2xT, *W2x, *W2eT, *W2e, *W2hT, *W2h, *WoT, *Wo, *WembC, *attrWT;
     float *be_p, *b1_p, *b2_p, *bo_p, *Etab;
     bool bound, fresh;
+    // instrumentation (bench.py): launch counter and optional CUDA-event brackets around GEMM launches
+    mutable long long launches = 0;
+    bool prof = false;
+    struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
     // variable indices
     int iWemb, iWe, ibe, iWo, ibo, iW1, ib1, iW2, ib2, iAW, iAb;
     mutable std::string err;
@@ -67,4 +73,4 @@ struct s2vt_handle {
         cudaError_t _e = (expr);                                                                                 \
         if (_e != cudaSuccess) return (h)->fail(S2VT_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
-#define KCHECK(h) CUDA_TRY(h, cudaGetLastError())
+#define KCHECK(h) do { (h)->launches++; CUDA_TRY(h, cudaGetLastError()); } while (0)

@@ -14,13 +14,13 @@
 // -----------------------------------------------------------------------------------------------------------------
 // tile configurations
 // -----------------------------------------------------------------------------------------------------------------
-template <int BM_, int BN_, int WM_, int WN_>
+template <int BM_, int BN_, int WM_, int WN_, int BK_ = 32, int ST_ = 3>
 struct TileCfg {
     static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_;
     static constexpr int NWARPS = (BM / WM) * (BN / WN);
     static constexpr int NTHREADS = NWARPS * 32;
     static constexpr int LDC = BN + 8;  // fp32 epilogue tile row stride
-    static constexpr int BK = 32, STAGES = 3, LDS = BK + 8;
+    static constexpr int BK = BK_, STAGES = ST_, LDS = BK + 8;
     static constexpr size_t PIPE_BYTES = (size_t)STAGES * (BM + BN) * LDS * 2;
     static constexpr size_t SIMT_BYTES = (size_t)16 * (BM + 4 + BN + 4) * 4;
     static constexpr size_t EPI_BYTES = (size_t)BM * LDC * 4;
@@ -28,7 +28,7 @@ struct TileCfg {
         (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) > SIMT_BYTES ? (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) : SIMT_BYTES;
 };
 typedef TileCfg<128, 128, 64, 32> CfgBig;    // batched GEMMs: 8 warps, warp tile 64x32
-typedef TileCfg<64, 32, 16, 32> CfgStep;     // recurrent-step GEMMs: 4 warps, many CTAs for small M
+typedef TileCfg<64, 32, 16, 32, 128, 3> CfgStep;   // recurrent-step GEMMs: 4 warps, many CTAs for small M, long K blocks (few barriers)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -67,14 +67,15 @@ struct Mainloop<bf16, Cfg> {
         auto load_stage = [&](int s, int kt) {
             bf16* a = sA + s * BM * LDS;
             bf16* b = sB + s * BN * LDS;
-            for (int c = tid; c < BM * 4; c += Cfg::NTHREADS) {
-                int r = c >> 2, ch = c & 3, gr = m0 + r;
+            constexpr int CH = Cfg::BK / 8;   // 16-byte chunks per tile row
+            for (int c = tid; c < BM * CH; c += Cfg::NTHREADS) {
+                int r = c / CH, ch = c % CH, gr = m0 + r;
                 bool ok = gr < M;
-                cp_async16(a + r * LDS + ch * 8, A + (size_t)(ok ? gr : 0) * lda + kt * 32 + ch * 8, ok ? 16 : 0);
+                cp_async16(a + r * LDS + ch * 8, A + (size_t)(ok ? gr : 0) * lda + kt * Cfg::BK + ch * 8, ok ? 16 : 0);
             }
-            for (int c = tid; c < BN * 4; c += Cfg::NTHREADS) {
-                int r = c >> 2, ch = c & 3;
-                cp_async16(b + r * LDS + ch * 8, B + (size_t)(n0 + r) * ldb + kt * 32 + ch * 8, 16);
+            for (int c = tid; c < BN * CH; c += Cfg::NTHREADS) {
+                int r = c / CH, ch = c % CH;
+                cp_async16(b + r * LDS + ch * 8, B + (size_t)(n0 + r) * ldb + kt * Cfg::BK + ch * 8, 16);
             }
         };
 
@@ -99,7 +100,7 @@ struct Mainloop<bf16, Cfg> {
             const bf16* a = sA + (kt % ST) * BM * LDS;
             const bf16* b = sB + (kt % ST) * BN * LDS;
 #pragma unroll
-            for (int kk = 0; kk < 32; kk += 16) {
+            for (int kk = 0; kk < Cfg::BK; kk += 16) {
                 uint32_t af[MT][4];
 #pragma unroll
                 for (int i = 0; i < MT; ++i)

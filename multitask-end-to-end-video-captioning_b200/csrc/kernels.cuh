@@ -376,16 +376,19 @@ __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, double* __re
 //   theta -= lr_t * m / (sqrt(v) + eps),  lr_t = lr * sqrt(1-b2^t)/(1-b1^t) (computed on the host)
 // sq[0] = dense sum of squares of all gradients, sq[1] = dense Wemb part, sq[2] = Wemb slice square norm.
 __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
-                            const double* __restrict__ sq, int use_slice_norm, float clip, float lr_t, float b1, float b2, float eps,
+                            const double* __restrict__ sq, int use_slice_norm, int normalize, float clip, float lr_t, float b1, float b2, float eps,
                             float* __restrict__ gnorm_out) {
+    // normalize: the gradients were accumulated with norm = 1 (data-parallel); g[n+2] holds the global sum(mask) (R1)
+    const float inv = normalize ? 1.0f / g[n + 2] : 1.0f;
     double s = sq[0];
     if (use_slice_norm) s = s - sq[1] + sq[2];
+    s *= (double)inv * (double)inv;
     float gn = (float)sqrt(s);
     float scale = 1.0f;
     if (clip > 0.f && gn > 0.f) scale = clip * fminf(1.0f / gn, 1.0f / clip);
-    if (gnorm_out && blockIdx.x == 0 && threadIdx.x == 0) gnorm_out[0] = gn;
+    if (gnorm_out && blockIdx.x == 0 && threadIdx.x == 0) { gnorm_out[0] = gn; gnorm_out[1] = g[n + 1] * inv; }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float gi = g[i] * scale;
+        float gi = g[i] * inv * scale;
         float mi = b1 * m[i] + (1.f - b1) * gi;
         float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi; v[i] = vi;

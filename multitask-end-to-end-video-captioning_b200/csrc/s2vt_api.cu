@@ -61,6 +61,7 @@ __global__ void sigmoid_ce_kernel(const float* __restrict__ z, int ldz, const fl
 
 __global__ void add_scaled_scalar_kernel(float* dst, const float* src, float scale) { dst[0] += scale * src[0]; }
 __global__ void copy_slice_norm_kernel(const float* src, double* dst) { dst[0] = (double)src[0]; }
+__global__ void set_norm_kernel(float* nrm, const float* local_sum, float override_) { nrm[0] = override_ > 0.f ? override_ : local_sum[0]; }
 __global__ void xe_total_kernel(float* out, const double* sq, float decay, float scale) {
     float wd = decay * 0.5f * (float)sq[3];
     out[1] = wd;
@@ -214,9 +215,32 @@ static int pack(s2vt_handle* h, cudaStream_t st, const float* src, int lds, int 
     return 0;
 }
 
+static cudaEvent_t prof_event(s2vt_handle* h) {
+    if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+// logical (un-padded) size of a padded dimension, for the algorithmic FLOP count of the roofline report
+static double logical_dim(const s2vt_handle* h, int x) {
+    if (x == h->Gp) return 4.0 * h->H;
+    if (x == h->Hp) return h->H;
+    if (x == h->Vp) return h->V;
+    if (x == h->Ep) return h->E;
+    if (x == h->Dp) return h->D;
+    return x;
+}
 template <typename T, class Cfg, class Epi>
-static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const typename Epi::Params& ep) {
+static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const typename Epi::Params& ep,
+                int logical_k = 0, int logical_m = 0) {
+    s2vt_handle::ProfRec rec;
+    if (h->prof) {
+        rec.a = prof_event(h); rec.b = prof_event(h);
+        rec.flops = 2.0 * (logical_m ? (double)logical_m : logical_dim(h, M)) * logical_dim(h, N) * (logical_k ? (double)logical_k : logical_dim(h, K));
+        rec.cls = Cfg::BM >= 128 ? 0 : 1;
+        cudaEventRecord(rec.a, st);
+    }
+    h->launches++;
     CUDA_TRY(h, (launch_gemm<T, Cfg, Epi>(st, (const T*)A, lda, (const T*)B, ldb, M, N, K, ep)));
+    if (h->prof) { cudaEventRecord(rec.b, st); h->prof_recs.push_back(rec); }
     return 0;
 }
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
@@ -519,9 +543,9 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         return 0;
     }
     // ---------------- loss coefficients ----------------
-    float* nrm = h->scal;   // scal[0] = norm
-    if (norm > 0.f) { CUDA_TRY(h, cudaMemcpyAsync(nrm, &norm, sizeof(float), cudaMemcpyHostToDevice, st)); }
-    else { sum_kernel<<<1, 256, 0, st>>>(mask, N * Tc, nrm); KCHECK(h); }
+    float* nrm = h->scal;   // scal[0] = norm used by the objective, scal[1] = sum(mask) of this call
+    sum_kernel<<<1, 256, 0, st>>>(mask, N * Tc, h->scal + 1); KCHECK(h);
+    set_norm_kernel<<<1, 1, 0, st>>>(nrm, h->scal + 1, norm); KCHECK(h);
     if (!accumulate) CUDA_TRY(h, cudaMemsetAsync(h->grads, 0, (h->P + 8) * sizeof(float), st));
     loss_coef_kernel<<<(Tc * N + 255) / 256, 256, 0, st>>>(mode, mask, rewards, base_line, N, Tc, nrm, grad_scale, ls, V, p.ca, p.cb, p.cc); KCHECK(h);
     softmax_rows_kernel<T><<<Tc * N, ROW_THREADS, 0, st>>>(p.logits, Vp, V, Vp, p.target, p.ca, p.cb, p.cc, p.logp, p.sumlsm, p.dlogits, logp_out, N, Tc);
@@ -532,6 +556,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         else CUDA_TRY(h, cudaMemcpyAsync(loss_out, h->scal + 4, sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     add_scaled_scalar_kernel<<<1, 1, 0, st>>>(h->grads + h->P + 1, h->scal + 4, grad_scale); KCHECK(h);   // aux[1] = loss (summed by the DP allreduce)
+    if (mode == 0) { add_scaled_scalar_kernel<<<1, 1, 0, st>>>(h->grads + h->P + 2, h->scal + 1, 1.f); KCHECK(h); }   // aux[2] = sum(mask)
 
     // ---------------- backward ----------------
     const int MD = Tc * N, M2 = T_ * N, M1 = T_ * B, ME = Tv * B;
@@ -544,7 +569,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         TRY(transpose<T>(h, st, p.out2d, Hp, MD, Hp, p.tA, MpD, Hp));
         TRY(transpose<T>(h, st, p.dlogits, Vp, MD, Vp, p.tB, MpD, Vp));
         EpiGradStore::Params ep = {h->G_(h->iWo), V, H, V, 0, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Hp, Vp, MpD, ep)));
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Hp, Vp, MpD, ep, MD, H)));
         rowsum_grad_kernel<T><<<Vp, 256, 0, st>>>(p.tB, MpD, MD, V, 0, h->G_(h->ibo)); KCHECK(h);
     }
     // LSTM2 BPTT
@@ -577,16 +602,16 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         rowsum_grad_kernel<T><<<Gp, 256, 0, st>>>(p.tB, Mp2, M2, 0, H, h->G_(h->ib2)); KCHECK(h);
         TRY(transpose<T>(h, st, p.out1d, Hp, M2, Hp, p.tA, Mp2, Hp));
         EpiGradStore::Params e1 = {gW2, G, H, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp2, p.tB, Mp2, Hp, Gp, Mp2, e1)));
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp2, p.tB, Mp2, Hp, Gp, Mp2, e1, M2, H)));
         TRY(transpose<T>(h, st, p.h2_all, Hp, M2, Hp, p.tA, Mp2, Hp));       // h2 before step t = h2_all[t]
         EpiGradStore::Params e3 = {gW2 + (size_t)(H + E) * G, G, H, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp2, p.tB, Mp2, Hp, Gp, Mp2, e3)));
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp2, p.tB, Mp2, Hp, Gp, Mp2, e3, M2, H)));
         // embedding rows: decode steps only
         TRY(transpose<T>(h, st, p.dG2 + (size_t)Tv * N * Gp, Gp, MD, Gp, p.tB, MpD, Gp));
         gather_rows_kernel<T><<<MD, 128, 0, st>>>((const T*)h->WembC, Ep, p.prev_tok, MD, p.emb); KCHECK(h);
         TRY(transpose<T>(h, st, p.emb, Ep, MD, Ep, p.tA, MpD, Ep));
         EpiGradStore::Params e2 = {gW2 + (size_t)H * G, G, E, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Ep, Gp, MpD, e2)));
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Ep, Gp, MpD, e2, MD, E)));
     }
     // LSTM1 BPTT over the B shared rows
     reduce_dropout_kernel<<<M1, 256, 0, st>>>(p.dout1, B, N, Hp, p.dh1, drop_seed, S2VT_STREAM_DROP1, row_base, keep); KCHECK(h);
@@ -611,12 +636,12 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         rowsum_grad_kernel<T><<<Gp, 256, 0, st>>>(p.tB, Mp1, M1, 0, H, h->G_(h->ib1)); KCHECK(h);
         TRY(transpose<T>(h, st, p.f.h1_all, Hp, M1, Hp, p.tA, Mp1, Hp));
         EpiGradStore::Params e2 = {gW1 + (size_t)E * G, G, H, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp1, p.tB, Mp1, Hp, Gp, Mp1, e2)));
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp1, p.tB, Mp1, Hp, Gp, Mp1, e2, M1, H)));
         // frame-embedding rows: encoder steps only
         TRY(transpose<T>(h, st, p.dG1, Gp, ME, Gp, p.tB, MpE, Gp));
         TRY(transpose<T>(h, st, p.f.img, Ep, ME, Ep, p.tA, MpE, Ep));
         EpiGradStore::Params e1 = {gW1, G, E, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpE, p.tB, MpE, Ep, Gp, MpE, e1)));
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpE, p.tB, MpE, Ep, Gp, MpE, e1, ME, E)));
     }
     {   // frame projection gradients: dimg = dG1[enc] . W1[x rows]^T ; dWe = X^T . dimg ; dbe = column sums
         typename EpiStore<T>::Params ep = {p.dimgF, p.dimgT_src, Ep, nullptr, ME, 0};
@@ -625,7 +650,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         rowsum_grad_kernel<T><<<Ep, 256, 0, st>>>(p.tB, MpE, ME, E, 0, h->G_(h->ibe)); KCHECK(h);
         TRY(transpose<T>(h, st, p.f.Xc, Dp, ME, Dp, p.tA, MpE, Dp));
         EpiGradStore::Params e = {h->G_(h->iWe), E, D, E, 0, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpE, p.tB, MpE, Dp, Ep, MpE, e)));
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpE, p.tB, MpE, Dp, Ep, MpE, e, ME, D)));
     }
     if (mode == 1 && decay > 0.f) {   // Q4: L2 on every variable without 'bias' in its name (the LSTM '/biases' only)
         CUDA_TRY(h, cudaMemsetAsync(h->sq + 3, 0, sizeof(double), st));
@@ -708,7 +733,8 @@ extern "C" int s2vt_attribute_backward(s2vt_handle* h, const float* video, int B
 }
 
 // ---- optimiser ----------------------------------------------------------------------------------------------------
-extern "C" int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int wemb_slice_norm, float* gnorm_out, s2vt_stream st_) {
+extern "C" int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int flags, float* gnorm_out, s2vt_stream st_) {
+    const int wemb_slice_norm = flags & 1, normalize = (flags >> 1) & 1;
     if (!h || !h->bound) return S2VT_ESTATE;
     if (step < 1) return h->fail(S2VT_EINVAL, "Adam step is 1-based");
     cudaStream_t st = (cudaStream_t)st_;
@@ -719,7 +745,7 @@ extern "C" int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, in
     sumsq_kernel<<<148, 256, 0, st>>>(h->grads + we.off, we.count(), h->sq + 1); KCHECK(h);
     copy_slice_norm_kernel<<<1, 1, 0, st>>>(h->grads + h->P, h->sq + 2); KCHECK(h);
     double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step));
-    adam_kernel<<<148 * 8, 256, 0, st>>>(h->params, h->grads, h->adam_m, h->adam_v, h->P, h->sq, wemb_slice_norm, clip_norm, (float)lr_t, b1, b2, eps, gnorm_out);
+    adam_kernel<<<148 * 8, 256, 0, st>>>(h->params, h->grads, h->adam_m, h->adam_v, h->P, h->sq, wemb_slice_norm, normalize, clip_norm, (float)lr_t, b1, b2, eps, gnorm_out);
     KCHECK(h);
     h->fresh = false;
     return s2vt_refresh(h, st_);
@@ -749,3 +775,26 @@ extern "C" size_t s2vt_workspace_bytes(const s2vt_handle* h, int n_videos, int n
 }
 
 #include "beam.cuh"
+
+// ---- instrumentation ------------------------------------------------------------------------------------------------
+extern "C" long long s2vt_launch_count(const s2vt_handle* h) { return h ? h->launches : 0; }
+extern "C" int s2vt_profile(s2vt_handle* h, int enable) {
+    if (!h) return S2VT_EINVAL;
+    h->prof = enable != 0;
+    return 0;
+}
+// Synchronises the device, aggregates the bracketed GEMM launches per class (0: batched GEMMs, 1: recurrent-step GEMMs)
+// and clears the record list.
+extern "C" int s2vt_profile_read(s2vt_handle* h, double* ms_out, double* flops_out, long long* launches_out) {
+    if (!h || !ms_out || !flops_out || !launches_out) return S2VT_EINVAL;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    for (int c = 0; c < 2; ++c) { ms_out[c] = 0; flops_out[c] = 0; launches_out[c] = 0; }
+    for (auto& r : h->prof_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        ms_out[r.cls] += ms; flops_out[r.cls] += r.flops; launches_out[r.cls] += 1;
+        h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b);
+    }
+    h->prof_recs.clear();
+    return 0;
+}

@@ -217,12 +217,27 @@ class Video_Caption_Generator(object):
         self._check(self.lib.s2vt_attribute_backward(self.h, _ptr(v), v.shape[0], _ptr(y), float(grad_scale), _ptr(out), _stream()))
         return out
 
-    def optimizer_step(self, lr, clip_norm, wemb_slice_norm=True):
-        """clip_by_global_norm + Adam apply (:650-652).  Returns the global gradient norm (1-element device tensor)."""
+    def optimizer_step(self, lr, clip_norm, wemb_slice_norm=True, normalize=False):
+        """clip_by_global_norm + Adam apply (:650-652).  Returns device tensor [global gradient norm, loss aux slot].
+        normalize=True: gradients were accumulated with norm=1 (and all-reduced); divide by the global sum(mask)."""
         self.adam_step += 1
-        gn = torch.empty(1, dtype=torch.float32, device=self.device)
-        self._check(self.lib.s2vt_optimizer_step(self.h, float(lr), float(clip_norm), self.adam_step, int(bool(wemb_slice_norm)), _ptr(gn), _stream()))
-        return gn
+        out = torch.empty(2, dtype=torch.float32, device=self.device)
+        flags = (1 if wemb_slice_norm else 0) | (2 if normalize else 0)
+        self._check(self.lib.s2vt_optimizer_step(self.h, float(lr), float(clip_norm), self.adam_step, flags, _ptr(out), _stream()))
+        return out
+
+    # ---- instrumentation -----------------------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.s2vt_launch_count(self.h))
+
+    def profile(self, enable):
+        self._check(self.lib.s2vt_profile(self.h, int(bool(enable))))
+
+    def profile_read(self):
+        """-> {'batched': (ms, flops, launches), 'step': (...)} of the GEMM launches since the last read."""
+        ms, fl, n = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
+        self._check(self.lib.s2vt_profile_read(self.h, ms, fl, n))
+        return {'batched': (ms[0], fl[0], n[0]), 'step': (ms[1], fl[1], n[1])}
 
     # ---- drop-in step functions (the literal sess.run contracts) ------------------------------------------------
     def rl_step(self, mask, captions, video, rewards, base_line, lr, clip_norm=5.0, drop_seed=0, n_videos=None):

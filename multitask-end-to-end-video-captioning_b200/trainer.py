@@ -1,0 +1,116 @@
+"""Training / decoding loops of the reference scripts on top of the B200 library.
+
+`ReinforceTrainer.step` is one iteration of the hot loop of reinforcement_multisampling_tf_s2vt.py:734-829:
+K sampled captions + greedy baseline per video, CIDEr-D rewards, REINFORCE gradient, global-norm clip, Adam -- with
+every stage on the device and, under torch.distributed (one process per GPU), one NCCL all-reduce of the flat
+gradient block per iteration.
+"""
+import numpy as np
+import torch
+
+try:
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    dist = None
+
+
+def _world():
+    if dist is not None and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def exponential_decay(lr0, global_step, decay_steps, rate=0.5):
+    """tf.train.exponential_decay(..., staircase=True) (:639-640; tf_s2vt.py:442-443)."""
+    return lr0 * rate ** (global_step // decay_steps)
+
+
+def allreduce_gradients(model, bucket_bytes=32 << 20):
+    """Sum the flat fp32 gradient block (+ aux slots: slice norm, loss, sum(mask)) over the ranks.  Buckets are
+    launched back to back on NCCL's stream so the first ones overlap the tail of the previous kernels."""
+    rank, world = _world()
+    if world == 1:
+        return
+    g = model.grads
+    n = g.numel()
+    step = max(1, bucket_bytes // 4)
+    works = [dist.all_reduce(g[i:min(n, i + step)], op=dist.ReduceOp.SUM, async_op=True) for i in range(0, n, step)]
+    for w in works:
+        w.wait()
+
+
+class ReinforceTrainer(object):
+    """Stage-2 trainer (K-sample REINFORCE with CIDEr-D reward and greedy baseline).
+
+    Data parallel rule: each rank owns its videos and all K samples of them; gradients are accumulated
+    with norm = 1, summed over ranks together with sum(mask), and divided by the global sum(mask) inside the
+    optimiser kernel, so the update equals the single-process update on the concatenated batch.
+    """
+
+    def __init__(self, model, scorer, n_samples=5, start_learning_rate=1e-6, decay_steps=1000, clip_norm=5.0, seed=2024,
+                 dropout=True, wemb_slice_norm=True):
+        self.model, self.scorer, self.K = model, scorer, int(n_samples)
+        self.lr0, self.decay_steps, self.clip = start_learning_rate, decay_steps, clip_norm
+        self.seed, self.dropout, self.wemb_slice_norm = int(seed), dropout, wemb_slice_norm
+        self.global_step = 0
+        self.last = {}
+
+    def step(self, video, video_index):
+        """video: float32 [B, T_v, D] on the device or in (pinned) host memory; video_index: int32 [B] corpus video
+        of each row (reference lists for the reward).  Returns a device tensor [global grad norm, loss]."""
+        m, K = self.model, self.K
+        rank, world = _world()
+        v = video if torch.is_tensor(video) else torch.from_numpy(np.ascontiguousarray(video, dtype=np.float32))
+        v = v.to(m.device, torch.float32, non_blocking=True)
+        vi = torch.as_tensor(video_index).to(m.device, torch.int32, non_blocking=True)
+        B = v.shape[0]
+        it = self.global_step
+        row_base = rank * K * B
+        samp, greedy = m.rollout(v, K, seed=self.seed + it, row_base=row_base)                    # :743-753
+        mask, _ = m.caption_masks(samp)                                                           # :784
+        rows = vi.repeat(K)
+        r = self.scorer.score_ids(samp, rows).to(torch.float32)                                   # :806
+        b = self.scorer.score_ids(greedy, vi).to(torch.float32).repeat(K)                         # :790-795
+        drop_seed = (self.seed * 7919 + it + 1) if self.dropout else 0
+        m.rl_backward(v, samp, mask, r, b, norm=1.0, drop_seed=drop_seed, row_base=row_base)      # :643-650, norm deferred
+        allreduce_gradients(m)
+        lr = exponential_decay(self.lr0, it, self.decay_steps)
+        out = m.optimizer_step(lr, self.clip, wemb_slice_norm=self.wemb_slice_norm, normalize=True)   # :650-652
+        self.global_step += 1
+        self.last = dict(samples=samp, greedy=greedy, rewards=r, baseline=b, mask=mask)
+        return out
+
+
+class XETrainer(object):
+    """Stage-1 trainer: tf_s2vt.py:442-448, 482-497 (label-smoothed XE + L2, Adam 1e-3 halved every 5000, clip 10)."""
+
+    def __init__(self, model, start_learning_rate=1e-3, decay_steps=5000, clip_norm=10.0, seed=2024, dropout=True):
+        self.model, self.lr0, self.decay_steps, self.clip = model, start_learning_rate, decay_steps, clip_norm
+        self.seed, self.dropout, self.global_step = int(seed), dropout, 0
+
+    def step(self, video, captions, mask):
+        m = self.model
+        rank, world = _world()
+        it = self.global_step
+        drop_seed = (self.seed * 7919 + it + 1) if self.dropout else 0
+        n = captions.shape[0] if hasattr(captions, 'shape') else len(captions)
+        loss = m.xe_backward(video, captions, mask, drop_seed=drop_seed, row_base=rank * n).clone()
+        if world > 1:   # every rank holds an equal share of the batch: average the per-rank objectives
+            allreduce_gradients(m)
+            m.grads.mul_(1.0 / world)
+        m.optimizer_step(exponential_decay(self.lr0, it, self.decay_steps), self.clip, wemb_slice_norm=False)
+        self.global_step += 1
+        return loss
+
+
+def greedy_decode_all(model, features_by_video, batch_size):
+    """evaluation() loop (reinforcement_multisampling_tf_s2vt.py:969-976): greedy ids for every video, in chunks."""
+    vids = list(features_by_video)
+    out = {}
+    for i in range(0, len(vids), batch_size):
+        chunk = vids[i:i + batch_size]
+        feats = np.stack([features_by_video[v] for v in chunk]).astype(np.float32)
+        ids = model.greedy(feats).cpu().numpy()
+        for v, row in zip(chunk, ids):
+            out[v] = row
+    return out

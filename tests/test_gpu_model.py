@@ -251,7 +251,7 @@ def test_optimizer_step_matches_tf_adam():
     for step in range(2):
         lr = M.exponential_decay(1e-3, step, 1)
         m.rl_backward(video, cap, mask, r, b)
-        gn = m.optimizer_step(lr, clip, wemb_slice_norm=True).item()
+        gn = m.optimizer_step(lr, clip, wemb_slice_norm=True)[0].item()
         _, grads, aux = M.rl_objective(p, vid_rows, cap, mask, r, b)
         clipped, ref_gn = M.clip_by_global_norm(grads, clip, emb_slice_sqnorm=aux['emb_slice_sqnorm'])
         assert ref_gn > clip
