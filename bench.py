@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--ref-videos', type=int, default=8, help='videos per step of the CPU reference arm / cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='timed region only (for ncu launch lists): no e2e / roofline / CPU passes')
     return ap.parse_args()
 
 
@@ -267,6 +268,11 @@ def run_b200(args):
     launches = model.launch_count() - l0 + 2 * args.steps          # + 2 CIDEr-D kernels per step (launched outside the handle)
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'videos/s', 'ms_per_step': ms / args.steps, 'gpu_launches': int(launches),
+                              'quick': True}), flush=True)
+        return
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(args.steps, step_e2e)

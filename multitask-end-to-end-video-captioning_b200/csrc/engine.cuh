@@ -55,6 +55,7 @@ struct s2vt_handle {
     struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
+    void* tc_cache = nullptr;             // tc::MapCache (TMA tensor maps keyed by pointer / shape)
     // variable indices
     int iWemb, iWe, ibe, iWo, ibo, iW1, ib1, iW2, ib2, iAW, iAb;
     mutable std::string err;

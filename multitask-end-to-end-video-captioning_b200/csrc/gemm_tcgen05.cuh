@@ -1,0 +1,243 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] . B[N,K]^T, bf16 operands (K-major), fp32 accumulation in TMEM.
+//
+// One CTA computes one 128 x BN output tile:
+//   warp 0 (one lane)  : TMA producer  -- cp.async.bulk.tensor.2d of the A (128x64) and B (BNx64) K-blocks, 128B swizzle,
+//                        rows beyond M are zero-filled by the tensor map (no guards in the kernel)
+//   warp 1 (one lane)  : MMA issuer    -- tcgen05.mma.cta_group::1.kind::f16, 4 x (K=16) per K-block, accumulator in TMEM;
+//                        tcgen05.commit releases each smem stage and finally signals the epilogue
+//   warps 2..5         : TMEM -> registers (tcgen05.ld 32x32b) -> fp32 tile in shared memory
+//   all 6 warps        : the same epilogue functors as the other mainloops (EpiStore / EpiGradStore / EpiLstmFwd / EpiLstmBwd)
+// Every mbarrier wait is bounded (trap after ~2 s) so a protocol bug cannot hang the GPU.
+#pragma once
+#include <cuda.h>
+
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int BM = 128, BK = 64, NTHREADS = 192;
+
+template <int BN_>
+struct Cfg {
+    static constexpr int BM = tc::BM, BN = BN_, BK = tc::BK, NTHREADS = tc::NTHREADS;
+    static constexpr int LDC = BN + 4;
+    static constexpr int STAGES = BN >= 128 ? 5 : 4;   // BN <= 64: <= 98 KB per CTA so two CTAs share an SM
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int EPI_BYTES = BM * LDC * 4;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) + BAR_BYTES + 1024;   // + alignment slack
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;   // power of two >= 32
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6), a/b_format BF16 [7,10)/[10,13),
+    // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), done = 0;
+    long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) { printf("s2vt: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+// K-major, 128-byte swizzle smem matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO=1 [16,30),
+// SBO = 1024 B >> 4 = 64 [32,46) (stride between 8-row groups), version 1 at [46,48), SWIZZLE_128B = 2 at [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int K,
+                                                           typename Epi::Params ep) {
+    using C = Cfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024 B alignment
+    constexpr int MAIN = C::PIPE_BYTES > C::EPI_BYTES ? C::PIPE_BYTES : C::EPI_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + MAIN);
+    uint64_t* empty = full + C::STAGES;
+    uint64_t* tmem_full = empty + C::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* Cs = reinterpret_cast<float*>(smem);   // aliases the pipeline buffers once every MMA has retired
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * C::BM, n0 = blockIdx.x * BN;
+    const int KB = K / C::BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation is warp-wide; the same warp frees it at the end
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % C::STAGES;
+                if (kb >= C::STAGES) mbar_wait(empty + s, ((kb / C::STAGES) - 1) & 1);
+                mbar_expect_tx(full + s, C::STAGE_BYTES);
+                unsigned char* a = smem + s * C::STAGE_BYTES;
+                tma_load_2d(a, &mapA, full + s, kb * C::BK, m0);
+                tma_load_2d(a + C::A_BYTES, &mapB, full + s, kb * C::BK, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % C::STAGES;
+                mbar_wait(full + s, (kb / C::STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a = smem_u32(smem + s * C::STAGE_BYTES);
+                const uint64_t adesc = make_desc(a), bdesc = make_desc(a + C::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < C::BK / 16; ++k)   // +32 bytes (>>4 = 2) per K=16 step inside the 128-byte swizzle atom
+                    mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (kb | k) != 0);
+                mma_commit(empty + s);                  // implies tcgen05.fence::before_thread_sync
+            }
+            mma_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                         // a warp may only touch TMEM lanes [32 (warp % 4), +32)
+        const int row = q * 32 + lane;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(Cs + row * C::LDC + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    Epi::template apply<C>(ep, Cs, m0, n0);
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side: tensor maps ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr; int rows, cols, ld, box_rows;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        h ^= std::hash<long long>()(((long long)k.rows << 32) ^ k.cols) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+        h ^= std::hash<long long>()(((long long)k.ld << 32) ^ k.box_rows) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+        return h;
+    }
+};
+typedef std::unordered_map<MapKey, CUtensorMap, MapKeyHash> MapCache;
+
+// bf16 row-major [rows, cols] with row stride ld elements; box = 64 columns x box_rows rows, 128-byte swizzle, zero fill.
+inline const CUtensorMap* get_map(MapCache& cache, const void* ptr, int rows, int cols, int ld, int box_rows) {
+    MapKey key = {ptr, rows, cols, ld, box_rows};
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return nullptr;
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nullptr;
+    return &cache.emplace(key, m).first->second;
+}
+
+template <int BN, class Epi>
+inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K,
+                          const typename Epi::Params& ep) {
+    if (M <= 0) return cudaSuccess;
+    using C = Cfg<BN>;
+    if (cache.size() > 32768) cache.clear();   // before either lookup: element pointers stay valid across inserts, not across clear
+    const CUtensorMap* ma = get_map(cache, A, M, K, lda, BM);
+    const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN);
+    if (!ma || !mb) return cudaErrorInvalidValue;
+    auto kern = gemm_tc_kernel<BN, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid(N / BN, (M + BM - 1) / BM);
+    kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(*ma, *mb, K, ep);
+    return cudaGetLastError();
+}
+
+}  // namespace tc

@@ -9,7 +9,10 @@
 //   logits   : out2 . embed_word_W + b                      [per step in rollouts, batched when teacher forced]
 //   backward : mirror image; weight gradients as batched GEMMs over the stashed per-step gate gradients.
 #include "engine.cuh"
+#include <type_traits>
+
 #include "gemm.cuh"
+#include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 
 template <typename T>
@@ -151,7 +154,10 @@ extern "C" int s2vt_create(const s2vt_config* cfg, s2vt_handle** out) {
     return S2VT_OK;
 }
 
-extern "C" void s2vt_destroy(s2vt_handle* h) { delete h; }
+extern "C" void s2vt_destroy(s2vt_handle* h) {
+    if (h && h->tc_cache) delete static_cast<tc::MapCache*>(h->tc_cache);
+    delete h;
+}
 extern "C" const char* s2vt_last_error(const s2vt_handle* h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" size_t s2vt_num_params(const s2vt_handle* h) { return h->P; }
 extern "C" size_t s2vt_state_bytes(const s2vt_handle* h) { return h->state_bytes; }
@@ -239,7 +245,18 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
         cudaEventRecord(rec.a, st);
     }
     h->launches++;
-    CUDA_TRY(h, (launch_gemm<T, Cfg, Epi>(st, (const T*)A, lda, (const T*)B, ldb, M, N, K, ep)));
+    bool done = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC) {   // tcgen05 + TMA + TMEM path (default for bf16)
+            if (!h->tc_cache) h->tc_cache = new tc::MapCache();
+            tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
+            if (Cfg::BM >= 128) CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep)));
+            else if (M > 128 && N > 1024) CUDA_TRY(h, (tc::launch<64, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep)));
+            else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep)));
+            done = true;
+        }
+    }
+    if (!done) CUDA_TRY(h, (launch_gemm<T, Cfg, Epi>(st, (const T*)A, lda, (const T*)B, ldb, M, N, K, ep)));
     if (h->prof) { cudaEventRecord(rec.b, st); h->prof_recs.push_back(rec); }
     return 0;
 }
