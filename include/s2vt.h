@@ -104,7 +104,8 @@ int s2vt_teacher_forward(s2vt_handle* h, const float* video, int B, const int32_
                          uint32_t row_base, float* logp_out, float* logits_out, s2vt_stream st);
 /* REINFORCE objective and its gradient (:643-650): sum_loss = -sum(logp*mask*(rewards-base_line)) / norm.
  * norm <= 0 means sum(mask) of this call; pass the global sum for data-parallel runs.  Overwrites s2vt_grads()
- * (scaled by grad_scale, 1 for the plain objective, (1-lambda) for the stage-3 mixes) and writes loss_out[0] (device). */
+ * (scaled by grad_scale, 1 for the plain objective, (1-lambda) for the stage-3 mixes) and writes
+ * loss_out[0] = grad_scale * sum_loss (device); with accumulate != 0 both gradients and loss_out[0] are added to. */
 int s2vt_rl_backward(s2vt_handle* h, const float* video, int B, const int32_t* captions, const float* mask, const float* rewards,
                      const float* base_line, int N, float norm, float grad_scale, int accumulate, uint64_t drop_seed, uint32_t row_base,
                      float* loss_out, s2vt_stream st);

@@ -1,0 +1,212 @@
+"""Entry points behind the reference-named scripts at the repo root (`tf_s2vt.py`, `reinforcement_multisampling_tf_s2vt.py`,
+`reinforce_multitask_e2e_attribute_s2vt.py`, `final_beam_search.py`, `e2e_beam_search.py`).
+
+The reference scripts take `--task {train,test,evaluate} --gpu N` and keep every other setting as a module-level
+constant edited in place (tf_s2vt.py:275-320).  Here those constants are flags whose defaults are the reference values.
+Under `torchrun` (one process per GPU) training is data parallel over NCCL.
+"""
+import argparse
+import json
+import os
+import random
+import time
+
+import numpy as np
+
+
+def build_parser(description, defaults):
+    ap = argparse.ArgumentParser(description=description)
+    ap.add_argument('--task', default=defaults.get('task', 'train'), choices=['train', 'test', 'evaluate'], help='tf_s2vt.py:27-37')
+    ap.add_argument('--gpu', type=int, default=0, help='device index (tf.device("/gpu:N"), tf_s2vt.py:702); LOCAL_RANK wins under torchrun')
+    ap.add_argument('--net', default=None); ap.add_argument('--dataset', default=None)      # parsed and never read by the reference
+    ap.add_argument('--tg', default=None); ap.add_argument('--ft', default=None)
+    d = dict(video_train_feature_file='data/msvd_train_features.txt', video_test_feature_file='data/msvd_test_features.txt',
+             video_train_sent_file='msvd_sents_train_noval_lc_nopunc.txt', video_test_sent_file='msvd_sents_test_lc_nopunc.txt',
+             vocabulary_file='msvd_vocabulary1.txt', model_path='models', model_name='s2vt_model', restore=None, out_file='captions.txt',
+             dim_image=1536, lstm_dim=1000, word_dim=500, n_video_lstm_step=5, n_caption_lstm_step=35, n_epochs=30, batch_size=64,
+             start_learning_rate=1e-3, decay_steps=5000, clip_norm=10.0, dropout_rate=0.9, decay_value=5e-5, seed_num=4,
+             n_samples=8, beam_size=3, length_normalization_factor=0.0, alpha=0.5, precision='bf16', max_iters=0)
+    d.update({k: v for k, v in defaults.items() if k != 'task'})
+    for k, v in d.items():
+        ap.add_argument('--' + k, type=(type(v) if v is not None else str), default=v)
+    return ap
+
+
+def _setup(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', str(args.gpu)))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank = dist.get_rank() if world > 1 else 0
+    random.seed(args.seed_num + rank); np.random.seed(args.seed_num + rank)
+    return rank, world
+
+
+def _vocab_and_model(args, pkg, max_rows_factor=1, beam=1, n_attributes=0):
+    vocabulary = pkg.text.read_vocabulary(args.vocabulary_file)
+    wordtoix, ixtoword = pkg.text.preProBuildWordVocab(vocabulary, word_count_threshold=0)
+    os.makedirs('./new_vocab1_data', exist_ok=True)                                   # tf_s2vt.py:417-419
+    np.save('./new_vocab1_data/wordtoix', wordtoix); np.save('./new_vocab1_data/ixtoword', ixtoword)
+    model = pkg.Video_Caption_Generator(dim_image=args.dim_image, n_words=len(wordtoix), word_dim=args.word_dim, lstm_dim=args.lstm_dim,
+                                        batch_size=args.batch_size, n_lstm_steps=args.n_video_lstm_step + args.n_caption_lstm_step,
+                                        n_video_lstm_step=args.n_video_lstm_step, n_caption_lstm_step=args.n_caption_lstm_step,
+                                        bias_init_vector=None, decay_value=args.decay_value, dropout_rate=args.dropout_rate,
+                                        beam_size=beam, n_attributes=n_attributes, precision=args.precision, max_videos=args.batch_size,
+                                        max_rows=args.batch_size * max_rows_factor, seed=args.seed_num)
+    if args.restore:
+        restored, _ = pkg.checkpoint.optimistic_restore(model, args.restore)
+        print('restored %d variables from %s' % (len(restored), args.restore))
+    return wordtoix, ixtoword, model
+
+
+def _batches(n, bs, rank, world):
+    """zip(range(0, n - bs, bs), range(bs, n, bs)) (tf_s2vt.py:482, drops the tail, Q6), strided over ranks."""
+    starts = list(range(0, n - bs, bs))
+    return starts[rank::world]
+
+
+def run_xe(args):
+    """tf_s2vt.py train()/evaluation()/test(): stage-1 cross-entropy S2VT."""
+    import s2vt_b200 as pkg
+    rank, world = _setup(args)
+    wordtoix, ixtoword, model = _vocab_and_model(args, pkg)
+    if args.task in ('evaluate', 'test'):
+        return _decode_task(args, pkg, model, wordtoix, ixtoword, beam=False)
+    train_captions, train_features = pkg.text.get_video_feature_caption_pair(args.video_train_sent_file, args.video_train_feature_file)
+    trainer = pkg.trainer.XETrainer(model, args.start_learning_rate, args.decay_steps, args.clip_norm, seed=args.seed_num)
+    it = 0
+    for epoch in range(args.n_epochs):
+        index = list(range(len(train_captions))); random.shuffle(index)
+        for start in _batches(len(index), args.batch_size, rank, world):
+            t0 = time.time()
+            rows = index[start:start + args.batch_size]
+            vids, sents = train_captions[rows, 0], train_captions[rows, 1].tolist()
+            feats = np.stack([train_features[v] for v in vids])
+            ids, mask = pkg.text.sentence_padding_toix(sents, wordtoix, args.n_caption_lstm_step)
+            loss = trainer.step(feats, ids, mask)
+            if rank == 0:
+                print('idx: ', start, ' Epoch: ', epoch, ' loss: ', float(loss[0].item()), ' Elapsed time: ', str(time.time() - t0))
+            it += 1
+            if args.max_iters and it >= args.max_iters:
+                break
+        if rank == 0:
+            pkg.checkpoint.save(model, os.path.join(args.model_path, '%s-%d' % (args.model_name, epoch)), trainer.global_step)
+        if args.max_iters and it >= args.max_iters:
+            break
+
+
+def run_rl(args):
+    """reinforcement_multisampling_tf_s2vt.py train(): stage-2 K-sample REINFORCE with CIDEr-D reward and greedy baseline."""
+    import s2vt_b200 as pkg
+    rank, world = _setup(args)
+    wordtoix, ixtoword, model = _vocab_and_model(args, pkg, max_rows_factor=args.n_samples)
+    if args.task in ('evaluate', 'test'):
+        return _decode_task(args, pkg, model, wordtoix, ixtoword, beam=False)
+    train_captions, train_features = pkg.text.get_video_feature_caption_pair(args.video_train_sent_file, args.video_train_feature_file)
+    by, order = pkg.text.group_by_video(train_captions)
+    vindex = {v: i for i, v in enumerate(order)}
+    scorer = pkg.cider.CiderD([by[v] for v in order], wordtoix)                        # CiderD(df=<train corpus>), cider_evaluation.py:12
+    trainer = pkg.trainer.ReinforceTrainer(model, scorer, n_samples=args.n_samples, start_learning_rate=args.start_learning_rate,
+                                           decay_steps=args.decay_steps, clip_norm=args.clip_norm, seed=args.seed_num)
+    it = 0
+    for epoch in range(args.n_epochs):
+        index = list(range(len(train_captions))); random.shuffle(index)
+        for start in _batches(len(index), args.batch_size, rank, world):
+            t0 = time.time()
+            vids = train_captions[index[start:start + args.batch_size], 0]             # a batch indexes caption rows (R3)
+            feats = np.stack([train_features[v] for v in vids])
+            out = trainer.step(feats, np.array([vindex[v] for v in vids], dtype=np.int32))
+            if rank == 0:
+                print('idx: ', start, ' Epoch: ', epoch, ' loss: ', float(out[1].item()), ' Elapsed time: ', str(time.time() - t0))
+            it += 1
+            if args.max_iters and it >= args.max_iters:
+                break
+        if rank == 0:
+            pkg.checkpoint.save(model, os.path.join(args.model_path, '%s-%d' % (args.model_name, epoch)), trainer.global_step)
+        if args.max_iters and it >= args.max_iters:
+            break
+
+
+def run_stage3(args):
+    """reinforce_multitask_e2e_attribute_s2vt.py on precomputed features: sum_loss = -(1-lambda) RL + lambda XE (:850),
+    lambda = --alpha (0.5), single sample per video, clip 5 (:856)."""
+    import torch
+    import s2vt_b200 as pkg
+    rank, world = _setup(args)
+    wordtoix, ixtoword, model = _vocab_and_model(args, pkg, max_rows_factor=1)
+    if args.task in ('evaluate', 'test'):
+        return _decode_task(args, pkg, model, wordtoix, ixtoword, beam=False)
+    train_captions, train_features = pkg.text.get_video_feature_caption_pair(args.video_train_sent_file, args.video_train_feature_file)
+    by, order = pkg.text.group_by_video(train_captions)
+    vindex = {v: i for i, v in enumerate(order)}
+    scorer = pkg.cider.CiderD([by[v] for v in order], wordtoix)
+    lam, it, step = args.alpha, 0, 0
+    for epoch in range(args.n_epochs):
+        index = list(range(len(train_captions))); random.shuffle(index)
+        for start in _batches(len(index), args.batch_size, rank, world):
+            rows = index[start:start + args.batch_size]
+            vids, sents = train_captions[rows, 0], train_captions[rows, 1].tolist()
+            feats = torch.from_numpy(np.stack([train_features[v] for v in vids])).to(model.device)
+            vi = torch.tensor([vindex[v] for v in vids], dtype=torch.int32, device=model.device)
+            gt_ids, gt_mask = pkg.text.sentence_padding_toix(sents, wordtoix, args.n_caption_lstm_step)
+            samp, greedy = model.rollout(feats, 1, seed=args.seed_num + step, row_base=rank * len(rows))
+            mask, _ = model.caption_masks(samp)
+            r = scorer.score_ids(samp, vi).float(); b = scorer.score_ids(greedy, vi).float()
+            rl = model.rl_backward(feats, samp, mask, r, b, grad_scale=1.0 - lam, drop_seed=step + 1).clone()
+            xe = model.xe_backward(feats, gt_ids, gt_mask, grad_scale=lam, accumulate=True, drop_seed=step + 1)
+            pkg.trainer.allreduce_gradients(model)
+            if world > 1:
+                model.grads.mul_(1.0 / world)
+            lr = pkg.trainer.exponential_decay(args.start_learning_rate, step, args.decay_steps)
+            model.optimizer_step(lr, args.clip_norm, wemb_slice_norm=False)
+            step += 1; it += 1
+            if rank == 0:
+                print('idx: ', start, ' Epoch: ', epoch, ' loss: ', float(xe[0].item()))
+            if args.max_iters and it >= args.max_iters:
+                break
+        if rank == 0:
+            pkg.checkpoint.save(model, os.path.join(args.model_path, '%s-%d' % (args.model_name, epoch)), step)
+        if args.max_iters and it >= args.max_iters:
+            break
+
+
+def _decode_task(args, pkg, model, wordtoix, ixtoword, beam):
+    """--task test (write captions, tf_s2vt.py:565-609 / final_beam_search.py:504-555) and --task evaluate (greedy or beam
+    decode of the test split + CIDEr-D against the test references)."""
+    test_captions, test_features = pkg.text.get_video_feature_caption_pair(args.video_test_sent_file, args.video_test_feature_file)
+    by, order = pkg.text.group_by_video(test_captions)
+    vids = [v for v in test_features]
+    t0 = time.time()
+    hyps = {}
+    for i in range(0, len(vids), args.batch_size):
+        chunk = vids[i:i + args.batch_size]
+        feats = np.stack([test_features[v] for v in chunk]).astype(np.float32)
+        if beam:
+            sent, lens, lp, sc = model.beam_search(feats, args.beam_size, args.length_normalization_factor)
+            ids = sent.cpu().numpy()
+        else:
+            ids = model.greedy(feats).cpu().numpy()
+        for v, s in zip(chunk, pkg.text.decode_captions(ids, ixtoword)):
+            hyps[v] = s
+    print('generation time: ', time.time() - t0)
+    with open(args.out_file, 'w') as f:
+        for v in vids:
+            f.write(v + '\t' + hyps[v] + '\n')
+    if args.task == 'evaluate':
+        keep = [v for v in vids if v in by]
+        scorer = pkg.cider.CiderD([by[v] for v in keep], wordtoix)
+        score = float(scorer.score_strings([hyps[v] for v in keep], np.arange(len(keep), dtype=np.int32)).mean().item())
+        print(json.dumps({'CIDEr-D': score, 'videos': len(keep)}))
+        return score
+    return hyps
+
+
+def run_beam(args):
+    """final_beam_search.py / e2e_beam_search.py --task test|evaluate on precomputed features."""
+    import s2vt_b200 as pkg
+    _setup(args)
+    wordtoix, ixtoword, model = _vocab_and_model(args, pkg, beam=args.beam_size)
+    return _decode_task(args, pkg, model, wordtoix, ixtoword, beam=True)

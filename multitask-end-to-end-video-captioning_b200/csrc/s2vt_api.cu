@@ -568,9 +568,9 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     softmax_rows_kernel<T><<<Tc * N, ROW_THREADS, 0, st>>>(p.logits, Vp, V, Vp, p.target, p.ca, p.cb, p.cc, p.logp, p.sumlsm, p.dlogits, logp_out, N, Tc);
     KCHECK(h);
     loss_reduce_kernel<<<1, 256, 0, st>>>(mode, p.logp, p.sumlsm, mask, rewards, base_line, N, Tc, nrm, ls, V, h->scal + 4, nullptr); KCHECK(h);
-    if (loss_out) {
-        if (accumulate) { add_scaled_scalar_kernel<<<1, 1, 0, st>>>(loss_out, h->scal + 4, grad_scale); KCHECK(h); }
-        else CUDA_TRY(h, cudaMemcpyAsync(loss_out, h->scal + 4, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (loss_out) {   // loss_out[0] (+)= grad_scale * objective, so a sequence of accumulate calls yields the mixed loss
+        if (!accumulate) CUDA_TRY(h, cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+        add_scaled_scalar_kernel<<<1, 1, 0, st>>>(loss_out, h->scal + 4, grad_scale); KCHECK(h);
     }
     add_scaled_scalar_kernel<<<1, 1, 0, st>>>(h->grads + h->P + 1, h->scal + 4, grad_scale); KCHECK(h);   // aux[1] = loss (summed by the DP allreduce)
     if (mode == 0) { add_scaled_scalar_kernel<<<1, 1, 0, st>>>(h->grads + h->P + 2, h->scal + 1, 1.f); KCHECK(h); }   // aux[2] = sum(mask)
