@@ -27,7 +27,7 @@ def _inputs():
 def _model(p):
     import s2vt_b200
     m = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=2 * B,
-                                          n_video_lstm_step=Tv, n_caption_lstm_step=Tc, dropout_rate=0.9, precision='fp32', max_videos=2 * B,
+                                          n_video_lstm_step=Tv, n_caption_lstm_step=Tc, dropout_rate=0.9, precision='fp32', max_videos=2 * K * B,
                                           max_rows=2 * K * B)
     m.load_variables(p)
     return m
