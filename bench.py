@@ -283,6 +283,7 @@ def run_b200(args):
     barrier()
     for _ in range(args.steps):
         step_dev()
+    shapes = model.profile_shapes()
     prof = model.profile_read()
     model.profile(False)
     loss = float(trainer.step(feats_dev, vidx_dev)[1].item())
@@ -306,6 +307,8 @@ def run_b200(args):
            'clocks': clocks, 'e2e': {'value': e2e, 'unit': 'videos/s', 'h2d_bytes_per_step': int(feats_host.numel() * 4 + vidx_host.numel() * 4),
                                      'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps},
            'gpu_launches': int(launches), 'loss': loss,
+           'gemm_shapes': [{'class': 'batched' if c == 0 else 'step', 'M': M_, 'N': N_, 'K': K_, 'launches_per_step': n_ / args.steps,
+                            'us_per_launch': 1e3 * ms_ / n_, 'ms_per_step': ms_ / args.steps} for c, M_, N_, K_, ms_, n_ in sorted(shapes, key=lambda x: -x[4])],
            'roofline': {'kernel': 'gemm_kernel<bf16, 128x128x32 tiles> (batched GEMMs: projections, vocab logits, weight gradients)',
                         'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf if peak_tf else None,
                         'traffic': None, 'peak_source': peak_src, 'launches_per_step': bn / args.steps, 'ms_per_step': bms / args.steps,

@@ -83,6 +83,11 @@ int s2vt_load_param(s2vt_handle* h, const char* tf_name, const float* src_host, 
  * Must follow any direct write to s2vt_params(); s2vt_optimizer_step calls it itself. */
 int s2vt_refresh(s2vt_handle* h, s2vt_stream st);
 
+/* Opt-in: let the next s2vt_rl_backward / s2vt_xe_backward reuse the frame projection and LSTM1 forward that the
+ * preceding s2vt_rollout computed for the SAME video buffer (LSTM1 never sees a word and its state is not affected by the
+ * output dropout, so the two passes are identical).  The caller promises not to modify the buffer in between. */
+int s2vt_set_reuse_frontend(s2vt_handle* h, int enable);
+
 /* ---- decoding -------------------------------------------------------------------------------------------------
  * build_sampler (:342-391): greedy argmax decode, no early stop.   video fp32 [B, T_v, dim_image] -> ids int32 [B, T_c] */
 int s2vt_greedy(s2vt_handle* h, const float* video, int B, int32_t* ids_out, s2vt_stream st);
@@ -133,6 +138,10 @@ int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step,
 long long s2vt_launch_count(const s2vt_handle* h);
 int s2vt_profile(s2vt_handle* h, int enable);
 int s2vt_profile_read(s2vt_handle* h, double* ms_out, double* flops_out, long long* launches_out);
+/* per (class, M, N, K) totals of the current records (call before s2vt_profile_read); returns the number of rows */
+/* debug: per-launch phase timestamps (%globaltimer) of CTA (0,0) of every tcgen05 GEMM; NULL disables */
+int s2vt_debug_probe(void* device_buffer);
+int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* K, double* ms, long long* count);
 
 /* ---- beam search: beam_probability + the host loop of final_beam_search.py:202-294 / e2e_beam_search.py:235-344,
  * batched over B videos on the device, semantics B1-B7 of SURVEY.md.

@@ -39,6 +39,7 @@ SIGNATURES = {
     's2vt_variable_info': (_i32, [_vp, _i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.POINTER(_i64 * 2), C.POINTER(_i32)]),
     's2vt_load_param': (_i32, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i32, _vp]),
     's2vt_refresh': (_i32, [_vp, _vp]),
+    's2vt_set_reuse_frontend': (_i32, [_vp, _i32]),
     's2vt_greedy': (_i32, [_vp, _vp, _i32, _vp, _vp]),
     's2vt_rollout': (_i32, [_vp, _vp, _i32, _i32, _u64, _u32, _vp, _vp, _vp]),
     's2vt_caption_masks': (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
@@ -50,6 +51,8 @@ SIGNATURES = {
     's2vt_launch_count': (C.c_longlong, [_vp]),
     's2vt_profile': (_i32, [_vp, _i32]),
     's2vt_profile_read': (_i32, [_vp, _vp, _vp, _vp]),
+    's2vt_debug_probe': (_i32, [_vp]),
+    's2vt_profile_shapes': (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     's2vt_beam_search': (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     's2vt_beam_init': (_i32, [_vp, _vp, _vp, _vp, _vp]),
     's2vt_beam_step': (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),

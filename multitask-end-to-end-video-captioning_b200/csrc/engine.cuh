@@ -52,10 +52,15 @@ struct s2vt_handle {
     // instrumentation (bench.py): launch counter and optional CUDA-event brackets around GEMM launches
     mutable long long launches = 0;
     bool prof = false;
-    struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
+    struct ProfRec { cudaEvent_t a, b; double flops; int cls; int M, N, K; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
-    void* tc_cache = nullptr;             // tc::MapCache (TMA tensor maps keyed by pointer / shape)
+    void* tc_cache = nullptr;
+    // LSTM1 forward cache shared by s2vt_rollout and the following training call (opt-in, s2vt_set_reuse_frontend)
+    bool reuse_front = false, front_valid = false;
+    int front_B = 0; const float* front_video = nullptr;
+    // internal side stream for the LSTM1 backward chain (fork/join inside one call; invisible to the caller)
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;             // tc::MapCache (TMA tensor maps keyed by pointer / shape)
     // variable indices
     int iWemb, iWe, ibe, iWo, ibo, iW1, ib1, iW2, ib2, iAW, iAb;
     mutable std::string err;

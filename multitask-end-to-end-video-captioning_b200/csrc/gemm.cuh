@@ -185,9 +185,24 @@ struct Mainloop<float, Cfg> {
 // -----------------------------------------------------------------------------------------------------------------
 // epilogues
 // -----------------------------------------------------------------------------------------------------------------
+// 8 consecutive values -> compute dtype, vector stores (dst 16-byte aligned)
+__device__ __forceinline__ void store8(float* dst, const float* v) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* dst, const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(dst) = u;
+}
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 // out = acc (+ bias[col]) (+ old out if accumulate); written as fp32 and/or compute dtype.
 template <typename T>
 struct EpiStore {
+    static constexpr bool kDirect = false;
     struct Params {
         float* outF; T* outT; int ldo; const float* bias; int M; int accumulate;
     };
@@ -212,6 +227,7 @@ struct EpiStore {
 // gate_h > 0 : columns are in packed gate order (c = 4u+g) and map to the TF order g*gate_h + u (u < gate_h).
 // gate_h == 0: identity columns, valid while c < ncols.   Rows valid while r < nrows.
 struct EpiGradStore {
+    static constexpr bool kDirect = false;
     struct Params {
         float* grad; int ldg; int nrows; int ncols; int gate_h; float scale;
     };
@@ -242,6 +258,14 @@ struct EpiGradStore {
 //   pre = acc + bias + add0[row0(row)] + add1[tok[row]] ; i,j,f,o -> c' = c*sig(f+1) + sig(i)*tanh(j) ; h' = tanh(c')*sig(o)
 template <typename T>
 struct EpiLstmFwd {
+    // Direct form (tcgen05 path): a thread owns one accumulator row and a chunk of 32 packed gate columns = 8 whole
+    // units, so the cell is evaluated straight from registers; `prefetch` issues every global load of the chunk before
+    // the accumulator is ready (the epilogue warps are idle during the mainloop).
+    static constexpr bool kDirect = true;
+    struct Pre { float4 add[8]; float4 c[2]; };
+    struct Params;
+    __device__ static void prefetch(const Params& p, int gr, int gc, Pre& pre);
+    __device__ static void direct(const Params& p, int gr, int gc, const float* v, const Pre& pre);
     struct Params {
         int M; int Hp;
         const float* bias;                 // [4Hp] packed
@@ -290,6 +314,56 @@ struct EpiLstmFwd {
     }
 };
 
+template <typename T>
+__device__ __forceinline__ void EpiLstmFwd<T>::prefetch(const Params& p, int gr, int gc, Pre& pre) {
+    if (gr >= p.M) return;
+    const size_t G = 4 * (size_t)p.Hp;
+    const float4* b = reinterpret_cast<const float4*>(p.bias + gc);
+    const float4* a0 = p.add0 ? reinterpret_cast<const float4*>(p.add0 + (size_t)(p.add0_mod > 0 ? gr % p.add0_mod : gr) * G + gc) : nullptr;
+    const float4* a1 = p.add1 ? reinterpret_cast<const float4*>(p.add1 + (size_t)p.tok[gr] * G + gc) : nullptr;
+    const float4* c = reinterpret_cast<const float4*>(p.c_prev + (size_t)gr * p.Hp + (gc >> 2));
+    float4 x0[8], x1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pre.add[j] = b[j]; x0[j] = a0 ? a0[j] : make_float4(0.f, 0.f, 0.f, 0.f); x1[j] = a1 ? a1[j] : make_float4(0.f, 0.f, 0.f, 0.f); }
+    pre.c[0] = c[0]; pre.c[1] = c[1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pre.add[j] = f4add(pre.add[j], f4add(x0[j], x1[j]));
+}
+template <typename T>
+__device__ __forceinline__ void EpiLstmFwd<T>::direct(const Params& p, int gr, int gc, const float* v, const Pre& pre) {
+    if (gr >= p.M) return;
+    const size_t G = 4 * (size_t)p.Hp;
+    const int u0 = gc >> 2;
+    const float cp[8] = {pre.c[0].x, pre.c[0].y, pre.c[0].z, pre.c[0].w, pre.c[1].x, pre.c[1].y, pre.c[1].z, pre.c[1].w};
+    float cn[8], hn[8];
+    float4 gt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float si = sigmoidf_(v[4 * j] + pre.add[j].x), tj = tanhf(v[4 * j + 1] + pre.add[j].y);
+        float sf = sigmoidf_(v[4 * j + 2] + pre.add[j].z + 1.0f), so = sigmoidf_(v[4 * j + 3] + pre.add[j].w);
+        cn[j] = cp[j] * sf + si * tj;
+        hn[j] = tanhf(cn[j]) * so;
+        gt[j] = make_float4(si, tj, sf, so);
+    }
+    const size_t o = (size_t)gr * p.Hp + u0;
+    store8(p.c_out + o, cn);
+    store8(p.h_out + o, hn);
+    if (p.h_outF) store8(p.h_outF + o, hn);
+    if (p.gates_out) {
+        float4* g = reinterpret_cast<float4*>(p.gates_out + (size_t)gr * G + gc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = gt[j];
+    }
+    if (p.hdrop_out) {
+        if (p.keep < 1.0f) {
+            float4 m0 = dropout_mult4(p.seed, p.stream, p.row_base + gr, p.step, u0, p.keep);
+            float4 m1 = dropout_mult4(p.seed, p.stream, p.row_base + gr, p.step, u0 + 4, p.keep);
+            hn[0] *= m0.x; hn[1] *= m0.y; hn[2] *= m0.z; hn[3] *= m0.w; hn[4] *= m1.x; hn[5] *= m1.y; hn[6] *= m1.z; hn[7] *= m1.w;
+        }
+        store8(p.hdrop_out + o, hn);
+    }
+}
+
 // BasicLSTMCell backward for one time step.  dh = dh_rec + dh_ext * dropout ; produces the pre-activation gate
 // gradients (packed order) and dc for the previous step.
 struct LstmBwdArgs {
@@ -326,9 +400,58 @@ __device__ __forceinline__ void lstm_bwd_unit(const LstmBwdArgs& p, T* dg_out, i
 // GEMM form: acc[row, u] = dG(t+1)[row, :] . Wh[u, :]   (N dimension = hidden units)
 template <typename T>
 struct EpiLstmBwd {
+    // Direct form: a thread owns one row and a chunk of 8 hidden units of dh_rec (the accumulator columns are units).
+    static constexpr bool kDirect = true;
+    static constexpr int kUnitsPerChunk = 8;
+    struct Pre { float4 g[8]; float4 cn[2], cp[2], dc[2], dh[2]; };
     struct Params {
         LstmBwdArgs a; T* dg_out;
     };
+    __device__ static void prefetch(const Params& p, int gr, int u0, Pre& pre) {
+        const LstmBwdArgs& a = p.a;
+        if (gr >= a.M) return;
+        const size_t o = (size_t)gr * a.Hp + u0;
+        const float4* g = reinterpret_cast<const float4*>(a.gates + (size_t)gr * 4 * a.Hp + 4 * u0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pre.g[j] = g[j];
+        const float4* cn = reinterpret_cast<const float4*>(a.c_new + o); pre.cn[0] = cn[0]; pre.cn[1] = cn[1];
+        const float4* cp = reinterpret_cast<const float4*>(a.c_prev + o); pre.cp[0] = cp[0]; pre.cp[1] = cp[1];
+        const float4* dc = reinterpret_cast<const float4*>(a.dc + o); pre.dc[0] = dc[0]; pre.dc[1] = dc[1];
+        if (a.dh_ext) { const float4* dh = reinterpret_cast<const float4*>(a.dh_ext + o); pre.dh[0] = dh[0]; pre.dh[1] = dh[1]; }
+        else { pre.dh[0] = pre.dh[1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+    // v: dh_rec of the 8 units
+    __device__ static void direct(const Params& p, int gr, int u0, const float* v, const Pre& pre) {
+        const LstmBwdArgs& a = p.a;
+        if (gr >= a.M) return;
+        const size_t o = (size_t)gr * a.Hp + u0;
+        const float cn[8] = {pre.cn[0].x, pre.cn[0].y, pre.cn[0].z, pre.cn[0].w, pre.cn[1].x, pre.cn[1].y, pre.cn[1].z, pre.cn[1].w};
+        const float cp[8] = {pre.cp[0].x, pre.cp[0].y, pre.cp[0].z, pre.cp[0].w, pre.cp[1].x, pre.cp[1].y, pre.cp[1].z, pre.cp[1].w};
+        const float dcn[8] = {pre.dc[0].x, pre.dc[0].y, pre.dc[0].z, pre.dc[0].w, pre.dc[1].x, pre.dc[1].y, pre.dc[1].z, pre.dc[1].w};
+        float dhx[8] = {pre.dh[0].x, pre.dh[0].y, pre.dh[0].z, pre.dh[0].w, pre.dh[1].x, pre.dh[1].y, pre.dh[1].z, pre.dh[1].w};
+        if (a.dh_ext && a.keep < 1.0f) {
+            float4 m0 = dropout_mult4(a.seed, a.stream, a.row_base + gr, a.step, u0, a.keep);
+            float4 m1 = dropout_mult4(a.seed, a.stream, a.row_base + gr, a.step, u0 + 4, a.keep);
+            dhx[0] *= m0.x; dhx[1] *= m0.y; dhx[2] *= m0.z; dhx[3] *= m0.w; dhx[4] *= m1.x; dhx[5] *= m1.y; dhx[6] *= m1.z; dhx[7] *= m1.w;
+        }
+        float dcp[8], dg[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float si = pre.g[j].x, tj = pre.g[j].y, sf = pre.g[j].z, so = pre.g[j].w;
+            float dh = v[j] + dhx[j];
+            float tc = tanhf(cn[j]);
+            float d_o = dh * tc;
+            float dc = dcn[j] + dh * so * (1.0f - tc * tc);
+            dcp[j] = dc * sf;
+            dg[4 * j] = dc * tj * si * (1.0f - si);
+            dg[4 * j + 1] = dc * si * (1.0f - tj * tj);
+            dg[4 * j + 2] = dc * cp[j] * sf * (1.0f - sf);
+            dg[4 * j + 3] = d_o * so * (1.0f - so);
+        }
+        store8(a.dc + o, dcp);
+        T* d = p.dg_out + (size_t)gr * 4 * a.Hp + 4 * u0;
+        store8(d, dg); store8(d + 8, dg + 8); store8(d + 16, dg + 16); store8(d + 24, dg + 24);
+    }
     template <class Cfg>
     __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
         for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::NTHREADS) {

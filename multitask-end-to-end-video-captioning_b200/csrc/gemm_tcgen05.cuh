@@ -17,13 +17,20 @@
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64, NTHREADS = 192;
+// Debug probe (s2vt_debug_probe): when set, CTA (0,0) of every tcgen05 GEMM launch records %globaltimer at its phase
+// boundaries into slot [launch*8 .. launch*8+7] of the buffer (slot 0 of the buffer is the launch counter).
+__device__ unsigned long long* g_probe = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-template <int BN_>
+constexpr int BM = 128, BK = 64, NTHREADS = 192;   // NTHREADS: staged-epilogue kernels (2 role warps + 4 epilogue warps)
+
+template <int BN_, int NTHREADS_ = tc::NTHREADS>
 struct Cfg {
-    static constexpr int BM = tc::BM, BN = BN_, BK = tc::BK, NTHREADS = tc::NTHREADS;
+    static constexpr int BM = tc::BM, BN = BN_, BK = tc::BK, NTHREADS = NTHREADS_;
     static constexpr int LDC = BN + 4;
-    static constexpr int STAGES = BN >= 128 ? 5 : 4;   // BN <= 64: <= 98 KB per CTA so two CTAs share an SM
+    // BN <= 64 (per-step GEMMs): small enough that CTAs of the NEXT step's kernel (programmatic dependent launch) fit on the
+    // SM beside the running ones: BN=32 -> 100 KB (2 per SM), BN=64 -> 72 KB (3 per SM)
+    static constexpr int STAGES = BN >= 128 ? 6 : (BN >= 64 ? 3 : 5);
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int EPI_BYTES = BM * LDC * 4;
@@ -88,10 +95,51 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN, class Epi>
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int K,
-                                                           typename Epi::Params ep) {
-    using C = Cfg<BN>;
+// One 32-column accumulator chunk through a direct epilogue.  EpiLstmFwd: 32 packed gate columns = one 8-unit call.
+// EpiLstmBwd (kUnitsPerChunk = 8): the 32 columns are 32 units, handled as four 8-unit calls; the operands of the next
+// call are fetched before the current one is computed.
+template <class Epi, class = void> struct DirectTraits { static constexpr int kSub = 32; };
+template <class Epi> struct DirectTraits<Epi, decltype((void)Epi::kUnitsPerChunk)> { static constexpr int kSub = Epi::kUnitsPerChunk; };
+template <class Epi>
+__device__ __forceinline__ void direct_chunk(const typename Epi::Params& ep, int gr, int gc, const float* v, typename Epi::Pre& pre, bool more) {
+    constexpr int SUB = DirectTraits<Epi>::kSub;
+    if constexpr (SUB == 32) {
+        Epi::direct(ep, gr, gc, v, pre);
+        if (more) Epi::prefetch(ep, gr, gc + 32, pre);
+    } else {
+#pragma unroll
+        for (int s = 0; s < 32; s += SUB) {
+            typename Epi::Pre cur = pre;
+            if (s + SUB < 32 || more) Epi::prefetch(ep, gr, gc + s + SUB, pre);
+            Epi::direct(ep, gr, gc + s, v + s, cur);
+        }
+    }
+}
+
+// Epilogue warps: the staged epilogues use 4 (one per TMEM lane quarter); the direct (register) epilogues use one warp per
+// (lane quarter, 32-column chunk) so every thread handles exactly one chunk whose operands were prefetched.
+template <int BN, class Epi> struct Threads {
+    static constexpr int NEPI = Epi::kDirect ? 4 * (BN / 32) : 4;
+    static constexpr int N = 64 + 32 * NEPI;
+};
+
+__device__ __forceinline__ uint32_t cluster_map(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// KS > 1: split-K over a cluster of KS CTAs (cluster dims (1,1,KS), rank = blockIdx.z).  Each CTA accumulates its K range
+// in TMEM; partial tiles are exchanged through distributed shared memory so that CTA r reduces and finishes rows
+// [32r, 32r+32) of the tile (KS == 4): the K loop AND the epilogue are both split four ways.
+template <int BN, class Epi, int KS>
+__global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                                      int K, typename Epi::Params ep) {
+    using C = Cfg<BN, Threads<BN, Epi>::N>;
+    static_assert(KS == 1 || (KS == 4 && Epi::kDirect), "split-K needs a direct epilogue and a cluster of 4");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024 B alignment
     constexpr int MAIN = C::PIPE_BYTES > C::EPI_BYTES ? C::PIPE_BYTES : C::EPI_BYTES;
@@ -100,10 +148,20 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
     uint64_t* tmem_full = empty + C::STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
     float* Cs = reinterpret_cast<float*>(smem);   // aliases the pipeline buffers once every MMA has retired
+    float* recv = reinterpret_cast<float*>(smem + MAIN + C::BAR_BYTES);   // [KS][32][BN] partial tiles from the cluster (KS > 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * C::BM, n0 = blockIdx.x * BN;
-    const int KB = K / C::BK;
+    const int rank = KS > 1 ? (int)blockIdx.z : 0;
+    const int KBL = K / C::BK / KS, kb0 = rank * KBL;   // this CTA's K-blocks
+    __shared__ unsigned long long* probe;
+    if (threadIdx.x == 0) {
+        probe = nullptr;
+        if (g_probe && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+            unsigned long long slot = atomicAdd(g_probe, 1ull);
+            if (slot < 4000) { probe = g_probe + 8 * (slot + 1); probe[0] = gtimer(); probe[6] = ((unsigned long long)(BN + 1000 * KS) << 32) | (unsigned)K; probe[7] = gridDim.x * gridDim.y * gridDim.z; }
+        }
+    }
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -120,52 +178,127 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if constexpr (KS > 1) {   // every CTA of the cluster must be running before its shared memory is written remotely
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    }
+
+    // Programmatic dependent launch: let the next kernel in the stream start its prologue now; the weight (B) tiles of the
+    // first stages never depend on the previous kernel, so they are requested before waiting for it.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int pre = KBL < C::STAGES ? KBL : C::STAGES;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < pre; ++i) {
+            mbar_expect_tx(full + i, C::STAGE_BYTES);
+            tma_load_2d(smem + i * C::STAGE_BYTES + C::A_BYTES, &mapB, full + i, (kb0 + i) * C::BK, n0);
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (probe && threadIdx.x == 0) probe[1] = gtimer();
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % C::STAGES;
-                if (kb >= C::STAGES) mbar_wait(empty + s, ((kb / C::STAGES) - 1) & 1);
-                mbar_expect_tx(full + s, C::STAGE_BYTES);
+            for (int i = 0; i < KBL; ++i) {
+                const int s = i % C::STAGES;
                 unsigned char* a = smem + s * C::STAGE_BYTES;
-                tma_load_2d(a, &mapA, full + s, kb * C::BK, m0);
-                tma_load_2d(a + C::A_BYTES, &mapB, full + s, kb * C::BK, n0);
+                if (i >= C::STAGES) {
+                    mbar_wait(empty + s, ((i / C::STAGES) - 1) & 1);
+                    mbar_expect_tx(full + s, C::STAGE_BYTES);
+                    tma_load_2d(a + C::A_BYTES, &mapB, full + s, (kb0 + i) * C::BK, n0);
+                }
+                tma_load_2d(a, &mapA, full + s, (kb0 + i) * C::BK, m0);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % C::STAGES;
-                mbar_wait(full + s, (kb / C::STAGES) & 1);
+            for (int i = 0; i < KBL; ++i) {
+                const int s = i % C::STAGES;
+                mbar_wait(full + s, (i / C::STAGES) & 1);
+                if (probe && i == 0) probe[2] = gtimer();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a = smem_u32(smem + s * C::STAGE_BYTES);
                 const uint64_t adesc = make_desc(a), bdesc = make_desc(a + C::A_BYTES);
 #pragma unroll
                 for (int k = 0; k < C::BK / 16; ++k)   // +32 bytes (>>4 = 2) per K=16 step inside the 128-byte swizzle atom
-                    mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (kb | k) != 0);
+                    mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (i | k) != 0);
                 mma_commit(empty + s);                  // implies tcgen05.fence::before_thread_sync
             }
             mma_commit(tmem_full);
+            if (probe) probe[3] = gtimer();
         }
         __syncwarp();
     } else {
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int e = warp - 2;
         const int q = warp & 3;                         // a warp may only touch TMEM lanes [32 (warp % 4), +32)
         const int row = q * 32 + lane;
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        if constexpr (Epi::kDirect && KS == 1) {
+            // register epilogue: one 32-column chunk per thread; its operands are fetched while the MMAs are still running
+            const int c0 = (e >> 2) * 32;
+            typename Epi::Pre pre;
+            Epi::prefetch(ep, m0 + row, n0 + c0, pre);
+            mbar_wait(tmem_full, 0);
+            if (probe && threadIdx.x == 64) probe[4] = gtimer();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld32(trow + (uint32_t)c0, v);
+            direct_chunk<Epi>(ep, m0 + row, n0 + c0, v, pre, false);
+        } else if constexpr (Epi::kDirect) {
+            // split-K: final mapping of this thread = row (32 rank + t / (BN/8)), units [8 (t % (BN/8)), +8)
+            constexpr int UPR = BN / 8;                 // 8-unit tasks per row
+            const int t = threadIdx.x - 64;
+            const int frow = t / UPR, fc8 = t % UPR;
+            typename Epi::Pre pre;
+            Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, pre);
+            mbar_wait(tmem_full, 0);
+            if (probe && threadIdx.x == 64) probe[4] = gtimer();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {   // send this warp's 32 x 32 partial (rows of lane quarter q) to CTA q, slot `rank`, 16-byte chunks XOR-swizzled by row
+                const int c0 = (e >> 2) * 32;
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+                const uint32_t base = cluster_map(smem_u32(recv), (uint32_t)q) + (uint32_t)(((rank * 32 + lane) * BN) * 4);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(Cs + row * C::LDC + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 8; ++j) {
+                    const int pos = ((c0 >> 2) + j) ^ (lane & 7);
+                    st_cluster_f4(base + pos * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int src = 0; src < KS; ++src) {
+                const float* rp = recv + (src * 32 + frow) * BN;
+                const float4 x0 = *reinterpret_cast<const float4*>(rp + (((2 * fc8) ^ (frow & 7)) << 2));
+                const float4 x1 = *reinterpret_cast<const float4*>(rp + (((2 * fc8 + 1) ^ (frow & 7)) << 2));
+                acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w; acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+            }
+            Epi::direct(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, acc, pre);
+        } else {
+            mbar_wait(tmem_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(Cs + row * C::LDC + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (probe && threadIdx.x == 64) probe[5] = gtimer();
+    }
+    if constexpr (KS > 1) {
+        if (warp < 2) {   // the producer / MMA warps take part in the cluster barrier too (it counts every thread)
+            asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+        }
     }
     __syncthreads();
-    Epi::template apply<C>(ep, Cs, m0, n0);
+    if constexpr (!Epi::kDirect) Epi::template apply<C>(ep, Cs, m0, n0);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
@@ -219,25 +352,44 @@ inline const CUtensorMap* get_map(MapCache& cache, const void* ptr, int rows, in
     return &cache.emplace(key, m).first->second;
 }
 
-template <int BN, class Epi>
+template <int BN, class Epi, int KS = 1>
 inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K,
-                          const typename Epi::Params& ep) {
+                          const typename Epi::Params& ep, bool pdl = false) {
     if (M <= 0) return cudaSuccess;
-    using C = Cfg<BN>;
+    constexpr int NT = Threads<BN, Epi>::N;
+    using C = Cfg<BN, NT>;
+    constexpr int SMEM = C::SMEM_BYTES + (KS > 1 ? KS * 32 * BN * 4 : 0);
     if (cache.size() > 32768) cache.clear();   // before either lookup: element pointers stay valid across inserts, not across clear
     const CUtensorMap* ma = get_map(cache, A, M, K, lda, BM);
     const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN);
     if (!ma || !mb) return cudaErrorInvalidValue;
-    auto kern = gemm_tc_kernel<BN, Epi>;
+    auto kern = gemm_tc_kernel<BN, Epi, KS>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid(N / BN, (M + BM - 1) / BM);
-    kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(*ma, *mb, K, ep);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(N / BN, (M + BM - 1) / BM, KS);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (KS > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = KS;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, ep);
 }
 
 }  // namespace tc

@@ -154,7 +154,19 @@ extern "C" int s2vt_create(const s2vt_config* cfg, s2vt_handle** out) {
     return S2VT_OK;
 }
 
+// Debug: device buffer of >= 8 * 4001 uint64 (zeroed by the caller) receiving per-launch phase timestamps, or NULL.
+extern "C" int s2vt_debug_probe(void* device_buffer) {
+    unsigned long long* p = (unsigned long long*)device_buffer;
+    return cudaMemcpyToSymbol(tc::g_probe, &p, sizeof p) == cudaSuccess ? 0 : S2VT_ECUDA;
+}
+extern "C" int s2vt_set_reuse_frontend(s2vt_handle* h, int enable) {
+    if (!h) return S2VT_EINVAL;
+    h->reuse_front = enable != 0;
+    h->front_valid = false;
+    return 0;
+}
 extern "C" void s2vt_destroy(s2vt_handle* h) {
+    if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     if (h && h->tc_cache) delete static_cast<tc::MapCache*>(h->tc_cache);
     delete h;
 }
@@ -242,6 +254,7 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
         rec.a = prof_event(h); rec.b = prof_event(h);
         rec.flops = 2.0 * (logical_m ? (double)logical_m : logical_dim(h, M)) * logical_dim(h, N) * (logical_k ? (double)logical_k : logical_dim(h, K));
         rec.cls = Cfg::BM >= 128 ? 0 : 1;
+        rec.M = M; rec.N = N; rec.K = K;
         cudaEventRecord(rec.a, st);
     }
     h->launches++;
@@ -250,9 +263,18 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
         if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC) {   // tcgen05 + TMA + TMEM path (default for bf16)
             if (!h->tc_cache) h->tc_cache = new tc::MapCache();
             tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
-            if (Cfg::BM >= 128) CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep)));
-            else if (M > 128 && N > 1024) CUDA_TRY(h, (tc::launch<64, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep)));
-            else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep)));
+            // per-step GEMMs are launched as programmatic dependents: their prologue and weight prefetch overlap the tail of the
+            // preceding kernel (which never writes weights: only s2vt_refresh does, and a batched GEMM always follows it)
+            if (Cfg::BM >= 128) CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
+            else if constexpr (std::is_same<Epi, EpiLstmBwd<bf16>>::value) {
+                // cell backward: K = 4H is long and N = H gives few tiles -> split K over a cluster of 4 CTAs (DSMEM reduction)
+                if ((K / tc::BK) % 4 == 0) {
+                    if (M > 128) CUDA_TRY(h, (tc::launch<64, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+                    else CUDA_TRY(h, (tc::launch<32, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+                } else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+            }
+            else if (M > 128 && N > 1024) CUDA_TRY(h, (tc::launch<64, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+            else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
             done = true;
         }
     }
@@ -298,6 +320,7 @@ static int refresh_impl(s2vt_handle* h, cudaStream_t st) {
     typename EpiStore<T>::Params ep = {h->Etab, nullptr, Gp, nullptr, Vp, 0};
     TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, h->WembC, Ep, h->W2eT, Ep, Vp, Gp, Ep, ep)));
     h->fresh = true;
+    h->front_valid = false;
     return 0;
 }
 
@@ -358,7 +381,7 @@ struct Roll {
 };
 template <typename T>
 static void plan_roll(const s2vt_handle* h, Arena& a, int B, int R, Roll<T>& r) {
-    plan_front<T>(h, a, B, false, r.f);
+    plan_front<T>(h, a, B, true, r.f);   // same layout as the training plan so the LSTM1 forward can be shared
     r.G2x = a.take<float>((size_t)h->T * B * h->Gp);
     for (int i = 0; i < 2; ++i) { r.h2e[i] = a.take<T>((size_t)B * h->Hp); r.c2e[i] = a.take<float>((size_t)B * h->Hp); }
     for (int i = 0; i < 2; ++i) { r.h2r[i] = a.take<T>((size_t)R * h->Hp); r.c2r[i] = a.take<float>((size_t)R * h->Hp); }
@@ -371,7 +394,9 @@ static void plan_roll(const s2vt_handle* h, Arena& a, int B, int R, Roll<T>& r) 
 template <typename T>
 static int run_encoder(s2vt_handle* h, cudaStream_t st, const float* video, int B, Roll<T>& r) {
     const int Tv = h->Tv, T_ = h->T, Hp = h->Hp, Gp = h->Gp;
+    h->front_valid = false;
     TRY(run_front<T>(h, st, video, B, r.f));
+    h->front_valid = true; h->front_B = B; h->front_video = video;
     {   // G2x = h1 . W2[out1 rows] for every step (bare cells: no dropout in the samplers, Q2)
         typename EpiStore<T>::Params ep = {r.G2x, nullptr, Gp, nullptr, T_ * B, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, r.f.h1_all + (size_t)B * Hp, Hp, h->W2xT, Hp, T_ * B, Gp, Hp, ep)));
@@ -459,6 +484,7 @@ struct Train {
     // backward
     T* dlogits; float* dout2; T* dG2; float* dc2; float* dout1; float* dEmb; float* dh1; T* dG1; float* dc1; float* dimgF; T* dimgT_src;
     T *tA, *tB;   // transposed operand scratch (largest: [Vp, Mp])
+    T *tA2, *tB2; // same for the LSTM1 chain on the side stream
     T* emb;
 };
 
@@ -497,6 +523,9 @@ static void plan_train(const s2vt_handle* h, Arena& a, int B, int N, bool backwa
     if ((size_t)Gp * Mp2 > tb) tb = (size_t)Gp * Mp2;
     p.tA = a.take<T>(ta + 256);
     p.tB = a.take<T>(tb + 256);
+    size_t ta2 = (size_t)(Dp > Hp ? Dp : Hp) * Mp1, tb2 = (size_t)Gp * Mp1;
+    p.tA2 = a.take<T>(ta2 + 256);
+    p.tB2 = a.take<T>(tb2 + 256);
 }
 
 template <typename T>
@@ -521,11 +550,15 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     if (N % B != 0) return h->fail(S2VT_EINVAL, "N (%d) must be a multiple of B (%d): row n uses video n %% B", N, B);
     Arena a(h->ws, h->ws_bytes);
     Train<T> p;
-    plan_train<T>(h, a, B, N, backward, false, p);
+    plan_train<T>(h, a, B, N, true, false, p);
     if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small: need %zu bytes", a.used);
 
     // ---------------- forward ----------------
-    TRY(run_front<T>(h, st, video, B, p.f));
+    // LSTM1 (and the frame projection) depend on the video only: reuse the pass the preceding rollout already made
+    if (!(backward && h->reuse_front && h->front_valid && h->front_B == B && h->front_video == video)) {
+        h->front_valid = false;
+        TRY(run_front<T>(h, st, video, B, p.f));
+    }
     expand_dropout_kernel<T><<<T_ * N, 256, 0, st>>>(p.f.h1_all + (size_t)B * Hp, B, N, Hp, H, p.out1d, drop_seed, S2VT_STREAM_DROP1, row_base, keep);
     KCHECK(h);
     {
@@ -582,13 +615,6 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         typename EpiStore<T>::Params ep = {p.dout2, nullptr, Hp, nullptr, MD, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dlogits, Vp, h->Wo, Vp, MD, Hp, Vp, ep)));
     }
-    {   // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums
-        TRY(transpose<T>(h, st, p.out2d, Hp, MD, Hp, p.tA, MpD, Hp));
-        TRY(transpose<T>(h, st, p.dlogits, Vp, MD, Vp, p.tB, MpD, Vp));
-        EpiGradStore::Params ep = {h->G_(h->iWo), V, H, V, 0, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Hp, Vp, MpD, ep, MD, H)));
-        rowsum_grad_kernel<T><<<Vp, 256, 0, st>>>(p.tB, MpD, MD, V, 0, h->G_(h->ibo)); KCHECK(h);
-    }
     // LSTM2 BPTT
     CUDA_TRY(h, cudaMemsetAsync(p.dc2, 0, (size_t)N * Hp * sizeof(float), st));
     for (int t = T_ - 1; t >= 0; --t) {
@@ -606,9 +632,69 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
             TRY((gemm<T, CfgStep, EpiLstmBwd<T>>(h, st, p.dG2 + (size_t)(t + 1) * N * Gp, Gp, h->W2h, Gp, N, Hp, Gp, ep)));
         }
     }
-    {   // gradient flowing into LSTM1's (dropped) output and into the word embeddings
+    {   // gradient flowing into LSTM1's (dropped, shared-per-video) output
         typename EpiStore<T>::Params ep = {p.dout1, nullptr, Hp, nullptr, M2, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2, Gp, h->W2x, Gp, M2, Hp, Gp, ep)));
+        reduce_dropout_kernel<<<M1, 256, 0, st>>>(p.dout1, B, N, Hp, p.dh1, drop_seed, S2VT_STREAM_DROP1, row_base, keep); KCHECK(h);
+    }
+    // ---- fork: the LSTM1 chain (B rows, few CTAs per step) runs on the side stream while the main stream computes the
+    //      LSTM2 / vocabulary weight gradients (large GEMMs); joined before returning.
+    if (!h->side) {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t s2 = h->side;
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+    CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
+    // LSTM1 BPTT over the B shared rows (side stream)
+    CUDA_TRY(h, cudaMemsetAsync(p.dc1, 0, (size_t)B * Hp * sizeof(float), s2));
+    for (int t = T_ - 1; t >= 0; --t) {
+        LstmBwdArgs b;
+        memset(&b, 0, sizeof b);
+        b.M = B; b.Hp = Hp; b.dh_ext = p.dh1 + (size_t)t * B * Hp;
+        b.gates = p.f.gates1 + (size_t)t * B * Gp; b.c_prev = p.f.c1_all + (size_t)t * B * Hp; b.c_new = p.f.c1_all + (size_t)(t + 1) * B * Hp;
+        b.dc = p.dc1; b.keep = 1.f;
+        T* dg = p.dG1 + (size_t)t * B * Gp;
+        if (t == T_ - 1) {
+            lstm_bwd_elem_kernel<T><<<(B * Hp + 255) / 256, 256, 0, s2>>>(b, dg); KCHECK(h);
+        } else {
+            typename EpiLstmBwd<T>::Params ep = {b, dg};
+            TRY((gemm<T, CfgStep, EpiLstmBwd<T>>(h, s2, p.dG1 + (size_t)(t + 1) * B * Gp, Gp, h->W1h, Gp, B, Hp, Gp, ep)));
+        }
+    }
+    {   // LSTM1 kernel / bias gradients (side stream, own transpose scratch)
+        float* gW1 = h->G_(h->iW1);
+        TRY(transpose<T>(h, s2, p.dG1, Gp, M1, Gp, p.tB2, Mp1, Gp));
+        rowsum_grad_kernel<T><<<Gp, 256, 0, s2>>>(p.tB2, Mp1, M1, 0, H, h->G_(h->ib1)); KCHECK(h);
+        TRY(transpose<T>(h, s2, p.f.h1_all, Hp, M1, Hp, p.tA2, Mp1, Hp));
+        EpiGradStore::Params e2 = {gW1 + (size_t)E * G, G, H, G, H, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, s2, p.tA2, Mp1, p.tB2, Mp1, Hp, Gp, Mp1, e2, M1, H)));
+        // frame-embedding rows: encoder steps only
+        TRY(transpose<T>(h, s2, p.dG1, Gp, ME, Gp, p.tB2, MpE, Gp));
+        TRY(transpose<T>(h, s2, p.f.img, Ep, ME, Ep, p.tA2, MpE, Ep));
+        EpiGradStore::Params e1 = {gW1, G, E, G, H, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, s2, p.tA2, MpE, p.tB2, MpE, Ep, Gp, MpE, e1, ME, E)));
+    }
+    {   // frame projection gradients: dimg = dG1[enc] . W1[x rows]^T ; dWe = X^T . dimg ; dbe = column sums (side stream)
+        typename EpiStore<T>::Params ep = {p.dimgF, p.dimgT_src, Ep, nullptr, ME, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, s2, p.dG1, Gp, h->W1x, Gp, ME, Ep, Gp, ep)));
+        TRY(transpose<T>(h, s2, p.dimgT_src, Ep, ME, Ep, p.tB2, MpE, Ep));
+        rowsum_grad_kernel<T><<<Ep, 256, 0, s2>>>(p.tB2, MpE, ME, E, 0, h->G_(h->ibe)); KCHECK(h);
+        TRY(transpose<T>(h, s2, p.f.Xc, Dp, ME, Dp, p.tA2, MpE, Dp));
+        EpiGradStore::Params e = {h->G_(h->iWe), E, D, E, 0, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, s2, p.tA2, MpE, p.tB2, MpE, Dp, Ep, MpE, e, ME, D)));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
+    // ---- main stream meanwhile: vocabulary projection, embedding and LSTM2 weight gradients
+    {   // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums
+        TRY(transpose<T>(h, st, p.out2d, Hp, MD, Hp, p.tA, MpD, Hp));
+        TRY(transpose<T>(h, st, p.dlogits, Vp, MD, Vp, p.tB, MpD, Vp));
+        EpiGradStore::Params ep = {h->G_(h->iWo), V, H, V, 0, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Hp, Vp, MpD, ep, MD, H)));
+        rowsum_grad_kernel<T><<<Vp, 256, 0, st>>>(p.tB, MpD, MD, V, 0, h->G_(h->ibo)); KCHECK(h);
+    }
+    {   // word-embedding gradient
         typename EpiStore<T>::Params ee = {p.dEmb, nullptr, Ep, nullptr, MD, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2 + (size_t)Tv * N * Gp, Gp, h->W2e, Gp, MD, Ep, Gp, ee)));
         scatter_emb_grad_kernel<<<MD, 128, 0, st>>>(p.dEmb, Ep, p.prev_tok, MD, E, h->G_(h->iWemb), h->grads + h->P); KCHECK(h);   // aux[0] = slice square norm (R6)
@@ -630,45 +716,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         EpiGradStore::Params e2 = {gW2 + (size_t)H * G, G, E, G, H, 1.f};
         TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Ep, Gp, MpD, e2, MD, E)));
     }
-    // LSTM1 BPTT over the B shared rows
-    reduce_dropout_kernel<<<M1, 256, 0, st>>>(p.dout1, B, N, Hp, p.dh1, drop_seed, S2VT_STREAM_DROP1, row_base, keep); KCHECK(h);
-    CUDA_TRY(h, cudaMemsetAsync(p.dc1, 0, (size_t)B * Hp * sizeof(float), st));
-    for (int t = T_ - 1; t >= 0; --t) {
-        LstmBwdArgs b;
-        memset(&b, 0, sizeof b);
-        b.M = B; b.Hp = Hp; b.dh_ext = p.dh1 + (size_t)t * B * Hp;
-        b.gates = p.f.gates1 + (size_t)t * B * Gp; b.c_prev = p.f.c1_all + (size_t)t * B * Hp; b.c_new = p.f.c1_all + (size_t)(t + 1) * B * Hp;
-        b.dc = p.dc1; b.keep = 1.f;
-        T* dg = p.dG1 + (size_t)t * B * Gp;
-        if (t == T_ - 1) {
-            lstm_bwd_elem_kernel<T><<<(B * Hp + 255) / 256, 256, 0, st>>>(b, dg); KCHECK(h);
-        } else {
-            typename EpiLstmBwd<T>::Params ep = {b, dg};
-            TRY((gemm<T, CfgStep, EpiLstmBwd<T>>(h, st, p.dG1 + (size_t)(t + 1) * B * Gp, Gp, h->W1h, Gp, B, Hp, Gp, ep)));
-        }
-    }
-    {   // LSTM1 kernel / bias gradients
-        float* gW1 = h->G_(h->iW1);
-        TRY(transpose<T>(h, st, p.dG1, Gp, M1, Gp, p.tB, Mp1, Gp));
-        rowsum_grad_kernel<T><<<Gp, 256, 0, st>>>(p.tB, Mp1, M1, 0, H, h->G_(h->ib1)); KCHECK(h);
-        TRY(transpose<T>(h, st, p.f.h1_all, Hp, M1, Hp, p.tA, Mp1, Hp));
-        EpiGradStore::Params e2 = {gW1 + (size_t)E * G, G, H, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp1, p.tB, Mp1, Hp, Gp, Mp1, e2, M1, H)));
-        // frame-embedding rows: encoder steps only
-        TRY(transpose<T>(h, st, p.dG1, Gp, ME, Gp, p.tB, MpE, Gp));
-        TRY(transpose<T>(h, st, p.f.img, Ep, ME, Ep, p.tA, MpE, Ep));
-        EpiGradStore::Params e1 = {gW1, G, E, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpE, p.tB, MpE, Ep, Gp, MpE, e1, ME, E)));
-    }
-    {   // frame projection gradients: dimg = dG1[enc] . W1[x rows]^T ; dWe = X^T . dimg ; dbe = column sums
-        typename EpiStore<T>::Params ep = {p.dimgF, p.dimgT_src, Ep, nullptr, ME, 0};
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG1, Gp, h->W1x, Gp, ME, Ep, Gp, ep)));
-        TRY(transpose<T>(h, st, p.dimgT_src, Ep, ME, Ep, p.tB, MpE, Ep));
-        rowsum_grad_kernel<T><<<Ep, 256, 0, st>>>(p.tB, MpE, ME, E, 0, h->G_(h->ibe)); KCHECK(h);
-        TRY(transpose<T>(h, st, p.f.Xc, Dp, ME, Dp, p.tA, MpE, Dp));
-        EpiGradStore::Params e = {h->G_(h->iWe), E, D, E, 0, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpE, p.tB, MpE, Dp, Ep, MpE, e, ME, D)));
-    }
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));   // join
     if (mode == 1 && decay > 0.f) {   // Q4: L2 on every variable without 'bias' in its name (the LSTM '/biases' only)
         CUDA_TRY(h, cudaMemsetAsync(h->sq + 3, 0, sizeof(double), st));
         for (size_t i = 0; i < h->vars.size(); ++i) {
@@ -718,6 +766,7 @@ extern "C" int s2vt_xe_backward(s2vt_handle* h, const float* video, int B, const
 template <typename T>
 static int attribute_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B, const float* labels, float grad_scale, float* loss_out) {
     const int A = h->A, Ap = h->Ap, D = h->D, Dp = h->Dp, Bp = ru(B, S2VT_PAD);
+    h->front_valid = false;
     Arena a(h->ws, h->ws_bytes);
     T* pooled = a.take<T>((size_t)B * Dp);
     float* z = a.take<float>((size_t)B * Ap);
@@ -802,6 +851,21 @@ extern "C" int s2vt_profile(s2vt_handle* h, int enable) {
 }
 // Synchronises the device, aggregates the bracketed GEMM launches per class (0: batched GEMMs, 1: recurrent-step GEMMs)
 // and clears the record list.
+// Per-shape breakdown of the bracketed launches (does not clear): up to `cap` distinct (cls, M, N, K) rows.
+extern "C" int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* K, double* ms, long long* count) {
+    if (!h) return S2VT_EINVAL;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    int n = 0;
+    for (auto& r : h->prof_recs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        int i = 0;
+        for (; i < n; ++i) if (cls[i] == r.cls && M[i] == r.M && N[i] == r.N && K[i] == r.K) break;
+        if (i == n) { if (n >= cap) continue; cls[n] = r.cls; M[n] = r.M; N[n] = r.N; K[n] = r.K; ms[n] = 0; count[n] = 0; ++n; }
+        ms[i] += t; count[i] += 1;
+    }
+    return n;
+}
 extern "C" int s2vt_profile_read(s2vt_handle* h, double* ms_out, double* flops_out, long long* launches_out) {
     if (!h || !ms_out || !flops_out || !launches_out) return S2VT_EINVAL;
     CUDA_TRY(h, cudaDeviceSynchronize());

@@ -226,12 +226,23 @@ class Video_Caption_Generator(object):
         self._check(self.lib.s2vt_optimizer_step(self.h, float(lr), float(clip_norm), self.adam_step, flags, _ptr(out), _stream()))
         return out
 
+    def set_reuse_frontend(self, enable=True):
+        """Share the LSTM1 forward of a rollout with the training call that follows on the same video tensor."""
+        self._check(self.lib.s2vt_set_reuse_frontend(self.h, int(bool(enable))))
+
     # ---- instrumentation -----------------------------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.s2vt_launch_count(self.h))
 
     def profile(self, enable):
         self._check(self.lib.s2vt_profile(self.h, int(bool(enable))))
+
+    def profile_shapes(self, cap=256):
+        """[(cls, M, N, K, total ms, launches)] of the GEMM launches recorded since the last profile_read."""
+        I = C.c_int * cap
+        cls, M, N, K, ms, cnt = I(), I(), I(), I(), (C.c_double * cap)(), (C.c_longlong * cap)()
+        n = self.lib.s2vt_profile_shapes(self.h, cap, cls, M, N, K, ms, cnt)
+        return [(cls[i], M[i], N[i], K[i], ms[i], cnt[i]) for i in range(max(n, 0))]
 
     def profile_read(self):
         """-> {'batched': (ms, flops, launches), 'step': (...)} of the GEMM launches since the last read."""

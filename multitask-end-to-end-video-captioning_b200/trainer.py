@@ -54,6 +54,7 @@ class ReinforceTrainer(object):
         self.seed, self.dropout, self.wemb_slice_norm = int(seed), dropout, wemb_slice_norm
         self.global_step = 0
         self.last = {}
+        model.set_reuse_frontend(True)      # rollout and update run on the same feature tensor within step()
 
     def step(self, video, video_index):
         """video: float32 [B, T_v, D] on the device or in (pinned) host memory; video_index: int32 [B] corpus video
