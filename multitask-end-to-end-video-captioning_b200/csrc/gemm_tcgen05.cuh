@@ -30,7 +30,7 @@ struct Cfg {
     static constexpr int LDC = BN + 4;
     // BN <= 64 (per-step GEMMs): small enough that CTAs of the NEXT step's kernel (programmatic dependent launch) fit on the
     // SM beside the running ones: BN=32 -> 100 KB (2 per SM), BN=64 -> 72 KB (3 per SM)
-    static constexpr int STAGES = BN >= 128 ? 6 : (BN >= 64 ? 3 : 5);
+    static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 5 : (BN >= 64 ? 3 : 5));
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int EPI_BYTES = BM * LDC * 4;
@@ -78,6 +78,17 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -135,11 +146,26 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
 // KS > 1: split-K over a cluster of KS CTAs (cluster dims (1,1,KS), rank = blockIdx.z).  Each CTA accumulates its K range
 // in TMEM; partial tiles are exchanged through distributed shared memory so that CTA r reduces and finishes rows
 // [32r, 32r+32) of the tile (KS == 4): the K loop AND the epilogue are both split four ways.
-template <int BN, class Epi, int KS>
+// CX x CY > 1: TMA multicast over a (CX, CY, 1) cluster.  The CX CTAs of a cluster row compute the same 128 output rows, so
+// each loads 128/CX rows of the A K-block and multicasts them to the row; the CY CTAs of a cluster column share the B tile
+// the same way.  L2 reads per CTA drop from (128 + BN) to (128/CX + BN/CY) rows per K-block.  A stage may only be refilled
+// when every CTA that receives part of it has consumed it: the MMA warp's tcgen05.commit arrives (multicast) on the
+// `empty` barrier of each CTA that sends to it, and `empty` counts CX + CY - 1 arrivals.
+template <int BN, class Epi, int KS, int CX = 1, int CY = 1>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                       int K, typename Epi::Params ep) {
     using C = Cfg<BN, Threads<BN, Epi>::N>;
     static_assert(KS == 1 || (KS == 4 && Epi::kDirect), "split-K needs a direct epilogue and a cluster of 4");
+    static_assert(KS == 1 || (CX == 1 && CY == 1), "split-K and multicast clusters are exclusive");
+    constexpr bool MC = CX * CY > 1;
+    constexpr int A_ROWS = BM / CX, B_ROWS = BN / CY;   // rows this CTA fetches of each tile
+    uint32_t crank = 0;
+    if constexpr (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int cx = crank % CX, cy = crank / CX;
+    const uint16_t row_mask = (uint16_t)(((1u << CX) - 1u) << (cy * CX));
+    uint16_t col_mask = 0;
+#pragma unroll
+    for (int j = 0; j < CY; ++j) col_mask |= (uint16_t)(1u << (j * CX + cx));
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B atoms need 1024 B alignment
     constexpr int MAIN = C::PIPE_BYTES > C::EPI_BYTES ? C::PIPE_BYTES : C::EPI_BYTES;
@@ -166,7 +192,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CX + CY - 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -178,10 +204,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    if constexpr (KS > 1) {   // every CTA of the cluster must be running before its shared memory is written remotely
-        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-    }
+    if constexpr (KS > 1 || MC) cluster_sync_all();   // every CTA of the cluster is running and its barriers are initialised
 
     // Programmatic dependent launch: let the next kernel in the stream start its prologue now; the weight (B) tiles of the
     // first stages never depend on the previous kernel, so they are requested before waiting for it.
@@ -190,7 +213,9 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < pre; ++i) {
             mbar_expect_tx(full + i, C::STAGE_BYTES);
-            tma_load_2d(smem + i * C::STAGE_BYTES + C::A_BYTES, &mapB, full + i, (kb0 + i) * C::BK, n0);
+            unsigned char* b = smem + i * C::STAGE_BYTES + C::A_BYTES + cy * B_ROWS * 128;
+            if constexpr (CY > 1) tma_load_2d_mc(b, &mapB, full + i, (kb0 + i) * C::BK, n0 + cy * B_ROWS, col_mask);
+            else tma_load_2d(b, &mapB, full + i, (kb0 + i) * C::BK, n0);
         }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -204,9 +229,12 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
                 if (i >= C::STAGES) {
                     mbar_wait(empty + s, ((i / C::STAGES) - 1) & 1);
                     mbar_expect_tx(full + s, C::STAGE_BYTES);
-                    tma_load_2d(a + C::A_BYTES, &mapB, full + s, (kb0 + i) * C::BK, n0);
+                    unsigned char* b = a + C::A_BYTES + cy * B_ROWS * 128;
+                    if constexpr (CY > 1) tma_load_2d_mc(b, &mapB, full + s, (kb0 + i) * C::BK, n0 + cy * B_ROWS, col_mask);
+                    else tma_load_2d(b, &mapB, full + s, (kb0 + i) * C::BK, n0);
                 }
-                tma_load_2d(a, &mapA, full + s, (kb0 + i) * C::BK, m0);
+                if constexpr (CX > 1) tma_load_2d_mc(a + cx * A_ROWS * 128, &mapA, full + s, (kb0 + i) * C::BK, m0 + cx * A_ROWS, row_mask);
+                else tma_load_2d(a, &mapA, full + s, (kb0 + i) * C::BK, m0);
             }
         }
         __syncwarp();
@@ -222,7 +250,8 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
 #pragma unroll
                 for (int k = 0; k < C::BK / 16; ++k)   // +32 bytes (>>4 = 2) per K=16 step inside the 128-byte swizzle atom
                     mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (i | k) != 0);
-                mma_commit(empty + s);                  // implies tcgen05.fence::before_thread_sync
+                if constexpr (MC) mma_commit_mc(empty + s, (uint16_t)(row_mask | col_mask));
+                else mma_commit(empty + s);             // implies tcgen05.fence::before_thread_sync
             }
             mma_commit(tmem_full);
             if (probe) probe[3] = gtimer();
@@ -299,6 +328,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     }
     __syncthreads();
     if constexpr (!Epi::kDirect) Epi::template apply<C>(ep, Cs, m0, n0);
+    if constexpr (MC) cluster_sync_all();   // peers may still signal this CTA's barriers: nobody leaves before everybody is done
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
@@ -352,7 +382,7 @@ inline const CUtensorMap* get_map(MapCache& cache, const void* ptr, int rows, in
     return &cache.emplace(key, m).first->second;
 }
 
-template <int BN, class Epi, int KS = 1>
+template <int BN, class Epi, int KS = 1, int CX = 1, int CY = 1>
 inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K,
                           const typename Epi::Params& ep, bool pdl = false) {
     if (M <= 0) return cudaSuccess;
@@ -360,10 +390,10 @@ inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int l
     using C = Cfg<BN, NT>;
     constexpr int SMEM = C::SMEM_BYTES + (KS > 1 ? KS * 32 * BN * 4 : 0);
     if (cache.size() > 32768) cache.clear();   // before either lookup: element pointers stay valid across inserts, not across clear
-    const CUtensorMap* ma = get_map(cache, A, M, K, lda, BM);
-    const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN);
+    const CUtensorMap* ma = get_map(cache, A, M, K, lda, BM / CX);
+    const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN / CY);
     if (!ma || !mb) return cudaErrorInvalidValue;
-    auto kern = gemm_tc_kernel<BN, Epi, KS>;
+    auto kern = gemm_tc_kernel<BN, Epi, KS, CX, CY>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -371,7 +401,7 @@ inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int l
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(N / BN, (M + BM - 1) / BM, KS);
+    cfg.gridDim = dim3(N / BN, ((M + BM - 1) / BM + CY - 1) / CY * CY, KS);   // whole clusters; surplus row tiles are all-padding
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
@@ -382,9 +412,9 @@ inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int l
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
     }
-    if (KS > 1) {
+    if (KS > 1 || CX * CY > 1) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = KS;
+        attr[na].val.clusterDim.x = CX; attr[na].val.clusterDim.y = CY; attr[na].val.clusterDim.z = KS;
         ++na;
     }
     cfg.attrs = attr;

@@ -265,15 +265,29 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
             tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
             // per-step GEMMs are launched as programmatic dependents: their prologue and weight prefetch overlap the tail of the
             // preceding kernel (which never writes weights: only s2vt_refresh does, and a batched GEMM always follows it)
-            if (Cfg::BM >= 128) CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
+            if (Cfg::BM >= 128) {
+                // batched GEMMs are bound by L2 -> SM bandwidth, so use the widest tile (128 x 256: 85 flop per byte fetched vs
+                // 64 for 128 x 128).  gemm_backend 3 / 4 select the 128-wide tile without / with 2x2 TMA multicast (measured
+                // slower on B200: at cluster sizes <= 4 multicast does not reduce L2 traffic).
+                if (h->cfg.gemm_backend == 4 && (N / 128) % 2 == 0) CUDA_TRY(h, (tc::launch<128, Epi, 1, 2, 2>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
+                else if (h->cfg.gemm_backend == 3 || N % 256 != 0) CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
+                else CUDA_TRY(h, (tc::launch<256, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
+            }
             else if constexpr (std::is_same<Epi, EpiLstmBwd<bf16>>::value) {
                 // cell backward: K = 4H is long and N = H gives few tiles -> split K over a cluster of 4 CTAs (DSMEM reduction)
                 if ((K / tc::BK) % 4 == 0) {
-                    if (M > 128) CUDA_TRY(h, (tc::launch<64, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+                    if (M > 128 && h->cfg.gemm_backend != 7) CUDA_TRY(h, (tc::launch<128, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+                    else if (M > 128) CUDA_TRY(h, (tc::launch<64, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
                     else CUDA_TRY(h, (tc::launch<32, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
                 } else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
             }
-            else if (M > 128 && N > 1024) CUDA_TRY(h, (tc::launch<64, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+            else if (M > 128 && N > 1024) {
+                // every column tile of a row block reads the same activations: fetch them once per cluster of 8 (TMA multicast)
+                if (h->cfg.gemm_backend == 5 && (N / 64) % 8 == 0) CUDA_TRY(h, (tc::launch<64, Epi, 1, 8, 1>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+                else if (h->cfg.gemm_backend == 6 && (N / 64) % 4 == 0) CUDA_TRY(h, (tc::launch<64, Epi, 1, 4, 1>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+                else if (h->cfg.gemm_backend == 7) CUDA_TRY(h, (tc::launch<64, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+                else CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));   // <= 148 CTAs, one per SM: balanced smem fill
+            }
             else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
             done = true;
         }
