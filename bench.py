@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 DIMS = dict(D=1536, E=500, H=1000, V=9972)
 METRIC = 'reinforce_train_videos_per_s'
+# dram__bytes_read.sum + dram__bytes_write.sum per recurrent-step launch under ncu (cache flushed before each kernel), mean over the
+# step kernels of one iteration -- profiles/r1_tc_metrics.md
+STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = None
 
 
 def parse():
@@ -297,11 +300,11 @@ def run_b200(args):
         pass
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
-    bms, bfl, bn = prof['batched']
-    sms, sfl, sn = prof['step']
-    ach = bfl / (bms * 1e-3) / 1e12 if bms > 0 else 0.0
-    H, Tall = DIMS['H'], Tv + 35
-    step_bytes = sn and (sn * (H * 4 * H * 2.0) + 0.0)            # bf16 recurrent weights touched once per launch
+    bms, bfl, bn, bby = prof['batched']
+    sms, sfl, sn, sby = prof['step']
+    ach_tf = bfl / (bms * 1e-3) / 1e12 if bms > 0 else 0.0
+    ach_gb = sby / (sms * 1e-3) / 1e9 if sms > 0 else 0.0
+    hbm = peaks.get('hbm_gbs', 6650.0)
     out = {'metric': METRIC, 'value': value, 'unit': 'videos/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': workload_config(args, B, world),
@@ -310,18 +313,21 @@ def run_b200(args):
            'gpu_launches': int(launches), 'loss': loss,
            'gemm_shapes': [{'class': 'batched' if c == 0 else 'step', 'M': M_, 'N': N_, 'K': K_, 'launches_per_step': n_ / args.steps,
                             'us_per_launch': 1e3 * ms_ / n_, 'ms_per_step': ms_ / args.steps} for c, M_, N_, K_, ms_, n_ in sorted(shapes, key=lambda x: -x[4])],
-           'roofline': {'kernel': 'gemm_kernel<bf16, 128x128x32 tiles> (batched GEMMs: projections, vocab logits, weight gradients)',
-                        'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf if peak_tf else None,
-                        'traffic': None, 'peak_source': peak_src, 'launches_per_step': bn / args.steps, 'ms_per_step': bms / args.steps,
-                        'algorithmic_gflop_per_step': bfl / args.steps / 1e9,
-                        'pass': 'separate instrumented pass of the same %d steps (events around each launch)' % args.steps},
-           'roofline_recurrent_step': {'kernel': 'gemm_kernel<bf16, 64x32 tiles> + fused LSTM cell (one launch per time step)', 'bound': 'hbm',
-                                       'achieved': (step_bytes / (sms * 1e-3) / 1e9) if sms > 0 else None, 'peak': peaks.get('hbm_gbs', 6650.0),
-                                       'unit': 'GB/s', 'launches_per_step': sn / args.steps, 'ms_per_step': sms / args.steps,
-                                       'us_per_launch': 1e3 * sms / sn if sn else None,
-                                       'bytes_model': 'bf16 recurrent weights 1000x4000x2 B = 8.0 MB read once per launch'}}
-    if out['roofline_recurrent_step']['achieved']:
-        out['roofline_recurrent_step']['frac'] = out['roofline_recurrent_step']['achieved'] / out['roofline_recurrent_step']['peak']
+           # dominant kernel family by time: the per-time-step recurrent GEMM + fused LSTM cell (tcgen05, one launch per step)
+           'roofline': {'kernel': 'tc::gemm_tc_kernel<BN, EpiLstmFwd|EpiLstmBwd> (recurrent step: h.W_h on tcgen05 + fused BasicLSTMCell fwd/bwd)',
+                        'bound': 'hbm', 'achieved': ach_gb, 'peak': hbm, 'unit': 'GB/s', 'frac': ach_gb / hbm if hbm else None,
+                        'traffic': STEP_KERNEL_DRAM_BYTES_PER_LAUNCH, 'traffic_source': 'ncu dram__bytes_read+write per launch, cache flushed (profiles/)',
+                        'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)',
+                        'launches_per_step': sn / args.steps, 'ms_per_step': sms / args.steps, 'us_per_launch': 1e3 * sms / sn if sn else None,
+                        'algorithmic_bytes_per_launch': sby / sn if sn else None,
+                        'bytes_model': 'per launch: bf16 W_h (8.0 MB) + activation rows in + fp32 gate pre-activation addends, cell state, saved gate '
+                                       'activations and outputs (DESIGN.md section 4); weights and state are L2-resident, so the binding limit is the '
+                                       '~42 B/clk/SM L2->SM fill rate, not HBM',
+                        'pass': 'separate instrumented pass of the same %d steps: CUDA events around each chain of step launches' % args.steps},
+           'roofline_batched_gemm': {'kernel': 'tc::gemm_tc_kernel<256, EpiStore|EpiGradStore> (128x256 tcgen05 tiles: projections, vocab logits, weight gradients)',
+                                     'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach_tf / peak_tf if peak_tf else None,
+                                     'peak_source': peak_src, 'launches_per_step': bn / args.steps, 'ms_per_step': bms / args.steps,
+                                     'algorithmic_gflop_per_step': bfl / args.steps / 1e9}}
     if world == 1 and not args.no_cpu_baseline:
         o = OracleIteration(args, vocab, by, order, bias)
         o.step()

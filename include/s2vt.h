@@ -133,8 +133,10 @@ enum { S2VT_OPT_WEMB_SLICE_NORM = 1, S2VT_OPT_NORMALIZE = 2 };
 int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int flags, float* out, s2vt_stream st);
 
 /* ---- instrumentation used by bench.py: kernels launched by this handle so far; CUDA-event brackets around every GEMM
- * launch (class 0 = batched GEMMs, class 1 = recurrent-step GEMMs) with their algorithmic FLOPs.  profile_read
- * synchronises the device, fills ms/flops/launches [2] and clears the records. */
+ * launch of class 0 (batched GEMMs) and around every CHAIN of class 1 launches (recurrent-step GEMMs: bracketing each one
+ * would defeat their programmatic dependent launch overlap), with algorithmic FLOPs and bytes.  profile_read synchronises
+ * the device, fills ms[2], flops_out[4] = {flops class 0, flops class 1, bytes class 0, bytes class 1}, launches[2] and
+ * clears the records. */
 long long s2vt_launch_count(const s2vt_handle* h);
 int s2vt_profile(s2vt_handle* h, int enable);
 int s2vt_profile_read(s2vt_handle* h, double* ms_out, double* flops_out, long long* launches_out);

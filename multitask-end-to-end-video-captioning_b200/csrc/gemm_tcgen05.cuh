@@ -153,12 +153,15 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
 // `empty` barrier of each CTA that sends to it, and `empty` counts CX + CY - 1 arrivals.
 template <int BN, class Epi, int KS, int CX = 1, int CY = 1>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                                                                      int K, typename Epi::Params ep) {
+                                                                      int K, int a_rows, typename Epi::Params ep) {
+    // a_rows: rows of the A K-block actually fetched (TMA box height).  Problems with M <= 64 fetch 64 rows only; the rest of
+    // the 128-row smem tile is stale and only feeds accumulator rows >= M, which no epilogue reads.
     using C = Cfg<BN, Threads<BN, Epi>::N>;
     static_assert(KS == 1 || (KS == 4 && Epi::kDirect), "split-K needs a direct epilogue and a cluster of 4");
     static_assert(KS == 1 || (CX == 1 && CY == 1), "split-K and multicast clusters are exclusive");
     constexpr bool MC = CX * CY > 1;
     constexpr int A_ROWS = BM / CX, B_ROWS = BN / CY;   // rows this CTA fetches of each tile
+    const uint32_t stage_tx = (uint32_t)(MC ? C::STAGE_BYTES : a_rows * 128 + C::B_BYTES);
     uint32_t crank = 0;
     if constexpr (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const int cx = crank % CX, cy = crank / CX;
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     const int pre = KBL < C::STAGES ? KBL : C::STAGES;
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < pre; ++i) {
-            mbar_expect_tx(full + i, C::STAGE_BYTES);
+            mbar_expect_tx(full + i, stage_tx);
             unsigned char* b = smem + i * C::STAGE_BYTES + C::A_BYTES + cy * B_ROWS * 128;
             if constexpr (CY > 1) tma_load_2d_mc(b, &mapB, full + i, (kb0 + i) * C::BK, n0 + cy * B_ROWS, col_mask);
             else tma_load_2d(b, &mapB, full + i, (kb0 + i) * C::BK, n0);
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
                 unsigned char* a = smem + s * C::STAGE_BYTES;
                 if (i >= C::STAGES) {
                     mbar_wait(empty + s, ((i / C::STAGES) - 1) & 1);
-                    mbar_expect_tx(full + s, C::STAGE_BYTES);
+                    mbar_expect_tx(full + s, stage_tx);
                     unsigned char* b = a + C::A_BYTES + cy * B_ROWS * 128;
                     if constexpr (CY > 1) tma_load_2d_mc(b, &mapB, full + s, (kb0 + i) * C::BK, n0 + cy * B_ROWS, col_mask);
                     else tma_load_2d(b, &mapB, full + s, (kb0 + i) * C::BK, n0);
@@ -390,7 +393,8 @@ inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int l
     using C = Cfg<BN, NT>;
     constexpr int SMEM = C::SMEM_BYTES + (KS > 1 ? KS * 32 * BN * 4 : 0);
     if (cache.size() > 32768) cache.clear();   // before either lookup: element pointers stay valid across inserts, not across clear
-    const CUtensorMap* ma = get_map(cache, A, M, K, lda, BM / CX);
+    const int a_rows = (CX == 1 && M <= 64) ? ((M + 7) & ~7) : BM;
+    const CUtensorMap* ma = get_map(cache, A, M, K, lda, CX == 1 ? a_rows : BM / CX);
     const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN / CY);
     if (!ma || !mb) return cudaErrorInvalidValue;
     auto kern = gemm_tc_kernel<BN, Epi, KS, CX, CY>;
@@ -419,7 +423,7 @@ inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int l
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, ep);
+    return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, a_rows, ep);
 }
 
 }  // namespace tc

@@ -100,6 +100,14 @@ __global__ void reduce_dropout_kernel(const float* __restrict__ dout1, int B, in
     }
 }
 
+// Gumbel(0,1) noise -log(-log(u)) on the MUFU log path.  E = -log(u) is the delicate part for u -> 1 (the large noise
+// values that win the arg-max): there 1-u is exact in fp32 and a 3-term series of -log1p(-t) is used (rel. err < 1e-5).
+__device__ __forceinline__ float gumbel_fast(float u) {
+    float t = 1.0f - u;
+    float E = t < 0.03125f ? t * (1.0f + t * (0.5f + t * 0.33333334f)) : -__logf(u);
+    return -__logf(E);
+}
+
 // ---- vocabulary row kernels (one CTA per row, 128-bit loads, row kept in registers) -------------------------------
 #define ROW_THREADS 256
 #define ROW_MAXV4 12  // supports V <= 256*12*4 = 12288
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(ROW_THREADS) sample_rows_kernel(const float* _
             uint4 o = philox4x32_10((uint32_t)v4, step, grow, S2VT_STREAM_SAMPLE, (uint32_t)seed, (uint32_t)(seed >> 32));
             uint32_t rr[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) e[k] += -logf(-logf(u32_to_uniform(rr[k])));
+            for (int k = 0; k < 4; ++k) e[k] += gumbel_fast(u32_to_uniform(rr[k]));
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -348,6 +356,16 @@ __global__ void scatter_emb_grad_kernel(const float* __restrict__ demb, int ld, 
 
 // Bias gradients: row sums of a transposed gradient matrix XT [C, ld] over the first R columns.
 // gate_h > 0: row c is packed gate order 4u+g -> grad[g*gate_h + u]; else grad[c], c < ncols.
+__device__ __forceinline__ float sum8(const bf16* p) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]), c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
+    return (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+}
+__device__ __forceinline__ float sum8(const float* p) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    return (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
+}
 template <typename T>
 __global__ void rowsum_grad_kernel(const T* __restrict__ XT, int ld, int R, int ncols, int gate_h, float* __restrict__ grad) {
     __shared__ float red[32];
@@ -355,8 +373,10 @@ __global__ void rowsum_grad_kernel(const T* __restrict__ XT, int ld, int R, int 
     int dst;
     if (gate_h > 0) { int u = c >> 2, g = c & 3; if (u >= gate_h) return; dst = g * gate_h + u; }
     else { if (c >= ncols) return; dst = c; }
+    const T* row = XT + (size_t)c * ld;      // ld is a multiple of 128 elements and the pad columns are zero: vector loads over ru(R, 8)
     float acc = 0.f;
-    for (int r = threadIdx.x; r < R; r += blockDim.x) acc += to_f32(XT[(size_t)c * ld + r]);
+    const int R8 = (R + 7) & ~7;
+    for (int r = threadIdx.x * 8; r < R8; r += blockDim.x * 8) acc += sum8(row + r);
     acc = block_reduce(acc, [](float a, float b) { return a + b; }, red);
     if (threadIdx.x == 0) grad[dst] += acc;
 }

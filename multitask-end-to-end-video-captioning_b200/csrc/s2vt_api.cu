@@ -246,16 +246,61 @@ static double logical_dim(const s2vt_handle* h, int x) {
     if (x == h->Dp) return h->D;
     return x;
 }
+// Algorithmic bytes of the fused cell epilogues (logical sizes): what one per-step launch must move besides the
+// GEMM operands.  Used only for the roofline report.
+template <class Epi> struct EpiBytes { static double get(const s2vt_handle*, const typename Epi::Params&, int) { return 0.0; } };
+template <typename T> struct EpiBytes<EpiLstmFwd<T>> {
+    static double get(const s2vt_handle* h, const typename EpiLstmFwd<T>::Params& p, int M) {
+        const double H = h->H, G = 4.0 * h->H;
+        double b = M * H * 4 * 2 + M * H * sizeof(T);                       // c in, c out, h out
+        if (p.add0) b += M * G * 4;
+        if (p.add1) b += M * G * 4;
+        if (p.gates_out) b += M * G * 4;
+        if (p.hdrop_out) b += M * H * sizeof(T);
+        return b;
+    }
+};
+template <typename T> struct EpiBytes<EpiLstmBwd<T>> {
+    static double get(const s2vt_handle* h, const typename EpiLstmBwd<T>::Params& p, int M) {
+        const double H = h->H, G = 4.0 * h->H;
+        return M * G * 4 + M * H * 4 * 4 + (p.a.dh_ext ? M * H * 4 : 0) + M * G * sizeof(T);   // gates, c_new/c_prev/dc in/out, dh_ext, dG out
+    }
+};
+static int chain_begin(s2vt_handle* h, cudaStream_t st) {
+    if (!h->prof) return 0;
+    h->chain = s2vt_handle::ProfRec();
+    h->chain.a = prof_event(h); h->chain.b = prof_event(h);
+    h->chain.flops = h->chain.bytes = 0; h->chain.count = 0; h->chain.cls = 1; h->chain.M = h->chain.N = h->chain.K = 0;
+    h->chain_open = true;
+    cudaEventRecord(h->chain.a, st);
+    return 0;
+}
+static int chain_end(s2vt_handle* h, cudaStream_t st) {
+    if (!h->prof || !h->chain_open) return 0;
+    cudaEventRecord(h->chain.b, st);
+    h->prof_recs.push_back(h->chain);
+    h->chain_open = false;
+    return 0;
+}
 template <typename T, class Cfg, class Epi>
 static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const typename Epi::Params& ep,
                 int logical_k = 0, int logical_m = 0) {
     s2vt_handle::ProfRec rec;
+    const bool in_chain = h->prof && h->chain_open && Cfg::BM < 128;
+    const bool bracket = h->prof && !in_chain;
     if (h->prof) {
-        rec.a = prof_event(h); rec.b = prof_event(h);
-        rec.flops = 2.0 * (logical_m ? (double)logical_m : logical_dim(h, M)) * logical_dim(h, N) * (logical_k ? (double)logical_k : logical_dim(h, K));
+        const double lm = logical_m ? (double)logical_m : logical_dim(h, M), ln = logical_dim(h, N), lk = logical_k ? (double)logical_k : logical_dim(h, K);
+        rec.flops = 2.0 * lm * ln * lk;
+        rec.bytes = (lm * lk + ln * lk) * sizeof(T) + EpiBytes<Epi>::get(h, ep, M);   // operands once + epilogue traffic
         rec.cls = Cfg::BM >= 128 ? 0 : 1;
-        rec.M = M; rec.N = N; rec.K = K;
-        cudaEventRecord(rec.a, st);
+        rec.M = M; rec.N = N; rec.K = K; rec.count = 1;
+        if (in_chain) {
+            h->chain.flops += rec.flops; h->chain.bytes += rec.bytes; h->chain.count += 1;
+            h->chain.M = M; h->chain.N = N; h->chain.K = K;
+        } else {
+            rec.a = prof_event(h); rec.b = prof_event(h);
+            cudaEventRecord(rec.a, st);
+        }
     }
     h->launches++;
     bool done = false;
@@ -293,7 +338,7 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
         }
     }
     if (!done) CUDA_TRY(h, (launch_gemm<T, Cfg, Epi>(st, (const T*)A, lda, (const T*)B, ldb, M, N, K, ep)));
-    if (h->prof) { cudaEventRecord(rec.b, st); h->prof_recs.push_back(rec); }
+    if (bracket) { cudaEventRecord(rec.b, st); h->prof_recs.push_back(rec); }
     return 0;
 }
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
@@ -374,6 +419,7 @@ static int run_front(s2vt_handle* h, cudaStream_t st, const float* video, int B,
     }
     CUDA_TRY(h, cudaMemsetAsync(f.h1_all, 0, (size_t)B * Hp * sizeof(T), st));
     CUDA_TRY(h, cudaMemsetAsync(f.c1_all, 0, (size_t)B * Hp * sizeof(float), st));
+    chain_begin(h, st);
     for (int t = 0; t < T_; ++t) {   // :128-129 / :148-149 LSTM1; decoder steps get `padding` -> no input term (Q8)
         typename EpiLstmFwd<T>::Params ep;
         memset(&ep, 0, sizeof ep);
@@ -385,6 +431,7 @@ static int run_front(s2vt_handle* h, cudaStream_t st, const float* video, int B,
         ep.keep = 1.f;
         TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, f.h1_all + (size_t)t * B * Hp, Hp, h->W1hT, Hp, B, Gp, Hp, ep)));
     }
+    chain_end(h, st);
     return 0;
 }
 
@@ -417,6 +464,7 @@ static int run_encoder(s2vt_handle* h, cudaStream_t st, const float* video, int 
     }
     CUDA_TRY(h, cudaMemsetAsync(r.h2e[0], 0, (size_t)B * Hp * sizeof(T), st));
     CUDA_TRY(h, cudaMemsetAsync(r.c2e[0], 0, (size_t)B * Hp * sizeof(float), st));
+    chain_begin(h, st);
     for (int t = 0; t < Tv; ++t) {   // :131-132 LSTM2 on concat([output1, padding]) -> the embedding rows see zeros (Q8)
         typename EpiLstmFwd<T>::Params ep;
         memset(&ep, 0, sizeof ep);
@@ -424,6 +472,7 @@ static int run_encoder(s2vt_handle* h, cudaStream_t st, const float* video, int 
         ep.c_prev = r.c2e[t & 1]; ep.c_out = r.c2e[(t + 1) & 1]; ep.h_out = r.h2e[(t + 1) & 1]; ep.keep = 1.f;
         TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, r.h2e[t & 1], Hp, h->W2hT, Hp, B, Gp, Hp, ep)));
     }
+    chain_end(h, st);
     return 0;
 }
 
@@ -582,6 +631,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     caption_tables_kernel<<<(Tc * N + 255) / 256, 256, 0, st>>>(captions, N, Tc, p.prev_tok, p.target); KCHECK(h);
     CUDA_TRY(h, cudaMemsetAsync(p.h2_all, 0, (size_t)N * Hp * sizeof(T), st));
     CUDA_TRY(h, cudaMemsetAsync(p.c2_all, 0, (size_t)N * Hp * sizeof(float), st));
+    chain_begin(h, st);
     for (int t = 0; t < T_; ++t) {
         typename EpiLstmFwd<T>::Params ep;
         memset(&ep, 0, sizeof ep);
@@ -593,6 +643,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         ep.seed = drop_seed; ep.stream = S2VT_STREAM_DROP2; ep.step = (uint32_t)t; ep.row_base = row_base; ep.keep = keep;
         TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, p.h2_all + (size_t)t * N * Hp, Hp, h->W2hT, Hp, N, Gp, Hp, ep)));
     }
+    chain_end(h, st);
     {   // logits for all decode steps at once (:163 / :286)
         typename EpiStore<T>::Params ep = {p.logits, nullptr, Vp, h->bo_p, Tc * N, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.out2d, Hp, h->WoT, Hp, Tc * N, Vp, Hp, ep)));
@@ -629,8 +680,27 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         typename EpiStore<T>::Params ep = {p.dout2, nullptr, Hp, nullptr, MD, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dlogits, Vp, h->Wo, Vp, MD, Hp, Vp, ep)));
     }
+    // ---- side stream 1/2: the vocabulary-projection weight gradient only needs dlogits / out2, so it runs (large GEMM, fills
+    //      the idle SMs) while the main stream walks the latency-bound LSTM2 BPTT chain.
+    if (!h->side) {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t s2 = h->side;
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+    CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
+    {   // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums
+        TRY(transpose<T>(h, s2, p.out2d, Hp, MD, Hp, p.tA, MpD, Hp));
+        TRY(transpose<T>(h, s2, p.dlogits, Vp, MD, Vp, p.tB, MpD, Vp));
+        EpiGradStore::Params ep = {h->G_(h->iWo), V, H, V, 0, 1.f};
+        TRY((gemm<T, CfgBig, EpiGradStore>(h, s2, p.tA, MpD, p.tB, MpD, Hp, Vp, MpD, ep, MD, H)));
+        rowsum_grad_kernel<T><<<Vp, 256, 0, s2>>>(p.tB, MpD, MD, V, 0, h->G_(h->ibo)); KCHECK(h);
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
     // LSTM2 BPTT
     CUDA_TRY(h, cudaMemsetAsync(p.dc2, 0, (size_t)N * Hp * sizeof(float), st));
+    chain_begin(h, st);
     for (int t = T_ - 1; t >= 0; --t) {
         LstmBwdArgs b;
         memset(&b, 0, sizeof b);
@@ -646,6 +716,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
             TRY((gemm<T, CfgStep, EpiLstmBwd<T>>(h, st, p.dG2 + (size_t)(t + 1) * N * Gp, Gp, h->W2h, Gp, N, Hp, Gp, ep)));
         }
     }
+    chain_end(h, st);
     {   // gradient flowing into LSTM1's (dropped, shared-per-video) output
         typename EpiStore<T>::Params ep = {p.dout1, nullptr, Hp, nullptr, M2, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2, Gp, h->W2x, Gp, M2, Hp, Gp, ep)));
@@ -653,12 +724,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     }
     // ---- fork: the LSTM1 chain (B rows, few CTAs per step) runs on the side stream while the main stream computes the
     //      LSTM2 / vocabulary weight gradients (large GEMMs); joined before returning.
-    if (!h->side) {
-        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    }
-    cudaStream_t s2 = h->side;
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));   // dWo done: tA / tB are free again
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
     // LSTM1 BPTT over the B shared rows (side stream)
@@ -700,14 +766,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         TRY((gemm<T, CfgBig, EpiGradStore>(h, s2, p.tA2, MpE, p.tB2, MpE, Dp, Ep, MpE, e, ME, D)));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
-    // ---- main stream meanwhile: vocabulary projection, embedding and LSTM2 weight gradients
-    {   // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums
-        TRY(transpose<T>(h, st, p.out2d, Hp, MD, Hp, p.tA, MpD, Hp));
-        TRY(transpose<T>(h, st, p.dlogits, Vp, MD, Vp, p.tB, MpD, Vp));
-        EpiGradStore::Params ep = {h->G_(h->iWo), V, H, V, 0, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Hp, Vp, MpD, ep, MD, H)));
-        rowsum_grad_kernel<T><<<Vp, 256, 0, st>>>(p.tB, MpD, MD, V, 0, h->G_(h->ibo)); KCHECK(h);
-    }
+    // ---- main stream meanwhile: embedding and LSTM2 weight gradients
     {   // word-embedding gradient
         typename EpiStore<T>::Params ee = {p.dEmb, nullptr, Ep, nullptr, MD, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2 + (size_t)Tv * N * Gp, Gp, h->W2e, Gp, MD, Ep, Gp, ee)));
@@ -876,18 +935,18 @@ extern "C" int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, in
         int i = 0;
         for (; i < n; ++i) if (cls[i] == r.cls && M[i] == r.M && N[i] == r.N && K[i] == r.K) break;
         if (i == n) { if (n >= cap) continue; cls[n] = r.cls; M[n] = r.M; N[n] = r.N; K[n] = r.K; ms[n] = 0; count[n] = 0; ++n; }
-        ms[i] += t; count[i] += 1;
+        ms[i] += t; count[i] += r.count;
     }
     return n;
 }
 extern "C" int s2vt_profile_read(s2vt_handle* h, double* ms_out, double* flops_out, long long* launches_out) {
     if (!h || !ms_out || !flops_out || !launches_out) return S2VT_EINVAL;
     CUDA_TRY(h, cudaDeviceSynchronize());
-    for (int c = 0; c < 2; ++c) { ms_out[c] = 0; flops_out[c] = 0; launches_out[c] = 0; }
+    for (int c = 0; c < 2; ++c) { ms_out[c] = 0; flops_out[c] = 0; flops_out[2 + c] = 0; launches_out[c] = 0; }
     for (auto& r : h->prof_recs) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, r.a, r.b);
-        ms_out[r.cls] += ms; flops_out[r.cls] += r.flops; launches_out[r.cls] += 1;
+        ms_out[r.cls] += ms; flops_out[r.cls] += r.flops; flops_out[2 + r.cls] += r.bytes; launches_out[r.cls] += r.count;
         h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b);
     }
     h->prof_recs.clear();

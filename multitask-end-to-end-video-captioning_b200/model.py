@@ -246,9 +246,9 @@ class Video_Caption_Generator(object):
 
     def profile_read(self):
         """-> {'batched': (ms, flops, launches), 'step': (...)} of the GEMM launches since the last read."""
-        ms, fl, n = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
+        ms, fl, n = (C.c_double * 2)(), (C.c_double * 4)(), (C.c_longlong * 2)()
         self._check(self.lib.s2vt_profile_read(self.h, ms, fl, n))
-        return {'batched': (ms[0], fl[0], n[0]), 'step': (ms[1], fl[1], n[1])}
+        return {'batched': (ms[0], fl[0], n[0], fl[2]), 'step': (ms[1], fl[1], n[1], fl[3])}
 
     # ---- drop-in step functions (the literal sess.run contracts) ------------------------------------------------
     def rl_step(self, mask, captions, video, rewards, base_line, lr, clip_norm=5.0, drop_seed=0, n_videos=None):
