@@ -27,8 +27,8 @@ GOLD = os.path.join(ROOT, 'tests', 'golden')
 DIMS = dict(D=1536, E=500, H=1000, V=9972)
 METRIC = 'reinforce_train_videos_per_s'
 # dram__bytes_read.sum + dram__bytes_write.sum per recurrent-step launch under ncu (cache flushed before each kernel), mean over the
-# step kernels of one iteration -- profiles/r1_tc_metrics.md
-STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = None
+# step kernels of one iteration -- profiles/r1_tc_metrics.md (457 launches)
+STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = 14812657
 
 
 def parse():
@@ -291,6 +291,15 @@ def run_b200(args):
     prof = model.profile_read()
     model.profile(False)
     loss = float(trainer.step(feats_dev, vidx_dev)[1].item())
+    # secondary BASELINE metric: beam-5 decode captions/s (e2e_beam_search.py semantics, length normalisation 1), batch = B videos
+    beam = {}
+    if world == 1:
+        for _ in range(2):
+            model.beam_search(feats_dev, 5, 1.0)
+        bs_ms = timed(3, lambda: model.beam_search(feats_dev, 5, 1.0))
+        gr_ms = timed(3, lambda: model.greedy(feats_dev))
+        beam = {'beam5_captions_per_s': 3 * B / (bs_ms / 1e3), 'beam5_ms_per_batch': bs_ms / 3, 'greedy_captions_per_s': 3 * B / (gr_ms / 1e3),
+                'batch': B, 'T_v': Tv, 'beam_size': 5, 'length_normalization_factor': 1.0}
     if rank != 0:
         return
     peaks = {}
@@ -310,7 +319,7 @@ def run_b200(args):
            'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': workload_config(args, B, world),
            'clocks': clocks, 'e2e': {'value': e2e, 'unit': 'videos/s', 'h2d_bytes_per_step': int(feats_host.numel() * 4 + vidx_host.numel() * 4),
                                      'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps},
-           'gpu_launches': int(launches), 'loss': loss,
+           'gpu_launches': int(launches), 'loss': loss, 'decode': beam,
            'gemm_shapes': [{'class': 'batched' if c == 0 else 'step', 'M': M_, 'N': N_, 'K': K_, 'launches_per_step': n_ / args.steps,
                             'us_per_launch': 1e3 * ms_ / n_, 'ms_per_step': ms_ / args.steps} for c, M_, N_, K_, ms_, n_ in sorted(shapes, key=lambda x: -x[4])],
            # dominant kernel family by time: the per-time-step recurrent GEMM + fused LSTM cell (tcgen05, one launch per step)

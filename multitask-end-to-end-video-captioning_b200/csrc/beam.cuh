@@ -226,6 +226,8 @@ template <typename T>
 static int beam_step_impl(s2vt_handle* h, cudaStream_t st, const float* state2, const float* state1, const int32_t* word, int k, int32_t* idx_out,
                           float* prob_out, float* state2_out, float* state1_out) {
     const int Hp = h->Hp, H = h->H, Gp = h->Gp, Vp = h->Vp;
+    h->front_valid = false;
+    TRY(wait_late_weights(h, st));
     Arena a(h->ws, h->ws_bytes);
     float* c1 = a.take<float>(Hp); T* h1 = a.take<T>(Hp); float* c1n = a.take<float>(Hp); T* h1n = a.take<T>(Hp); float* h1F = a.take<float>(Hp);
     float* c2 = a.take<float>(Hp); T* h2 = a.take<T>(Hp); float* c2n = a.take<float>(Hp); T* h2n = a.take<T>(Hp); float* h2F = a.take<float>(Hp);

@@ -62,7 +62,8 @@ struct s2vt_handle {
     bool reuse_front = false, front_valid = false;
     int front_B = 0; const float* front_video = nullptr;
     // internal side stream for the LSTM1 backward chain (fork/join inside one call; invisible to the caller)
-    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;             // tc::MapCache (TMA tensor maps keyed by pointer / shape)
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_refresh = nullptr;
+    bool copies_zeroed = false;             // tc::MapCache (TMA tensor maps keyed by pointer / shape)
     // variable indices
     int iWemb, iWe, ibe, iWo, ibo, iW1, ib1, iW2, ib2, iAW, iAb;
     mutable std::string err;

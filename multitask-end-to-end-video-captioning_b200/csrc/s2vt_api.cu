@@ -166,7 +166,7 @@ extern "C" int s2vt_set_reuse_frontend(s2vt_handle* h, int enable) {
     return 0;
 }
 extern "C" void s2vt_destroy(s2vt_handle* h) {
-    if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+    if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_refresh); }
     if (h && h->tc_cache) delete static_cast<tc::MapCache*>(h->tc_cache);
     delete h;
 }
@@ -343,6 +343,21 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
 }
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
 
+static int ensure_side(s2vt_handle* h) {
+    if (h->side) return 0;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_refresh, cudaEventDisableTiming));
+    return 0;
+}
+// The "late" half of a refresh (everything but the frame projection / LSTM1 forward weights) runs on the side stream;
+// consumers on the caller's stream wait for it here.  A no-op when no refresh is in flight.
+static int wait_late_weights(s2vt_handle* h, cudaStream_t st) {
+    if (h->ev_refresh) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_refresh, 0));
+    return 0;
+}
+
 template <typename T>
 static int refresh_impl(s2vt_handle* h, cudaStream_t st) {
     const int E = h->E, H = h->H, V = h->V, D = h->D, Dp = h->Dp, Ep = h->Ep, Hp = h->Hp, Vp = h->Vp, Gp = h->Gp;
@@ -353,31 +368,41 @@ static int refresh_impl(s2vt_handle* h, cudaStream_t st) {
         layout_state(h, a, [&](float*, float*, float*, float*, double*, float*, char*, char*, char*, char*, char*, char*, char*, char*, char*, char*, char*,
                                char*, char*, char*, char*, float*, float*, float*, float*, float*, size_t b, size_t e) { begin = b; end = e; });
     }
-    CUDA_TRY(h, cudaMemsetAsync(h->state + begin, 0, end - begin, st));
+    if (!h->copies_zeroed) {   // the pads are never written afterwards
+        CUDA_TRY(h, cudaMemsetAsync(h->state + begin, 0, end - begin, st));
+        h->copies_zeroed = true;
+    }
     const float* W1 = h->P_(h->iW1); const float* W2 = h->P_(h->iW2);
     const int G = 4 * H;
+    TRY(ensure_side(h));
+    cudaStream_t s2 = h->side;
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));                 // parameters (and the zeroing) are final on `st` here
+    CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
+    // early half, caller's stream: what the next call needs first (frame projection and LSTM1 forward)
     TRY(pack<T>(h, st, h->P_(h->iWe), E, D, E, h->WeT, Dp, 0, 1));                         // WeT [Ep, Dp]
     TRY(pack<T>(h, st, W1, G, E, G, h->W1xT, Ep, H, 1));                                   // W1xT [Gp, Ep]
-    TRY(pack<T>(h, st, W1, G, E, G, h->W1x, Gp, H, 0));                                    // W1x  [Ep, Gp]
     TRY(pack<T>(h, st, W1 + (size_t)E * G, G, H, G, h->W1hT, Hp, H, 1));                   // W1hT [Gp, Hp]
-    TRY(pack<T>(h, st, W1 + (size_t)E * G, G, H, G, h->W1h, Gp, H, 0));                    // W1h  [Hp, Gp]
-    TRY(pack<T>(h, st, W2, G, H, G, h->W2xT, Hp, H, 1));                                   // rows [0,H): out1
-    TRY(pack<T>(h, st, W2, G, H, G, h->W2x, Gp, H, 0));
-    TRY(pack<T>(h, st, W2 + (size_t)H * G, G, E, G, h->W2eT, Ep, H, 1));                   // rows [H,H+E): word embedding
-    TRY(pack<T>(h, st, W2 + (size_t)H * G, G, E, G, h->W2e, Gp, H, 0));
-    TRY(pack<T>(h, st, W2 + (size_t)(H + E) * G, G, H, G, h->W2hT, Hp, H, 1));             // rows [H+E, 2H+E): h2
-    TRY(pack<T>(h, st, W2 + (size_t)(H + E) * G, G, H, G, h->W2h, Gp, H, 0));
-    TRY(pack<T>(h, st, h->P_(h->iWo), V, H, V, h->WoT, Hp, 0, 1));                         // WoT [Vp, Hp]
-    TRY(pack<T>(h, st, h->P_(h->iWo), V, H, V, h->Wo, Vp, 0, 0));                          // Wo  [Hp, Vp]
-    TRY(pack<T>(h, st, h->P_(h->iWemb), E, V, E, h->WembC, Ep, 0, 0));                     // Wemb [Vp, Ep]
-    if (h->A) TRY(pack<T>(h, st, h->P_(h->iAW), h->A, D, h->A, h->attrWT, Dp, 0, 1));      // attrWT [Ap, Dp]
     pack_vector_kernel<<<(E + 255) / 256, 256, 0, st>>>(h->P_(h->ibe), E, h->be_p, 0); KCHECK(h);
     pack_vector_kernel<<<(G + 255) / 256, 256, 0, st>>>(h->P_(h->ib1), G, h->b1_p, H); KCHECK(h);
-    pack_vector_kernel<<<(G + 255) / 256, 256, 0, st>>>(h->P_(h->ib2), G, h->b2_p, H); KCHECK(h);
-    pack_vector_kernel<<<(V + 255) / 256, 256, 0, st>>>(h->P_(h->ibo), V, h->bo_p, 0); KCHECK(h);
+    // late half, side stream: overlaps the next call's frame projection and LSTM1 chain (see wait_late_weights)
+    TRY(pack<T>(h, s2, W1, G, E, G, h->W1x, Gp, H, 0));                                    // W1x  [Ep, Gp]
+    TRY(pack<T>(h, s2, W1 + (size_t)E * G, G, H, G, h->W1h, Gp, H, 0));                    // W1h  [Hp, Gp]
+    TRY(pack<T>(h, s2, W2, G, H, G, h->W2xT, Hp, H, 1));                                   // rows [0,H): out1
+    TRY(pack<T>(h, s2, W2, G, H, G, h->W2x, Gp, H, 0));
+    TRY(pack<T>(h, s2, W2 + (size_t)H * G, G, E, G, h->W2eT, Ep, H, 1));                   // rows [H,H+E): word embedding
+    TRY(pack<T>(h, s2, W2 + (size_t)H * G, G, E, G, h->W2e, Gp, H, 0));
+    TRY(pack<T>(h, s2, W2 + (size_t)(H + E) * G, G, H, G, h->W2hT, Hp, H, 1));             // rows [H+E, 2H+E): h2
+    TRY(pack<T>(h, s2, W2 + (size_t)(H + E) * G, G, H, G, h->W2h, Gp, H, 0));
+    TRY(pack<T>(h, s2, h->P_(h->iWo), V, H, V, h->WoT, Hp, 0, 1));                         // WoT [Vp, Hp]
+    TRY(pack<T>(h, s2, h->P_(h->iWo), V, H, V, h->Wo, Vp, 0, 0));                          // Wo  [Hp, Vp]
+    TRY(pack<T>(h, s2, h->P_(h->iWemb), E, V, E, h->WembC, Ep, 0, 0));                     // Wemb [Vp, Ep]
+    if (h->A) TRY(pack<T>(h, s2, h->P_(h->iAW), h->A, D, h->A, h->attrWT, Dp, 0, 1));      // attrWT [Ap, Dp]
+    pack_vector_kernel<<<(G + 255) / 256, 256, 0, s2>>>(h->P_(h->ib2), G, h->b2_p, H); KCHECK(h);
+    pack_vector_kernel<<<(V + 255) / 256, 256, 0, s2>>>(h->P_(h->ibo), V, h->bo_p, 0); KCHECK(h);
     // Etab[v, :] = Wemb[v, :] . W2[emb rows]  (packed gate order) -- the word-embedding contribution to LSTM2's gates
     typename EpiStore<T>::Params ep = {h->Etab, nullptr, Gp, nullptr, Vp, 0};
-    TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, h->WembC, Ep, h->W2eT, Ep, Vp, Gp, Ep, ep)));
+    TRY((gemm<T, CfgBig, EpiStore<T>>(h, s2, h->WembC, Ep, h->W2eT, Ep, Vp, Gp, Ep, ep)));
+    CUDA_TRY(h, cudaEventRecord(h->ev_refresh, s2));
     h->fresh = true;
     h->front_valid = false;
     return 0;
@@ -458,6 +483,7 @@ static int run_encoder(s2vt_handle* h, cudaStream_t st, const float* video, int 
     h->front_valid = false;
     TRY(run_front<T>(h, st, video, B, r.f));
     h->front_valid = true; h->front_B = B; h->front_video = video;
+    TRY(wait_late_weights(h, st));
     {   // G2x = h1 . W2[out1 rows] for every step (bare cells: no dropout in the samplers, Q2)
         typename EpiStore<T>::Params ep = {r.G2x, nullptr, Gp, nullptr, T_ * B, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, r.f.h1_all + (size_t)B * Hp, Hp, h->W2xT, Hp, T_ * B, Gp, Hp, ep)));
@@ -622,6 +648,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         h->front_valid = false;
         TRY(run_front<T>(h, st, video, B, p.f));
     }
+    TRY(wait_late_weights(h, st));
     expand_dropout_kernel<T><<<T_ * N, 256, 0, st>>>(p.f.h1_all + (size_t)B * Hp, B, N, Hp, H, p.out1d, drop_seed, S2VT_STREAM_DROP1, row_base, keep);
     KCHECK(h);
     {
@@ -682,11 +709,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     }
     // ---- side stream 1/2: the vocabulary-projection weight gradient only needs dlogits / out2, so it runs (large GEMM, fills
     //      the idle SMs) while the main stream walks the latency-bound LSTM2 BPTT chain.
-    if (!h->side) {
-        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    }
+    TRY(ensure_side(h));
     cudaStream_t s2 = h->side;
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
@@ -840,6 +863,7 @@ template <typename T>
 static int attribute_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B, const float* labels, float grad_scale, float* loss_out) {
     const int A = h->A, Ap = h->Ap, D = h->D, Dp = h->Dp, Bp = ru(B, S2VT_PAD);
     h->front_valid = false;
+    TRY(wait_late_weights(h, st));
     Arena a(h->ws, h->ws_bytes);
     T* pooled = a.take<T>((size_t)B * Dp);
     float* z = a.take<float>((size_t)B * Ap);
@@ -878,6 +902,7 @@ extern "C" int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, in
     if (step < 1) return h->fail(S2VT_EINVAL, "Adam step is 1-based");
     cudaStream_t st = (cudaStream_t)st_;
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    TRY(wait_late_weights(h, st));   // a previous refresh may still be reading the parameters on the side stream
     CUDA_TRY(h, cudaMemsetAsync(h->sq, 0, 3 * sizeof(double), st));
     sumsq_kernel<<<148 * 4, 256, 0, st>>>(h->grads, h->P, h->sq); KCHECK(h);
     const Var& we = h->vars[h->iWemb];
