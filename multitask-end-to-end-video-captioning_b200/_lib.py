@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libs2vt_b200.so')
+LIB_PATH = os.environ.get('S2VT_LIB') or os.path.join(HERE, 'libs2vt_b200.so')   # S2VT_LIB: experimental builds (debug only)
 
 
 class S2vtConfig(C.Structure):

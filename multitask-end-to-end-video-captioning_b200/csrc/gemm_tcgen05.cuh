@@ -63,14 +63,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) { printf("s2vt: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
     }
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+__device__ __forceinline__ void tma_load_2d_raw(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+#ifdef S2VT_TMA_SPLIT
+// experiment: the tensor maps are built with 64-row boxes and every tile is fetched as rows/64 separate TMA instructions
+__device__ int g_split_rows_a, g_split_rows_b;
+#endif
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer, int rows = 0) {
+#ifdef S2VT_TMA_SPLIT
+    for (int r = 0; r < rows; r += 64) tma_load_2d_raw((char*)smem_dst + r * 128, map, bar, c_inner, c_outer + r);
+#else
+    tma_load_2d_raw(smem_dst, map, bar, c_inner, c_outer);
+#endif
 }
 // K-major, 128-byte swizzle smem matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO=1 [16,30),
 // SBO = 1024 B >> 4 = 64 [32,46) (stride between 8-row groups), version 1 at [46,48), SWIZZLE_128B = 2 at [61,64)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major, 128-byte swizzle: each K index is a 128-byte row of 64 MN-contiguous elements (what a TMA box {64 features,
+// 64 rows} of a row-major [rows, features] matrix produces); 8 K rows form a 1024-byte atom (SBO), the next 64 MN
+// elements live one box (8192 bytes) further (LBO).  cute::UMMA canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (512ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -151,7 +168,9 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
 // the same way.  L2 reads per CTA drop from (128 + BN) to (128/CX + BN/CY) rows per K-block.  A stage may only be refilled
 // when every CTA that receives part of it has consumed it: the MMA warp's tcgen05.commit arrives (multicast) on the
 // `empty` barrier of each CTA that sends to it, and `empty` counts CX + CY - 1 arrivals.
-template <int BN, class Epi, int KS, int CX = 1, int CY = 1>
+// MN == true: both operands are MN-major -- C[Mf, Nf] = sum_r X[r, Mf] . Y[r, Nf] for row-major X, Y (the weight-gradient
+// products), so no transposed copies are needed; the contraction runs over rows and its tail is zero-filled by TMA.
+template <int BN, class Epi, int KS, int CX = 1, int CY = 1, bool MN = false>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                       int K, int a_rows, typename Epi::Params ep) {
     // a_rows: rows of the A K-block actually fetched (TMA box height).  Problems with M <= 64 fetch 64 rows only; the rest of
@@ -159,9 +178,11 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     using C = Cfg<BN, Threads<BN, Epi>::N>;
     static_assert(KS == 1 || (KS == 4 && Epi::kDirect), "split-K needs a direct epilogue and a cluster of 4");
     static_assert(KS == 1 || (CX == 1 && CY == 1), "split-K and multicast clusters are exclusive");
+    static_assert(!MN || (KS == 1 && CX == 1 && CY == 1), "MN-major operands: plain kernel only");
+    constexpr uint32_t IDESC = C::IDESC | (MN ? ((1u << 15) | (1u << 16)) : 0u);
     constexpr bool MC = CX * CY > 1;
     constexpr int A_ROWS = BM / CX, B_ROWS = BN / CY;   // rows this CTA fetches of each tile
-    const uint32_t stage_tx = (uint32_t)(MC ? C::STAGE_BYTES : a_rows * 128 + C::B_BYTES);
+    const uint32_t stage_tx = (uint32_t)((MC || MN) ? C::STAGE_BYTES : a_rows * 128 + C::B_BYTES);
     uint32_t crank = 0;
     if constexpr (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const int cx = crank % CX, cy = crank / CX;
@@ -182,7 +203,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * C::BM, n0 = blockIdx.x * BN;
     const int rank = KS > 1 ? (int)blockIdx.z : 0;
-    const int KBL = K / C::BK / KS, kb0 = rank * KBL;   // this CTA's K-blocks
+    const int KBL = MN ? (K + C::BK - 1) / C::BK : K / C::BK / KS, kb0 = rank * KBL;   // this CTA's K-blocks (MN: ragged tail is zero-filled)
     __shared__ unsigned long long* probe;
     if (threadIdx.x == 0) {
         probe = nullptr;
@@ -217,8 +238,12 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
         for (int i = 0; i < pre; ++i) {
             mbar_expect_tx(full + i, stage_tx);
             unsigned char* b = smem + i * C::STAGE_BYTES + C::A_BYTES + cy * B_ROWS * 128;
-            if constexpr (CY > 1) tma_load_2d_mc(b, &mapB, full + i, (kb0 + i) * C::BK, n0 + cy * B_ROWS, col_mask);
-            else tma_load_2d(b, &mapB, full + i, (kb0 + i) * C::BK, n0);
+            if constexpr (MN) {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) tma_load_2d_raw(b + j * 8192, &mapB, full + i, n0 + 64 * j, (kb0 + i) * C::BK);
+            }
+            else if constexpr (CY > 1) tma_load_2d_mc(b, &mapB, full + i, (kb0 + i) * C::BK, n0 + cy * B_ROWS, col_mask);
+            else tma_load_2d(b, &mapB, full + i, (kb0 + i) * C::BK, n0, BN);
         }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -233,11 +258,19 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
                     mbar_wait(empty + s, ((i / C::STAGES) - 1) & 1);
                     mbar_expect_tx(full + s, stage_tx);
                     unsigned char* b = a + C::A_BYTES + cy * B_ROWS * 128;
-                    if constexpr (CY > 1) tma_load_2d_mc(b, &mapB, full + s, (kb0 + i) * C::BK, n0 + cy * B_ROWS, col_mask);
-                    else tma_load_2d(b, &mapB, full + s, (kb0 + i) * C::BK, n0);
+                    if constexpr (MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d_raw(b + j * 8192, &mapB, full + s, n0 + 64 * j, (kb0 + i) * C::BK);
+                    }
+                    else if constexpr (CY > 1) tma_load_2d_mc(b, &mapB, full + s, (kb0 + i) * C::BK, n0 + cy * B_ROWS, col_mask);
+                    else tma_load_2d(b, &mapB, full + s, (kb0 + i) * C::BK, n0, BN);
                 }
-                if constexpr (CX > 1) tma_load_2d_mc(a + cx * A_ROWS * 128, &mapA, full + s, (kb0 + i) * C::BK, m0 + cx * A_ROWS, row_mask);
-                else tma_load_2d(a, &mapA, full + s, (kb0 + i) * C::BK, m0);
+                if constexpr (MN) {
+                    tma_load_2d_raw(a, &mapA, full + s, m0, (kb0 + i) * C::BK);
+                    tma_load_2d_raw(a + 8192, &mapA, full + s, m0 + 64, (kb0 + i) * C::BK);
+                }
+                else if constexpr (CX > 1) tma_load_2d_mc(a + cx * A_ROWS * 128, &mapA, full + s, (kb0 + i) * C::BK, m0 + cx * A_ROWS, row_mask);
+                else tma_load_2d(a, &mapA, full + s, (kb0 + i) * C::BK, m0, a_rows);
             }
         }
         __syncwarp();
@@ -249,10 +282,11 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
                 if (probe && i == 0) probe[2] = gtimer();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a = smem_u32(smem + s * C::STAGE_BYTES);
-                const uint64_t adesc = make_desc(a), bdesc = make_desc(a + C::A_BYTES);
+                const uint64_t adesc = MN ? make_desc_mn(a) : make_desc(a), bdesc = MN ? make_desc_mn(a + C::A_BYTES) : make_desc(a + C::A_BYTES);
+                constexpr int KADV = MN ? 128 : 2;      // K-major: +32 bytes per K=16 step inside the swizzle atom; MN-major: +16 rows = 2048 bytes
 #pragma unroll
-                for (int k = 0; k < C::BK / 16; ++k)   // +32 bytes (>>4 = 2) per K=16 step inside the 128-byte swizzle atom
-                    mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (i | k) != 0);
+                for (int k = 0; k < C::BK / 16; ++k)
+                    mma_bf16(tmem_base, adesc + KADV * k, bdesc + KADV * k, IDESC, (i | k) != 0);
                 if constexpr (MC) mma_commit_mc(empty + s, (uint16_t)(row_mask | col_mask));
                 else mma_commit(empty + s);             // implies tcgen05.fence::before_thread_sync
             }
@@ -385,7 +419,9 @@ inline const CUtensorMap* get_map(MapCache& cache, const void* ptr, int rows, in
     return &cache.emplace(key, m).first->second;
 }
 
-template <int BN, class Epi, int KS = 1, int CX = 1, int CY = 1>
+// MN == false: A [M, K], B [N, K] row-major (K-major operands).  MN == true: A = X [K rows, M features], B = Y [K rows, N features]
+// row-major; C[M, N] = X^T . Y.
+template <int BN, class Epi, int KS = 1, int CX = 1, int CY = 1, bool MN = false>
 inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K,
                           const typename Epi::Params& ep, bool pdl = false) {
     if (M <= 0) return cudaSuccess;
@@ -394,10 +430,15 @@ inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int l
     constexpr int SMEM = C::SMEM_BYTES + (KS > 1 ? KS * 32 * BN * 4 : 0);
     if (cache.size() > 32768) cache.clear();   // before either lookup: element pointers stay valid across inserts, not across clear
     const int a_rows = (CX == 1 && M <= 64) ? ((M + 7) & ~7) : BM;
-    const CUtensorMap* ma = get_map(cache, A, M, K, lda, CX == 1 ? a_rows : BM / CX);
-    const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN / CY);
+#ifdef S2VT_TMA_SPLIT
+    const CUtensorMap* ma = get_map(cache, A, M, K, lda, a_rows < 64 ? a_rows : 64);
+    const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN < 64 ? BN : 64);
+#else
+    const CUtensorMap* ma = MN ? get_map(cache, A, K, M, lda, 64) : get_map(cache, A, M, K, lda, CX == 1 ? a_rows : BM / CX);
+    const CUtensorMap* mb = MN ? get_map(cache, B, K, N, ldb, 64) : get_map(cache, B, N, K, ldb, BN / CY);
+#endif
     if (!ma || !mb) return cudaErrorInvalidValue;
-    auto kern = gemm_tc_kernel<BN, Epi, KS, CX, CY>;
+    auto kern = gemm_tc_kernel<BN, Epi, KS, CX, CY, MN>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);

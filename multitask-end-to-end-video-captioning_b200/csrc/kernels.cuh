@@ -381,6 +381,34 @@ __global__ void rowsum_grad_kernel(const T* __restrict__ XT, int ld, int R, int 
     if (threadIdx.x == 0) grad[dst] += acc;
 }
 
+// Bias gradients straight from a row-major gradient matrix Y [R, ld]: column sums over the R rows (coalesced 2-column
+// loads; rows split over blockIdx.y, partial sums combined with atomicAdd).  Column mapping as in rowsum_grad_kernel.
+template <typename T>
+__global__ void colsum_grad_kernel(const T* __restrict__ Y, int ld, int R, int ncols, int gate_h, float* __restrict__ grad) {
+    __shared__ float red[8][64];
+    const int c = blockIdx.x * 64 + threadIdx.x * 2;
+    const int rows_per = (R + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+        const T* q = Y + (size_t)r * ld + c;
+        a0 += to_f32(q[0]); a1 += to_f32(q[1]);
+    }
+    red[threadIdx.y][threadIdx.x * 2] = a0; red[threadIdx.y][threadIdx.x * 2 + 1] = a1;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            float acc = 0.f;
+            for (int j = 0; j < 8; ++j) acc += red[j][threadIdx.x * 2 + e];
+            int cc = c + e, dst;
+            if (gate_h > 0) { int u = cc >> 2, g = cc & 3; if (u >= gate_h) continue; dst = g * gate_h + u; }
+            else { if (cc >= ncols) continue; dst = cc; }
+            atomicAdd(grad + dst, acc);
+        }
+    }
+}
+
 // ---- optimiser --------------------------------------------------------------------------------------------------
 // sum of squares of a float range into a double accumulator (global-norm clip)
 __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ out) {

@@ -341,7 +341,46 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
     if (bracket) { cudaEventRecord(rec.b, st); h->prof_recs.push_back(rec); }
     return 0;
 }
+
+// Weight gradient  grad (+)= X^T . Y  over R rows (X [R, ldx]: Mf padded features, Y [R, ldy]: Nf padded features).
+// tcgen05 path: MN-major operand descriptors read X and Y as they lie (no transposed copies, ragged R zero-filled by TMA).
+// Other mainloops need K-major operands: X and Y are transposed into the scratch buffers first.
+template <typename T> static int transpose(s2vt_handle* h, cudaStream_t st, const T* src, int lds, int R, int C, T* dst, int ldd, int rows_dst_padded);
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+template <typename T>
+static int wgrad(s2vt_handle* h, cudaStream_t st, const T* X, int ldx, int Mf, const T* Y, int ldy, int Nf, int R, const EpiGradStore::Params& ep,
+                 T* tA, T* tB, int logical_m) {
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC && h->cfg.gemm_backend != 8) {
+            s2vt_handle::ProfRec rec;
+            if (h->prof) {
+                rec.a = prof_event(h); rec.b = prof_event(h);
+                rec.flops = 2.0 * logical_m * logical_dim(h, Nf) * (double)R;
+                rec.bytes = ((double)logical_m + logical_dim(h, Nf)) * R * sizeof(T);
+                rec.cls = 0; rec.M = Mf; rec.N = Nf; rec.K = R; rec.count = 1;
+                cudaEventRecord(rec.a, st);
+            }
+            h->launches++;
+            if (!h->tc_cache) h->tc_cache = new tc::MapCache();
+            tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
+            if (Nf % 256 == 0) CUDA_TRY(h, (tc::launch<256, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false)));
+            else CUDA_TRY(h, (tc::launch<128, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false)));
+            if (h->prof) { cudaEventRecord(rec.b, st); h->prof_recs.push_back(rec); }
+            return 0;
+        }
+    }
+    const int Rp = ru(R, S2VT_PAD);
+    TRY(transpose<T>(h, st, X, ldx, R, Mf, tA, Rp, Mf));
+    TRY(transpose<T>(h, st, Y, ldy, R, Nf, tB, Rp, Nf));
+    return gemm<T, CfgBig, EpiGradStore>(h, st, tA, Rp, tB, Rp, Mf, Nf, Rp, ep, R, logical_m);
+}
+template <typename T>
+static int bias_grad(s2vt_handle* h, cudaStream_t st, const T* Y, int ldy, int Cpad, int R, int ncols, int gate_h, float* grad) {
+    dim3 grid(Cpad / 64, R >= 4096 ? 16 : (R >= 256 ? 4 : 1)), block(32, 8);
+    colsum_grad_kernel<T><<<grid, block, 0, st>>>(Y, ldy, R, ncols, gate_h, grad);
+    KCHECK(h);
+    return 0;
+}
 
 static int ensure_side(s2vt_handle* h) {
     if (h->side) return 0;
@@ -714,11 +753,9 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
     {   // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums
-        TRY(transpose<T>(h, s2, p.out2d, Hp, MD, Hp, p.tA, MpD, Hp));
-        TRY(transpose<T>(h, s2, p.dlogits, Vp, MD, Vp, p.tB, MpD, Vp));
         EpiGradStore::Params ep = {h->G_(h->iWo), V, H, V, 0, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, s2, p.tA, MpD, p.tB, MpD, Hp, Vp, MpD, ep, MD, H)));
-        rowsum_grad_kernel<T><<<Vp, 256, 0, s2>>>(p.tB, MpD, MD, V, 0, h->G_(h->ibo)); KCHECK(h);
+        TRY(wgrad<T>(h, s2, p.out2d, Hp, Hp, p.dlogits, Vp, Vp, MD, ep, p.tA, p.tB, H));
+        TRY(bias_grad<T>(h, s2, p.dlogits, Vp, Vp, MD, V, 0, h->G_(h->ibo)));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
     // LSTM2 BPTT
@@ -768,25 +805,19 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     }
     {   // LSTM1 kernel / bias gradients (side stream, own transpose scratch)
         float* gW1 = h->G_(h->iW1);
-        TRY(transpose<T>(h, s2, p.dG1, Gp, M1, Gp, p.tB2, Mp1, Gp));
-        rowsum_grad_kernel<T><<<Gp, 256, 0, s2>>>(p.tB2, Mp1, M1, 0, H, h->G_(h->ib1)); KCHECK(h);
-        TRY(transpose<T>(h, s2, p.f.h1_all, Hp, M1, Hp, p.tA2, Mp1, Hp));
+        TRY(bias_grad<T>(h, s2, p.dG1, Gp, Gp, M1, 0, H, h->G_(h->ib1)));
         EpiGradStore::Params e2 = {gW1 + (size_t)E * G, G, H, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, s2, p.tA2, Mp1, p.tB2, Mp1, Hp, Gp, Mp1, e2, M1, H)));
+        TRY(wgrad<T>(h, s2, p.f.h1_all, Hp, Hp, p.dG1, Gp, Gp, M1, e2, p.tA2, p.tB2, H));     // h1 before step t = h1_all[t]
         // frame-embedding rows: encoder steps only
-        TRY(transpose<T>(h, s2, p.dG1, Gp, ME, Gp, p.tB2, MpE, Gp));
-        TRY(transpose<T>(h, s2, p.f.img, Ep, ME, Ep, p.tA2, MpE, Ep));
         EpiGradStore::Params e1 = {gW1, G, E, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, s2, p.tA2, MpE, p.tB2, MpE, Ep, Gp, MpE, e1, ME, E)));
+        TRY(wgrad<T>(h, s2, p.f.img, Ep, Ep, p.dG1, Gp, Gp, ME, e1, p.tA2, p.tB2, E));
     }
     {   // frame projection gradients: dimg = dG1[enc] . W1[x rows]^T ; dWe = X^T . dimg ; dbe = column sums (side stream)
         typename EpiStore<T>::Params ep = {p.dimgF, p.dimgT_src, Ep, nullptr, ME, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, s2, p.dG1, Gp, h->W1x, Gp, ME, Ep, Gp, ep)));
-        TRY(transpose<T>(h, s2, p.dimgT_src, Ep, ME, Ep, p.tB2, MpE, Ep));
-        rowsum_grad_kernel<T><<<Ep, 256, 0, s2>>>(p.tB2, MpE, ME, E, 0, h->G_(h->ibe)); KCHECK(h);
-        TRY(transpose<T>(h, s2, p.f.Xc, Dp, ME, Dp, p.tA2, MpE, Dp));
+        TRY(bias_grad<T>(h, s2, p.dimgT_src, Ep, Ep, ME, E, 0, h->G_(h->ibe)));
         EpiGradStore::Params e = {h->G_(h->iWe), E, D, E, 0, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, s2, p.tA2, MpE, p.tB2, MpE, Dp, Ep, MpE, e, ME, D)));
+        TRY(wgrad<T>(h, s2, p.f.Xc, Dp, Dp, p.dimgT_src, Ep, Ep, ME, e, p.tA2, p.tB2, D));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
     // ---- main stream meanwhile: embedding and LSTM2 weight gradients
@@ -797,20 +828,15 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     }
     {   // LSTM2 kernel / bias gradients: [out1 ; emb ; h2]^T . dG2
         float* gW2 = h->G_(h->iW2);
-        TRY(transpose<T>(h, st, p.dG2, Gp, M2, Gp, p.tB, Mp2, Gp));
-        rowsum_grad_kernel<T><<<Gp, 256, 0, st>>>(p.tB, Mp2, M2, 0, H, h->G_(h->ib2)); KCHECK(h);
-        TRY(transpose<T>(h, st, p.out1d, Hp, M2, Hp, p.tA, Mp2, Hp));
+        TRY(bias_grad<T>(h, st, p.dG2, Gp, Gp, M2, 0, H, h->G_(h->ib2)));
         EpiGradStore::Params e1 = {gW2, G, H, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp2, p.tB, Mp2, Hp, Gp, Mp2, e1, M2, H)));
-        TRY(transpose<T>(h, st, p.h2_all, Hp, M2, Hp, p.tA, Mp2, Hp));       // h2 before step t = h2_all[t]
+        TRY(wgrad<T>(h, st, p.out1d, Hp, Hp, p.dG2, Gp, Gp, M2, e1, p.tA, p.tB, H));
         EpiGradStore::Params e3 = {gW2 + (size_t)(H + E) * G, G, H, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, Mp2, p.tB, Mp2, Hp, Gp, Mp2, e3, M2, H)));
+        TRY(wgrad<T>(h, st, p.h2_all, Hp, Hp, p.dG2, Gp, Gp, M2, e3, p.tA, p.tB, H));          // h2 before step t = h2_all[t]
         // embedding rows: decode steps only
-        TRY(transpose<T>(h, st, p.dG2 + (size_t)Tv * N * Gp, Gp, MD, Gp, p.tB, MpD, Gp));
         gather_rows_kernel<T><<<MD, 128, 0, st>>>((const T*)h->WembC, Ep, p.prev_tok, MD, p.emb); KCHECK(h);
-        TRY(transpose<T>(h, st, p.emb, Ep, MD, Ep, p.tA, MpD, Ep));
         EpiGradStore::Params e2 = {gW2 + (size_t)H * G, G, E, G, H, 1.f};
-        TRY((gemm<T, CfgBig, EpiGradStore>(h, st, p.tA, MpD, p.tB, MpD, Ep, Gp, MpD, e2, MD, E)));
+        TRY(wgrad<T>(h, st, p.emb, Ep, Ep, p.dG2 + (size_t)Tv * N * Gp, Gp, Gp, MD, e2, p.tA, p.tB, E));
     }
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));   // join
     if (mode == 1 && decay > 0.f) {   // Q4: L2 on every variable without 'bias' in its name (the LSTM '/biases' only)
@@ -879,11 +905,9 @@ static int attribute_impl(s2vt_handle* h, cudaStream_t st, const float* video, i
     TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, pooled, Dp, h->attrWT, Dp, B, Ap, Dp, ep)));
     sigmoid_ce_kernel<T><<<1, 256, 0, st>>>(z, Ap, labels, B, A, Ap, grad_scale, dz, h->scal + 8); KCHECK(h);
     if (loss_out) CUDA_TRY(h, cudaMemcpyAsync(loss_out, h->scal + 8, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    TRY(transpose<T>(h, st, pooled, Dp, B, Dp, pooledT, Bp, Dp));
-    TRY(transpose<T>(h, st, dz, Ap, B, Ap, dzT, Bp, Ap));
     EpiGradStore::Params eg = {h->G_(h->iAW), A, D, A, 0, 1.f};
-    TRY((gemm<T, CfgBig, EpiGradStore>(h, st, pooledT, Bp, dzT, Bp, Dp, Ap, Bp, eg)));
-    rowsum_grad_kernel<T><<<Ap, 256, 0, st>>>(dzT, Bp, B, A, 0, h->G_(h->iAb)); KCHECK(h);
+    TRY(wgrad<T>(h, st, pooled, Dp, Dp, dz, Ap, Ap, B, eg, pooledT, dzT, D));
+    TRY(bias_grad<T>(h, st, dz, Ap, Ap, B, A, 0, h->G_(h->iAb)));
     return 0;
 }
 
