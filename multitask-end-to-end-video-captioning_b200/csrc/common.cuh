@@ -55,6 +55,27 @@ __device__ __forceinline__ float4 dropout_mult4(unsigned long long seed, uint32_
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Gate non-linearities by compute dtype: fp32 mode uses the accurate library functions; bf16 mode the MUFU paths
+// (ex2 + rcp, absolute error ~1e-6, far below the bf16 rounding of the operands).
+template <typename T> __device__ __forceinline__ float sigm(float x);
+template <> __device__ __forceinline__ float sigm<float>(float x) { return 1.0f / (1.0f + expf(-x)); }
+template <> __device__ __forceinline__ float sigm<bf16>(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+template <typename T> __device__ __forceinline__ float tanh_(float x);
+template <> __device__ __forceinline__ float tanh_<float>(float x) { return tanhf(x); }
+template <> __device__ __forceinline__ float tanh_<bf16>(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+// four saved gate activations (si, tj, sf, so) in the compute dtype
+__device__ __forceinline__ float4 load_gates4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load_gates4(const bf16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store_gates4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store_gates4(bf16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
 
 // Block-wide reductions (blockDim.x multiple of 32, <= 1024).  `red` is a shared array of >= 32 elements.
 template <typename V, class Op>

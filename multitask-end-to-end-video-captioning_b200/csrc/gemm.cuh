@@ -274,7 +274,7 @@ struct EpiLstmFwd {
         const float* c_prev; float* c_out; // [M, Hp]
         T* h_out;                          // [M, Hp] compute dtype (next step's A operand / batched GEMM operand)
         float* h_outF;                     // optional fp32 copy
-        float* gates_out;                  // optional [M, 4Hp] saved activations (si, tj, sf, so) for BPTT
+        T* gates_out;                      // optional [M, 4Hp] saved activations (si, tj, sf, so) for BPTT, compute dtype
         T* hdrop_out;                      // optional dropout-applied output (DropoutWrapper, Q2)
         unsigned long long seed; uint32_t stream; uint32_t step; uint32_t row_base; float keep;
     };
@@ -298,14 +298,14 @@ struct EpiLstmFwd {
                 float4 a = *reinterpret_cast<const float4*>(p.add1 + (size_t)p.tok[gr] * G + gc);
                 v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
             }
-            float si = sigmoidf_(v.x), tj = tanhf(v.y), sf = sigmoidf_(v.z + 1.0f), so = sigmoidf_(v.w);
+            float si = sigm<T>(v.x), tj = tanh_<T>(v.y), sf = sigm<T>(v.z + 1.0f), so = sigm<T>(v.w);
             size_t o = (size_t)gr * p.Hp + u;
             float c = p.c_prev[o] * sf + si * tj;
-            float h = tanhf(c) * so;
+            float h = tanh_<T>(c) * so;
             p.c_out[o] = c;
             p.h_out[o] = from_f32<T>(h);
             if (p.h_outF) p.h_outF[o] = h;
-            if (p.gates_out) *reinterpret_cast<float4*>(p.gates_out + (size_t)gr * G + gc) = make_float4(si, tj, sf, so);
+            if (p.gates_out) store_gates4(p.gates_out + (size_t)gr * G + gc, make_float4(si, tj, sf, so));
             if (p.hdrop_out) {
                 float m = p.keep < 1.0f ? dropout_mult(p.seed, p.stream, p.row_base + gr, p.step, u, p.keep) : 1.0f;
                 p.hdrop_out[o] = from_f32<T>(h * m);
@@ -339,10 +339,10 @@ __device__ __forceinline__ void EpiLstmFwd<T>::direct(const Params& p, int gr, i
     float4 gt[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        float si = sigmoidf_(v[4 * j] + pre.add[j].x), tj = tanhf(v[4 * j + 1] + pre.add[j].y);
-        float sf = sigmoidf_(v[4 * j + 2] + pre.add[j].z + 1.0f), so = sigmoidf_(v[4 * j + 3] + pre.add[j].w);
+        float si = sigm<T>(v[4 * j] + pre.add[j].x), tj = tanh_<T>(v[4 * j + 1] + pre.add[j].y);
+        float sf = sigm<T>(v[4 * j + 2] + pre.add[j].z + 1.0f), so = sigm<T>(v[4 * j + 3] + pre.add[j].w);
         cn[j] = cp[j] * sf + si * tj;
-        hn[j] = tanhf(cn[j]) * so;
+        hn[j] = tanh_<T>(cn[j]) * so;
         gt[j] = make_float4(si, tj, sf, so);
     }
     const size_t o = (size_t)gr * p.Hp + u0;
@@ -350,9 +350,9 @@ __device__ __forceinline__ void EpiLstmFwd<T>::direct(const Params& p, int gr, i
     store8(p.h_out + o, hn);
     if (p.h_outF) store8(p.h_outF + o, hn);
     if (p.gates_out) {
-        float4* g = reinterpret_cast<float4*>(p.gates_out + (size_t)gr * G + gc);
+        T* g = p.gates_out + (size_t)gr * G + gc;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = gt[j];
+        for (int j = 0; j < 8; ++j) store_gates4(g + 4 * j, gt[j]);
     }
     if (p.hdrop_out) {
         if (p.keep < 1.0f) {
@@ -369,7 +369,7 @@ __device__ __forceinline__ void EpiLstmFwd<T>::direct(const Params& p, int gr, i
 struct LstmBwdArgs {
     int M; int Hp;
     const float* dh_ext;     // [M, Hp] nullable: gradient arriving from the layer above at this step
-    const float* gates;      // [M, 4Hp] (si, tj, sf, so)
+    const void* gates;       // [M, 4Hp] (si, tj, sf, so) in the compute dtype
     const float* c_prev;     // [M, Hp]
     const float* c_new;      // [M, Hp]
     float* dc;               // [M, Hp] in: dc from step t+1, out: dc for step t-1
@@ -384,9 +384,9 @@ __device__ __forceinline__ void lstm_bwd_unit(const LstmBwdArgs& p, T* dg_out, i
         float m = p.keep < 1.0f ? dropout_mult(p.seed, p.stream, p.row_base + gr, p.step, u, p.keep) : 1.0f;
         dh += p.dh_ext[o] * m;
     }
-    float4 g = *reinterpret_cast<const float4*>(p.gates + (size_t)gr * G + 4 * u);
+    float4 g = load_gates4(reinterpret_cast<const T*>(p.gates) + (size_t)gr * G + 4 * u);
     float si = g.x, tj = g.y, sf = g.z, so = g.w;
-    float tc = tanhf(p.c_new[o]);
+    float tc = tanh_<T>(p.c_new[o]);
     float d_o = dh * tc;
     float dc = p.dc[o] + dh * so * (1.0f - tc * tc);
     float di = dc * tj, dj = dc * si, df = dc * p.c_prev[o];
@@ -411,9 +411,9 @@ struct EpiLstmBwd {
         const LstmBwdArgs& a = p.a;
         if (gr >= a.M) return;
         const size_t o = (size_t)gr * a.Hp + u0;
-        const float4* g = reinterpret_cast<const float4*>(a.gates + (size_t)gr * 4 * a.Hp + 4 * u0);
+        const T* g = reinterpret_cast<const T*>(a.gates) + (size_t)gr * 4 * a.Hp + 4 * u0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pre.g[j] = g[j];
+        for (int j = 0; j < 8; ++j) pre.g[j] = load_gates4(g + 4 * j);
         const float4* cn = reinterpret_cast<const float4*>(a.c_new + o); pre.cn[0] = cn[0]; pre.cn[1] = cn[1];
         const float4* cp = reinterpret_cast<const float4*>(a.c_prev + o); pre.cp[0] = cp[0]; pre.cp[1] = cp[1];
         const float4* dc = reinterpret_cast<const float4*>(a.dc + o); pre.dc[0] = dc[0]; pre.dc[1] = dc[1];
@@ -439,7 +439,7 @@ struct EpiLstmBwd {
         for (int j = 0; j < 8; ++j) {
             float si = pre.g[j].x, tj = pre.g[j].y, sf = pre.g[j].z, so = pre.g[j].w;
             float dh = v[j] + dhx[j];
-            float tc = tanhf(cn[j]);
+            float tc = tanh_<T>(cn[j]);
             float d_o = dh * tc;
             float dc = dcn[j] + dh * so * (1.0f - tc * tc);
             dcp[j] = dc * sf;

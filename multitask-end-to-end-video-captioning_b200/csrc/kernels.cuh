@@ -122,11 +122,30 @@ __global__ void __launch_bounds__(ROW_THREADS) sample_rows_kernel(const float* _
     const float4* lr = reinterpret_cast<const float4*>(logits + (size_t)row * ld);
     bool sample = row < n_sample;
     uint32_t grow = row_base + (uint32_t)row;
+    // Sampling rows: with the 23-bit uniforms of u32_to_uniform the Gumbel noise lies in [-2.8, 16.7], so a word more than
+    // 19.5 below the row maximum can never win the arg-max.  Such words are skipped (exactly, not approximately: the result
+    // equals the full arg-max over the same Philox stream); one cheap max pass finds the cut.
+    __shared__ float redf[32];
+    float cut = -INFINITY;
+    if (sample) {
+        float mx = -INFINITY;
+        for (int v4 = threadIdx.x; v4 * 4 < V; v4 += ROW_THREADS) {
+            float4 x = lr[v4];
+            int v = v4 * 4;
+            if (v + 0 < V) mx = fmaxf(mx, x.x);
+            if (v + 1 < V) mx = fmaxf(mx, x.y);
+            if (v + 2 < V) mx = fmaxf(mx, x.z);
+            if (v + 3 < V) mx = fmaxf(mx, x.w);
+        }
+        mx = block_reduce(mx, [](float a, float b) { return fmaxf(a, b); }, redf);
+        cut = mx - 22.0f;
+    }
     ArgVal best; best.v = -INFINITY; best.i = 0x7fffffff;
     for (int v4 = threadIdx.x; v4 * 4 < V; v4 += ROW_THREADS) {
         float4 x = lr[v4];
         float e[4] = {x.x, x.y, x.z, x.w};
         if (sample) {
+            if (fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)) < cut) continue;
             uint4 o = philox4x32_10((uint32_t)v4, step, grow, S2VT_STREAM_SAMPLE, (uint32_t)seed, (uint32_t)(seed >> 32));
             uint32_t rr[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll

@@ -255,7 +255,7 @@ template <typename T> struct EpiBytes<EpiLstmFwd<T>> {
         double b = M * H * 4 * 2 + M * H * sizeof(T);                       // c in, c out, h out
         if (p.add0) b += M * G * 4;
         if (p.add1) b += M * G * 4;
-        if (p.gates_out) b += M * G * 4;
+        if (p.gates_out) b += M * G * sizeof(T);
         if (p.hdrop_out) b += M * H * sizeof(T);
         return b;
     }
@@ -263,7 +263,7 @@ template <typename T> struct EpiBytes<EpiLstmFwd<T>> {
 template <typename T> struct EpiBytes<EpiLstmBwd<T>> {
     static double get(const s2vt_handle* h, const typename EpiLstmBwd<T>::Params& p, int M) {
         const double H = h->H, G = 4.0 * h->H;
-        return M * G * 4 + M * H * 4 * 4 + (p.a.dh_ext ? M * H * 4 : 0) + M * G * sizeof(T);   // gates, c_new/c_prev/dc in/out, dh_ext, dG out
+        return M * G * sizeof(T) + M * H * 4 * 4 + (p.a.dh_ext ? M * H * 4 : 0) + M * G * sizeof(T);   // gates, c_new/c_prev/dc in/out, dh_ext, dG out
     }
 };
 static int chain_begin(s2vt_handle* h, cudaStream_t st) {
@@ -457,7 +457,7 @@ extern "C" int s2vt_refresh(s2vt_handle* h, s2vt_stream st) {
 // =================================================================================================================
 template <typename T>
 struct Front {   // per-video part: frame projection + LSTM1 over all T steps
-    T* Xc; T* img; float* G1x; T* h1_all; float* c1_all; float* gates1;
+    T* Xc; T* img; float* G1x; T* h1_all; float* c1_all; T* gates1;
 };
 template <typename T>
 static void plan_front(const s2vt_handle* h, Arena& a, int B, bool train, Front<T>& f) {
@@ -466,7 +466,7 @@ static void plan_front(const s2vt_handle* h, Arena& a, int B, bool train, Front<
     f.G1x = a.take<float>((size_t)h->Tv * B * h->Gp);
     f.h1_all = a.take<T>((size_t)(h->T + 1) * B * h->Hp);
     f.c1_all = a.take<float>((size_t)(h->T + 1) * B * h->Hp);
-    f.gates1 = train ? a.take<float>((size_t)h->T * B * h->Gp) : nullptr;
+    f.gates1 = train ? a.take<T>((size_t)h->T * B * h->Gp) : nullptr;
 }
 
 template <typename T>
@@ -607,7 +607,7 @@ extern "C" int s2vt_caption_masks(s2vt_handle* h, const int32_t* ids, int N, flo
 template <typename T>
 struct Train {
     Front<T> f;
-    T* out1d; float* G2x; T* h2_all; float* c2_all; float* gates2; T* out2d; float* logits;
+    T* out1d; float* G2x; T* h2_all; float* c2_all; T* gates2; T* out2d; float* logits;
     int *prev_tok, *target; float *ca, *cb, *cc, *logp, *sumlsm;
     // backward
     T* dlogits; float* dout2; T* dG2; float* dc2; float* dout1; float* dEmb; float* dh1; T* dG1; float* dc1; float* dimgF; T* dimgT_src;
@@ -624,7 +624,7 @@ static void plan_train(const s2vt_handle* h, Arena& a, int B, int N, bool backwa
     p.G2x = a.take<float>((size_t)T_ * N * Gp);
     p.h2_all = a.take<T>((size_t)(T_ + 1) * N * Hp);
     p.c2_all = a.take<float>((size_t)(T_ + 1) * N * Hp);
-    p.gates2 = backward ? a.take<float>((size_t)T_ * N * Gp) : nullptr;
+    p.gates2 = backward ? a.take<T>((size_t)T_ * N * Gp) : nullptr;
     p.out2d = a.take<T>((size_t)Tc * N * Hp);
     p.logits = a.take<float>((size_t)Tc * N * Vp);
     p.prev_tok = a.take<int>((size_t)Tc * N); p.target = a.take<int>((size_t)Tc * N);
