@@ -77,6 +77,14 @@ __device__ __forceinline__ void store_gates4(bf16* p, float4 v) {
     *reinterpret_cast<uint2*>(p) = u;
 }
 
+// Gumbel(0,1) noise -log(-log(u)) on the MUFU log path.  E = -log(u) is the delicate part for u -> 1 (the large noise
+// values that win the arg-max): there 1-u is exact in fp32 and a 3-term series of -log1p(-t) is used (rel. err < 1e-5).
+__device__ __forceinline__ float gumbel_fast(float u) {
+    float t = 1.0f - u;
+    float E = t < 0.03125f ? t * (1.0f + t * (0.5f + t * 0.33333334f)) : -__logf(u);
+    return -__logf(E);
+}
+
 // Block-wide reductions (blockDim.x multiple of 32, <= 1024).  `red` is a shared array of >= 32 elements.
 template <typename V, class Op>
 __device__ __forceinline__ V block_reduce(V v, Op op, V* red) {

@@ -223,6 +223,73 @@ struct EpiStore {
     }
 };
 
+// Vocabulary projection fused with the decoder's word choice (rollouts): the logits never reach HBM.  Each CTA reduces its
+// tile of (logit + bias [+ Gumbel noise for sampling rows]) to one (value, index) candidate per row; the next step's cell
+// kernel takes the arg-max over the tiles' candidates (EpiLstmFwd::prefetch).  Noise and tie-breaking are those of
+// sample_rows_kernel (same Philox stream, lowest index wins), so the chosen words are identical.
+template <typename T>
+struct EpiLogitsPick {
+    static constexpr bool kDirect = false;
+    struct Params {
+        int M, V; const float* bias; int n_sample; unsigned long long seed; uint32_t step, row_base;
+        float* pick_val; int* pick_idx; int pick_ld;     // [M, pick_ld] candidates, column = tile index
+    };
+    static constexpr int kEpiWarps = 16;   // tcgen05 kernel: 16 epilogue warps (the Philox / log work needs the lanes)
+    template <class Cfg>
+    __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
+        constexpr int PARTS = 4, PW = Cfg::BN / PARTS;          // each row's tile columns are scanned by 4 threads
+        __shared__ float part_v[PARTS][Cfg::BM];
+        __shared__ int part_i[PARTS][Cfg::BM];
+        const int tile = n0 / Cfg::BN;
+        for (int u = threadIdx.x; u < Cfg::BM * PARTS; u += Cfg::NTHREADS) {
+            const int r = u % Cfg::BM, part = u / Cfg::BM, gr = m0 + r;   // consecutive threads -> consecutive rows (conflict-free float4 reads)
+            ArgVal best; best.v = -INFINITY; best.i = 0x7fffffff;
+            if (gr < p.M) {
+                const bool sample = gr < p.n_sample;
+                const float* row = Cs + r * Cfg::LDC;
+                const int cb = part * PW;
+                float cut = -INFINITY;
+                if (sample) {   // words > 19.5 below the local maximum cannot win (bounded noise, see sample_rows_kernel)
+                    float mx = -INFINITY;
+                    for (int c = cb; c < cb + PW; c += 4) {
+                        float4 x = *reinterpret_cast<const float4*>(row + c), b = *reinterpret_cast<const float4*>(p.bias + n0 + c);
+                        if (n0 + c + 0 < p.V) mx = fmaxf(mx, x.x + b.x);
+                        if (n0 + c + 1 < p.V) mx = fmaxf(mx, x.y + b.y);
+                        if (n0 + c + 2 < p.V) mx = fmaxf(mx, x.z + b.z);
+                        if (n0 + c + 3 < p.V) mx = fmaxf(mx, x.w + b.w);
+                    }
+                    cut = mx - 22.0f;
+                }
+                for (int c = cb; c < cb + PW; c += 4) {
+                    float4 x = *reinterpret_cast<const float4*>(row + c), b = *reinterpret_cast<const float4*>(p.bias + n0 + c);
+                    float e[4] = {x.x + b.x, x.y + b.y, x.z + b.z, x.w + b.w};
+                    if (sample) {
+                        if (fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])) < cut) continue;
+                        uint4 o = philox4x32_10((uint32_t)((n0 + c) >> 2), p.step, p.row_base + (uint32_t)gr, S2VT_STREAM_SAMPLE, (uint32_t)p.seed,
+                                                (uint32_t)(p.seed >> 32));
+                        e[0] += gumbel_fast(u32_to_uniform(o.x)); e[1] += gumbel_fast(u32_to_uniform(o.y));
+                        e[2] += gumbel_fast(u32_to_uniform(o.z)); e[3] += gumbel_fast(u32_to_uniform(o.w));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (n0 + c + k < p.V) { ArgVal cand; cand.v = e[k]; cand.i = n0 + c + k; best = argmax_op(best, cand); }
+                }
+            }
+            part_v[part][r] = best.v; part_i[part][r] = best.i;
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < Cfg::BM; r += Cfg::NTHREADS) {
+            const int gr = m0 + r;
+            if (gr >= p.M) continue;
+            ArgVal best; best.v = part_v[0][r]; best.i = part_i[0][r];
+#pragma unroll
+            for (int q = 1; q < PARTS; ++q) { ArgVal c; c.v = part_v[q][r]; c.i = part_i[q][r]; best = argmax_op(best, c); }
+            p.pick_val[(size_t)gr * p.pick_ld + tile] = best.v;
+            p.pick_idx[(size_t)gr * p.pick_ld + tile] = best.i;
+        }
+    }
+};
+
 // Weight-gradient store into the fp32 TF-layout gradient block:  grad[(row0 + r) * ldg + colmap(c)] += scale * acc.
 // gate_h > 0 : columns are in packed gate order (c = 4u+g) and map to the TF order g*gate_h + u (u < gate_h).
 // gate_h == 0: identity columns, valid while c < ncols.   Rows valid while r < nrows.
@@ -271,6 +338,8 @@ struct EpiLstmFwd {
         const float* bias;                 // [4Hp] packed
         const float* add0; int add0_mod;   // [*, 4Hp] input-side pre-activations; row = add0_mod > 0 ? row % add0_mod : row
         const float* add1; const int* tok; // embedding table [V, 4Hp] gathered by tok[row] (nullable)
+        const float* pick_val; const int* pick_idx; int pick_ld, pick_nt;   // alternative to tok: per-tile candidates of EpiLogitsPick
+        int* tok_out; int* ids_out; int ids_ld, ids_col;                    // ...resolved here; CTA column 0 records the word
         const float* c_prev; float* c_out; // [M, Hp]
         T* h_out;                          // [M, Hp] compute dtype (next step's A operand / batched GEMM operand)
         float* h_outF;                     // optional fp32 copy
@@ -295,7 +364,7 @@ struct EpiLstmFwd {
                 v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
             }
             if (p.add1) {
-                float4 a = *reinterpret_cast<const float4*>(p.add1 + (size_t)p.tok[gr] * G + gc);
+                float4 a = *reinterpret_cast<const float4*>(p.add1 + (size_t)resolve_token(p, gr, gc) * G + gc);
                 v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
             }
             float si = sigm<T>(v.x), tj = tanh_<T>(v.y), sf = sigm<T>(v.z + 1.0f), so = sigm<T>(v.w);
@@ -314,13 +383,23 @@ struct EpiLstmFwd {
     }
 };
 
+template <class P>
+__device__ __forceinline__ int resolve_token(const P& p, int gr, int gc) {
+    if (!p.pick_val) return p.tok[gr];
+    const float* pv = p.pick_val + (size_t)gr * p.pick_ld;
+    float bv = pv[0]; int bt = 0;
+    for (int t = 1; t < p.pick_nt; ++t) { float v = pv[t]; if (v > bv) { bv = v; bt = t; } }   // first maximum = lowest word index
+    const int w = p.pick_idx[(size_t)gr * p.pick_ld + bt];
+    if (gc == 0) { if (p.tok_out) p.tok_out[gr] = w; if (p.ids_out) p.ids_out[(size_t)gr * p.ids_ld + p.ids_col] = w; }
+    return w;
+}
 template <typename T>
 __device__ __forceinline__ void EpiLstmFwd<T>::prefetch(const Params& p, int gr, int gc, Pre& pre) {
     if (gr >= p.M) return;
     const size_t G = 4 * (size_t)p.Hp;
     const float4* b = reinterpret_cast<const float4*>(p.bias + gc);
     const float4* a0 = p.add0 ? reinterpret_cast<const float4*>(p.add0 + (size_t)(p.add0_mod > 0 ? gr % p.add0_mod : gr) * G + gc) : nullptr;
-    const float4* a1 = p.add1 ? reinterpret_cast<const float4*>(p.add1 + (size_t)p.tok[gr] * G + gc) : nullptr;
+    const float4* a1 = p.add1 ? reinterpret_cast<const float4*>(p.add1 + (size_t)resolve_token(p, gr, gc) * G + gc) : nullptr;
     const float4* c = reinterpret_cast<const float4*>(p.c_prev + (size_t)gr * p.Hp + (gc >> 2));
     float4 x0[8], x1[8];
 #pragma unroll

@@ -146,8 +146,10 @@ __device__ __forceinline__ void direct_chunk(const typename Epi::Params& ep, int
 
 // Epilogue warps: the staged epilogues use 4 (one per TMEM lane quarter); the direct (register) epilogues use one warp per
 // (lane quarter, 32-column chunk) so every thread handles exactly one chunk whose operands were prefetched.
+template <class Epi, class = void> struct StagedWarps { static constexpr int value = 4; };
+template <class Epi> struct StagedWarps<Epi, decltype((void)Epi::kEpiWarps)> { static constexpr int value = Epi::kEpiWarps; };   // compute-heavy staged epilogues
 template <int BN, class Epi> struct Threads {
-    static constexpr int NEPI = Epi::kDirect ? 4 * (BN / 32) : 4;
+    static constexpr int NEPI = Epi::kDirect ? 4 * (BN / 32) : StagedWarps<Epi>::value;
     static constexpr int N = 64 + 32 * NEPI;
 };
 
@@ -345,8 +347,10 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
         } else {
             mbar_wait(tmem_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            constexpr int CPW = BN / (Threads<BN, Epi>::NEPI / 4);   // accumulator columns copied by each warp of a lane quarter
+            const int cbeg = (e >> 2) * CPW;
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = cbeg; c0 < cbeg + CPW; c0 += 32) {
                 float v[32];
                 tmem_ld32(trow + (uint32_t)c0, v);
 #pragma unroll

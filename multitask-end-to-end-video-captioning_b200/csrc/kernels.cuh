@@ -100,14 +100,6 @@ __global__ void reduce_dropout_kernel(const float* __restrict__ dout1, int B, in
     }
 }
 
-// Gumbel(0,1) noise -log(-log(u)) on the MUFU log path.  E = -log(u) is the delicate part for u -> 1 (the large noise
-// values that win the arg-max): there 1-u is exact in fp32 and a 3-term series of -log1p(-t) is used (rel. err < 1e-5).
-__device__ __forceinline__ float gumbel_fast(float u) {
-    float t = 1.0f - u;
-    float E = t < 0.03125f ? t * (1.0f + t * (0.5f + t * 0.33333334f)) : -__logf(u);
-    return -__logf(E);
-}
-
 // ---- vocabulary row kernels (one CTA per row, 128-bit loads, row kept in registers) -------------------------------
 #define ROW_THREADS 256
 #define ROW_MAXV4 12  // supports V <= 256*12*4 = 12288
@@ -259,6 +251,17 @@ __global__ void __launch_bounds__(ROW_THREADS) topk_rows_kernel(const float* __r
         taken[j] = best.i;
         if (threadIdx.x == 0) { idx_out[row * k + j] = best.i; logp_out[row * k + j] = best.v - lse; }
     }
+}
+
+// Last decode step of a rollout with fused word choice: arg-max over the per-tile candidates -> ids[:, col].
+__global__ void resolve_picks_kernel(const float* __restrict__ pick_val, const int* __restrict__ pick_idx, int ld, int nt, int R, int* __restrict__ ids,
+                                     int ids_ld, int col) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* pv = pick_val + (size_t)r * ld;
+    float bv = pv[0]; int bt = 0;
+    for (int t = 1; t < nt; ++t) { float v = pv[t]; if (v > bv) { bv = v; bt = t; } }
+    ids[(size_t)r * ids_ld + col] = pick_idx[(size_t)r * ld + bt];
 }
 
 // ---- small utilities --------------------------------------------------------------------------------------------

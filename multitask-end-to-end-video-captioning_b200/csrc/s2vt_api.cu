@@ -503,6 +503,7 @@ static int run_front(s2vt_handle* h, cudaStream_t st, const float* video, int B,
 template <typename T>
 struct Roll {
     Front<T> f; float* G2x; T* h2e[2]; float* c2e[2]; T* h2r[2]; float* c2r[2]; float* logits; int* tok[2]; int* ids;
+    float* pick_val; int* pick_idx; int pick_ld;
 };
 template <typename T>
 static void plan_roll(const s2vt_handle* h, Arena& a, int B, int R, Roll<T>& r) {
@@ -513,6 +514,8 @@ static void plan_roll(const s2vt_handle* h, Arena& a, int B, int R, Roll<T>& r) 
     r.logits = a.take<float>((size_t)R * h->Vp);
     r.tok[0] = a.take<int>(R); r.tok[1] = a.take<int>(R);
     r.ids = a.take<int>((size_t)R * h->Tc);
+    r.pick_ld = h->Vp / 128;
+    r.pick_val = a.take<float>((size_t)R * r.pick_ld); r.pick_idx = a.take<int>((size_t)R * r.pick_ld);
 }
 
 // frames -> (LSTM1 all steps, G2x all steps, LSTM2 encoder steps).  Leaves the encoder state in h2e[Tv&1], c2e[Tv&1].
@@ -556,19 +559,24 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
     tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2e[Tv & 1], B, R, Hp, r.h2r[0]); KCHECK(h);
     tile_rows_kernel<float><<<R, 256, 0, st>>>(r.c2e[Tv & 1], B, R, Hp, r.c2r[0]); KCHECK(h);
     fill_int_kernel<<<(R + 255) / 256, 256, 0, st>>>(r.tok[0], R, 1); KCHECK(h);   // <bos> = 1 (:321-323)
+    // tile width the vocabulary-projection GEMM will use (decides how many candidates per row the fused pick produces)
+    const bool tc_path = std::is_same<T, bf16>::value && h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC;
+    const int logits_bn = tc_path && h->cfg.gemm_backend != 3 && h->cfg.gemm_backend != 4 && Vp % 256 == 0 ? 256 : 128;
+    const int nt = Vp / logits_bn;
     for (int i = 0; i < Tc; ++i) {
         const int t = Tv + i;
         typename EpiLstmFwd<T>::Params ep;
         memset(&ep, 0, sizeof ep);
         ep.M = R; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp; ep.add0_mod = B;
-        ep.add1 = h->Etab; ep.tok = r.tok[i & 1];
+        ep.add1 = h->Etab; ep.tok = r.tok[0];                     // step 0: <bos>; later steps resolve the previous step's candidates
+        if (i > 0) { ep.pick_val = r.pick_val; ep.pick_idx = r.pick_idx; ep.pick_ld = r.pick_ld; ep.pick_nt = nt; ep.ids_out = r.ids; ep.ids_ld = Tc; ep.ids_col = i - 1; }
         ep.c_prev = r.c2r[i & 1]; ep.c_out = r.c2r[(i + 1) & 1]; ep.h_out = r.h2r[(i + 1) & 1]; ep.keep = 1.f;
         TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, r.h2r[i & 1], Hp, h->W2hT, Hp, R, Gp, Hp, ep)));
-        typename EpiStore<T>::Params el = {r.logits, nullptr, Vp, h->bo_p, R, 0};   // :332 logit_words
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, r.h2r[(i + 1) & 1], Hp, h->WoT, Hp, R, Vp, Hp, el)));
-        sample_rows_kernel<<<R, ROW_THREADS, 0, st>>>(r.logits, Vp, h->V, K * B, seed, (uint32_t)i, row_base, r.tok[(i + 1) & 1], r.ids, Tc);
-        KCHECK(h);
+        // :332-336 logit_words -> log_softmax -> tf.multinomial / :386-387 argmax, fused: the logits stay on chip
+        typename EpiLogitsPick<T>::Params el = {R, h->V, h->bo_p, K * B, seed, (uint32_t)i, row_base, r.pick_val, r.pick_idx, r.pick_ld};
+        TRY((gemm<T, CfgBig, EpiLogitsPick<T>>(h, st, r.h2r[(i + 1) & 1], Hp, h->WoT, Hp, R, Vp, Hp, el)));
     }
+    resolve_picks_kernel<<<(R + 127) / 128, 128, 0, st>>>(r.pick_val, r.pick_idx, r.pick_ld, nt, R, r.ids, Tc, Tc - 1); KCHECK(h);
     if (K > 0 && sampled_out)
         CUDA_TRY(h, cudaMemcpyAsync(sampled_out, r.ids, (size_t)K * B * Tc * sizeof(int), cudaMemcpyDeviceToDevice, st));
     if (want_greedy)
