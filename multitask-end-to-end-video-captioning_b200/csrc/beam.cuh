@@ -150,7 +150,7 @@ static int beam_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B,
     TRY(run_encoder<T>(h, st, video, B, r));
     beam_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(s); KCHECK(h);
     // every beam starts from the encoder state; step 0 only uses beam 0 (nlive = 1)
-    tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2e[Tv & 1], B, R, Hp, r.h2r[0]); KCHECK(h);
+    tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2_final, B, R, Hp, r.h2r[0]); KCHECK(h);
     tile_rows_kernel<float><<<R, 256, 0, st>>>(r.c2e[Tv & 1], B, R, Hp, r.c2r[0]); KCHECK(h);
     int cur = 0;   // sentence ping-pong index
     for (int i = 0; i < Tc; ++i) {
@@ -217,7 +217,7 @@ static int beam_init_impl(s2vt_handle* h, cudaStream_t st, const float* video, f
     TRY(run_encoder<T>(h, st, video, 1, r));
     to_f32_kernel<T><<<(Hp + 255) / 256, 256, 0, st>>>(r.f.h1_all + (size_t)Tv * Hp, Hp, hF); KCHECK(h);
     state_pack_kernel<<<1, 256, 0, st>>>(r.f.c1_all + (size_t)Tv * Hp, hF, H, state1_out); KCHECK(h);
-    to_f32_kernel<T><<<(Hp + 255) / 256, 256, 0, st>>>(r.h2e[Tv & 1], Hp, hF); KCHECK(h);
+    to_f32_kernel<T><<<(Hp + 255) / 256, 256, 0, st>>>(r.h2_final, Hp, hF); KCHECK(h);
     state_pack_kernel<<<1, 256, 0, st>>>(r.c2e[Tv & 1], hF, H, state2_out); KCHECK(h);
     return 0;
 }

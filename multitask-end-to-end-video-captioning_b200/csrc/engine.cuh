@@ -46,6 +46,7 @@ struct s2vt_handle {
     float *params, *grads, *adam_m, *adam_v;
     double* sq;                           // [0] dense grad sumsq, [1] dense Wemb sumsq, [2] Wemb slice sumsq, [3] scratch
     float* scal;                          // small fp32 scratch (loss parts, norm)
+    unsigned* gbar;                       // grid-barrier counters of the persistent step chains ([0] caller's stream, [16] side stream)
     void *WeT, *W1xT, *W1hT, *W1h, *W1x, *W2xT, *W2x, *W2eT, *W2e, *W2hT, *W2h, *WoT, *Wo, *WembC, *attrWT;
     float *be_p, *b1_p, *b2_p, *bo_p, *Etab;
     bool bound, fresh;

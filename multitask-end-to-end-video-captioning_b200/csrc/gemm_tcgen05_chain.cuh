@@ -1,0 +1,235 @@
+// Persistent recurrent-step kernel: ONE launch walks a whole chain of dependent time steps
+//     for s in 0 .. nsteps-1 :   C_s = A_s . B^T  ->  fused LSTM-cell epilogue (forward or backward)
+// where A_s (the previous step's hidden state / gate gradients) lives at row  a_row0 + s * a_row_stride  of one buffer
+// and B (the recurrent weights) is the same for every step.  The CTAs are the tiles of gemm_tc_kernel (same TMA /
+// tcgen05 / TMEM pipeline, same register epilogues, optional split-K cluster of 4) and stay resident; consecutive steps
+// are separated by a grid-wide barrier (atomic counter in global memory) instead of a kernel boundary.  Barriers,
+// TMEM allocation and tensor-map fetches are paid once per chain; the weight tiles of the next step are requested
+// before the barrier (they never depend on it).
+//
+// Memory ordering across the barrier: epilogue stores (generic proxy) -> __syncthreads -> thread 0: __threadfence +
+// atomicAdd ... other CTAs: acquire spin -> fence.proxy.async -> TMA loads (async proxy) of the rows just written.
+// Requires every CTA of the grid to be co-resident (checked by the host with the occupancy API).
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace tc {
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int BN, class Epi, int KS>
+__global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                                            int K, int a_rows, int a_row0, int a_row_stride,
+                                                                            const typename Epi::Params* __restrict__ steps, int nsteps,
+                                                                            unsigned* __restrict__ gbar) {
+    using C = Cfg<BN, Threads<BN, Epi>::N>;
+    static_assert(Epi::kDirect, "chain kernel: register epilogues only");
+    static_assert(KS == 1 || KS == 4, "split-K cluster of 4 or none");
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::PIPE_BYTES);
+    uint64_t* empty = full + C::STAGES;
+    uint64_t* tmem_full = empty + C::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* recv = reinterpret_cast<float*>(smem + C::PIPE_BYTES + C::BAR_BYTES);   // [KS][32][BN] (KS > 1)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * C::BM, n0 = blockIdx.x * BN;
+    const int rank = KS > 1 ? (int)blockIdx.z : 0;
+    const int KBL = K / C::BK / KS, kb0 = rank * KBL;
+    const unsigned ncta = gridDim.x * gridDim.y * gridDim.z;
+    const uint32_t stage_tx = (uint32_t)(a_rows * 128 + C::B_BYTES);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if constexpr (KS > 1) cluster_sync_all();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    const int pre = KBL < C::STAGES ? KBL : C::STAGES;
+    for (int s = 0; s < nsteps; ++s) {
+        const int g0 = s * KBL;   // running K-block counter at the start of this step (pipeline phases continue across steps)
+        // ---- weight tiles of the first stages: independent of the previous step, requested before the barrier
+        if (warp == 0 && lane == 0) {
+            for (int i = 0; i < pre; ++i) {
+                const int g = g0 + i, st = g % C::STAGES;
+                if (g >= C::STAGES) mbar_wait(empty + st, ((g / C::STAGES) - 1) & 1);
+                mbar_expect_tx(full + st, stage_tx);
+                tma_load_2d_raw(smem + st * C::STAGE_BYTES + C::A_BYTES, &mapB, full + st, (kb0 + i) * C::BK, n0);
+            }
+        }
+        // ---- dependency on the previous step (s == 0: on the previous kernel)
+        if (s == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+        } else {
+            __syncthreads();                       // this CTA's stores of step s-1 are issued
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(gbar, 1u);
+                const unsigned target = (unsigned)s * ncta;
+                long long t0 = clock64();
+                while (ld_acquire_gpu(gbar) < target) {
+                    if (clock64() - t0 > 4000000000LL) { printf("s2vt: grid barrier timed out (step %d, block %d,%d,%d)\n", s, blockIdx.x, blockIdx.y, blockIdx.z); __trap(); }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        const typename Epi::Params& ep = steps[s];
+        const int arow = a_row0 + s * a_row_stride + m0;
+
+        if (warp == 0) {
+            if (lane == 0) {
+                asm volatile("fence.proxy.async;" ::: "memory");   // rows written through the generic proxy by other SMs are read by TMA
+                for (int i = 0; i < KBL; ++i) {
+                    const int g = g0 + i, st = g % C::STAGES;
+                    unsigned char* a = smem + st * C::STAGE_BYTES;
+                    if (i >= pre) {
+                        mbar_wait(empty + st, ((g / C::STAGES) - 1) & 1);
+                        mbar_expect_tx(full + st, stage_tx);
+                        tma_load_2d_raw(a + C::A_BYTES, &mapB, full + st, (kb0 + i) * C::BK, n0);
+                    }
+                    tma_load_2d_raw(a, &mapA, full + st, (kb0 + i) * C::BK, arow);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0) {
+                for (int i = 0; i < KBL; ++i) {
+                    const int g = g0 + i, st = g % C::STAGES;
+                    mbar_wait(full + st, (g / C::STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a = smem_u32(smem + st * C::STAGE_BYTES);
+                    const uint64_t adesc = make_desc(a), bdesc = make_desc(a + C::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < C::BK / 16; ++k) mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (i | k) != 0);
+                    mma_commit(empty + st);
+                }
+                mma_commit(tmem_full);
+            }
+            __syncwarp();
+        } else {
+            const int e = warp - 2, q = warp & 3;
+            const int row = q * 32 + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            if constexpr (KS == 1) {
+                const int c0 = (e >> 2) * 32;
+                typename Epi::Pre prf;
+                Epi::prefetch(ep, m0 + row, n0 + c0, prf);
+                mbar_wait(tmem_full, s & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+                direct_chunk<Epi>(ep, m0 + row, n0 + c0, v, prf, false);
+            } else {
+                constexpr int UPR = BN / 8;
+                const int t = threadIdx.x - 64;
+                const int frow = t / UPR, fc8 = t % UPR;
+                typename Epi::Pre prf;
+                Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, prf);
+                mbar_wait(tmem_full, s & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                {
+                    const int c0 = (e >> 2) * 32;
+                    float v[32];
+                    tmem_ld32(trow + (uint32_t)c0, v);
+                    const uint32_t base = cluster_map(smem_u32(recv), (uint32_t)q) + (uint32_t)(((rank * 32 + lane) * BN) * 4);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int pos = ((c0 >> 2) + j) ^ (lane & 7);
+                        st_cluster_f4(base + pos * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+                cluster_sync_all();
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int src = 0; src < KS; ++src) {
+                    const float* rp = recv + (src * 32 + frow) * BN;
+                    const float4 x0 = *reinterpret_cast<const float4*>(rp + (((2 * fc8) ^ (frow & 7)) << 2));
+                    const float4 x1 = *reinterpret_cast<const float4*>(rp + (((2 * fc8 + 1) ^ (frow & 7)) << 2));
+                    acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w; acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+                }
+                Epi::direct(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, acc, prf);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+        if constexpr (KS > 1) {
+            if (warp < 2) cluster_sync_all();      // pairs with the exchange barrier of the epilogue warps
+            cluster_sync_all();                    // recv buffers may be overwritten by the next step only after everybody has read them
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    }
+}
+
+// Host launcher.  A: one buffer of `a_total_rows` rows (row stride lda); step s reads rows [a_row0 + s * a_row_stride, + M).
+// Returns cudaErrorLaunchOutOfResources (without launching) if the grid cannot be co-resident.
+template <int BN, class Epi, int KS>
+inline cudaError_t launch_chain(MapCache& cache, cudaStream_t st, const bf16* A, int lda, int a_total_rows, int a_row0, int a_row_stride, const bf16* B,
+                                int ldb, int M, int N, int K, const typename Epi::Params* steps_dev, int nsteps, unsigned* gbar, bool pdl) {
+    constexpr int NT = Threads<BN, Epi>::N;
+    using C = Cfg<BN, NT>;
+    constexpr int SMEM = C::SMEM_BYTES + (KS > 1 ? KS * 32 * BN * 4 : 0);
+    if (cache.size() > 32768) cache.clear();
+    const int a_rows = M <= 64 ? ((M + 7) & ~7) : BM;
+    const CUtensorMap* ma = get_map(cache, A, a_total_rows, K, lda, a_rows);
+    const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN);
+    if (!ma || !mb) return cudaErrorInvalidValue;
+    auto kern = gemm_tc_chain_kernel<BN, Epi, KS>;
+    static int max_ctas = -1;
+    if (max_ctas < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, SMEM);
+        if (e != cudaSuccess) return e;
+        max_ctas = per_sm * sms;
+    }
+    dim3 grid(N / BN, (M + BM - 1) / BM, KS);
+    if ((int)(grid.x * grid.y * grid.z) > max_ctas) return cudaErrorLaunchOutOfResources;
+    cudaError_t e = cudaMemsetAsync(gbar, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (KS > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = KS;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, a_rows, a_row0, a_row_stride, steps_dev, nsteps, gbar);
+}
+
+}  // namespace tc

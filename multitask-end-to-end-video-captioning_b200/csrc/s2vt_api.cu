@@ -13,6 +13,7 @@
 
 #include "gemm.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_chain.cuh"
 #include "kernels.cuh"
 
 template <typename T>
@@ -88,7 +89,7 @@ template <typename F> static void layout_state(s2vt_handle* h, Arena& a, F assig
     float* m = a.take<float>(h->P);
     float* v = a.take<float>(h->P);
     double* sq = a.take<double>(8);
-    float* scal = a.take<float>(64);
+    float* scal = a.take<float>(64 + 64);   // [64..127]: unsigned grid-barrier counters
     size_t copies_begin = a.used;
     char* WeT = a.take<char>((size_t)Ep * Dp * e);
     char* W1xT = a.take<char>((size_t)Gp * Ep * e);
@@ -196,7 +197,7 @@ extern "C" int s2vt_bind(s2vt_handle* h, void* state, size_t state_bytes, void* 
     layout_state(h, a, [&](float* params, float* grads, float* m, float* v, double* sq, float* scal, char* WeT, char* W1xT, char* W1hT, char* W1h, char* W1x,
                            char* W2xT, char* W2x, char* W2eT, char* W2e, char* W2hT, char* W2h, char* WoT, char* Wo, char* WembC, char* attrWT, float* be_p,
                            float* b1_p, float* b2_p, float* bo_p, float* Etab, size_t, size_t) {
-        h->params = params; h->grads = grads; h->adam_m = m; h->adam_v = v; h->sq = sq; h->scal = scal;
+        h->params = params; h->grads = grads; h->adam_m = m; h->adam_v = v; h->sq = sq; h->scal = scal; h->gbar = reinterpret_cast<unsigned*>(scal + 64);
         h->WeT = WeT; h->W1xT = W1xT; h->W1hT = W1hT; h->W1h = W1h; h->W1x = W1x; h->W2xT = W2xT; h->W2x = W2x; h->W2eT = W2eT; h->W2e = W2e;
         h->W2hT = W2hT; h->W2h = W2h; h->WoT = WoT; h->Wo = Wo; h->WembC = WembC; h->attrWT = attrWT;
         h->be_p = be_p; h->b1_p = b1_p; h->b2_p = b2_p; h->bo_p = bo_p; h->Etab = Etab;
@@ -382,6 +383,65 @@ static int bias_grad(s2vt_handle* h, cudaStream_t st, const T* Y, int ldy, int C
     return 0;
 }
 
+// A chain of dependent per-step GEMMs (one LSTM layer walked over time).  bf16 / tcgen05: ONE persistent launch with grid
+// barriers between the steps (gemm_tcgen05_chain.cuh); otherwise (fp32, mma.sync checker, grid too large to be co-resident,
+// gemm_backend 9) one launch per step.
+template <typename T, class Epi>
+struct StepChain {
+    std::vector<typename Epi::Params> eps;
+    const T* A; int lda, a_total_rows, a_row0, a_row_stride;   // step s reads rows [a_row0 + s * a_row_stride, + M) of A
+    const T* B; int ldb, M, N, K;
+};
+template <typename T, class Epi>
+static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void* dev_params) {
+    const int n = (int)c.eps.size();
+    if (n == 0) return 0;
+    chain_begin(h, st);
+    bool done = false;
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC && h->cfg.gemm_backend != 9 && n >= 2) {
+            if (!h->tc_cache) h->tc_cache = new tc::MapCache();
+            tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
+            typedef typename Epi::Params P;
+            CUDA_TRY(h, cudaMemcpyAsync(dev_params, c.eps.data(), (size_t)n * sizeof(P), cudaMemcpyHostToDevice, st));
+            unsigned* gbar = h->gbar + (st == h->side ? 16 : 0);
+            const P* dp = (const P*)dev_params;
+            cudaError_t e;
+            constexpr bool bwd = std::is_same<Epi, EpiLstmBwd<bf16>>::value;
+            if constexpr (bwd) {
+                if ((c.K / tc::BK) % 4 != 0) e = cudaErrorLaunchOutOfResources;
+                else if (c.M > 128) e = tc::launch_chain<128, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                else e = tc::launch_chain<32, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+            } else {
+                if (c.M > 128) e = tc::launch_chain<128, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                else e = tc::launch_chain<32, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+            }
+            if (e == cudaSuccess) {
+                done = true;
+                h->launches++;
+                if (h->prof && h->chain_open) {
+                    for (int s2 = 0; s2 < n; ++s2) {
+                        const double lm = logical_dim(h, c.M), ln = logical_dim(h, c.N), lk = logical_dim(h, c.K);
+                        h->chain.flops += 2.0 * lm * ln * lk;
+                        h->chain.bytes += (lm * lk + ln * lk) * sizeof(T) + EpiBytes<Epi>::get(h, c.eps[s2], c.M);
+                    }
+                    h->chain.count += n; h->chain.M = c.M; h->chain.N = c.N; h->chain.K = c.K;
+                }
+            } else if (e != cudaErrorLaunchOutOfResources) {
+                return h->fail(S2VT_ECUDA, "persistent chain launch failed: %s", cudaGetErrorString(e));
+            } else {
+                (void)cudaGetLastError();
+            }
+        }
+    }
+    if (!done) {
+        for (int s2 = 0; s2 < n; ++s2)
+            TRY((gemm<T, CfgStep, Epi>(h, st, c.A + (size_t)(c.a_row0 + s2 * c.a_row_stride) * c.lda, c.lda, c.B, c.ldb, c.M, c.N, c.K, c.eps[s2])));
+    }
+    chain_end(h, st);
+    return 0;
+}
+
 static int ensure_side(s2vt_handle* h) {
     if (h->side) return 0;
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
@@ -457,7 +517,7 @@ extern "C" int s2vt_refresh(s2vt_handle* h, s2vt_stream st) {
 // =================================================================================================================
 template <typename T>
 struct Front {   // per-video part: frame projection + LSTM1 over all T steps
-    T* Xc; T* img; float* G1x; T* h1_all; float* c1_all; T* gates1;
+    T* Xc; T* img; float* G1x; T* h1_all; float* c1_all; T* gates1; void* chain;
 };
 template <typename T>
 static void plan_front(const s2vt_handle* h, Arena& a, int B, bool train, Front<T>& f) {
@@ -467,6 +527,7 @@ static void plan_front(const s2vt_handle* h, Arena& a, int B, bool train, Front<
     f.h1_all = a.take<T>((size_t)(h->T + 1) * B * h->Hp);
     f.c1_all = a.take<float>((size_t)(h->T + 1) * B * h->Hp);
     f.gates1 = train ? a.take<T>((size_t)h->T * B * h->Gp) : nullptr;
+    f.chain = a.take<char>((size_t)(h->T + 1) * 512);   // per-step epilogue parameters of the persistent chains (<= 512 B each)
 }
 
 template <typename T>
@@ -483,7 +544,9 @@ static int run_front(s2vt_handle* h, cudaStream_t st, const float* video, int B,
     }
     CUDA_TRY(h, cudaMemsetAsync(f.h1_all, 0, (size_t)B * Hp * sizeof(T), st));
     CUDA_TRY(h, cudaMemsetAsync(f.c1_all, 0, (size_t)B * Hp * sizeof(float), st));
-    chain_begin(h, st);
+    StepChain<T, EpiLstmFwd<T>> ch;
+    ch.A = f.h1_all; ch.lda = Hp; ch.a_total_rows = (T_ + 1) * B; ch.a_row0 = 0; ch.a_row_stride = B;
+    ch.B = (const T*)h->W1hT; ch.ldb = Hp; ch.M = B; ch.N = Gp; ch.K = Hp;
     for (int t = 0; t < T_; ++t) {   // :128-129 / :148-149 LSTM1; decoder steps get `padding` -> no input term (Q8)
         typename EpiLstmFwd<T>::Params ep;
         memset(&ep, 0, sizeof ep);
@@ -493,23 +556,27 @@ static int run_front(s2vt_handle* h, cudaStream_t st, const float* video, int B,
         ep.h_out = f.h1_all + (size_t)(t + 1) * B * Hp;
         ep.gates_out = f.gates1 ? f.gates1 + (size_t)t * B * Gp : nullptr;
         ep.keep = 1.f;
-        TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, f.h1_all + (size_t)t * B * Hp, Hp, h->W1hT, Hp, B, Gp, Hp, ep)));
+        ch.eps.push_back(ep);
     }
-    chain_end(h, st);
+    TRY((run_chain<T, EpiLstmFwd<T>>(h, st, ch, f.chain)));
     return 0;
 }
 
 // ---- rollout (greedy + K samples), also the front half of beam search --------------------------------------------
 template <typename T>
 struct Roll {
-    Front<T> f; float* G2x; T* h2e[2]; float* c2e[2]; T* h2r[2]; float* c2r[2]; float* logits; int* tok[2]; int* ids;
+    Front<T> f; float* G2x; T* h2enc; float* c2e[2]; T* h2r[2]; float* c2r[2]; float* logits; int* tok[2]; int* ids; void* chain;
+    T* h2_final;   // encoder LSTM2 output state (rows of h2enc after the last frame)
     float* pick_val; int* pick_idx; int pick_ld;
 };
 template <typename T>
 static void plan_roll(const s2vt_handle* h, Arena& a, int B, int R, Roll<T>& r) {
     plan_front<T>(h, a, B, true, r.f);   // same layout as the training plan so the LSTM1 forward can be shared
     r.G2x = a.take<float>((size_t)h->T * B * h->Gp);
-    for (int i = 0; i < 2; ++i) { r.h2e[i] = a.take<T>((size_t)B * h->Hp); r.c2e[i] = a.take<float>((size_t)B * h->Hp); }
+    r.h2enc = a.take<T>((size_t)(h->Tv + 1) * B * h->Hp);   // LSTM2 state after every frame (one buffer: the persistent chain strides through it)
+    r.h2_final = r.h2enc ? r.h2enc + (size_t)h->Tv * B * h->Hp : nullptr;
+    for (int i = 0; i < 2; ++i) r.c2e[i] = a.take<float>((size_t)B * h->Hp);
+    r.chain = a.take<char>((size_t)(h->T + 1) * 512);
     for (int i = 0; i < 2; ++i) { r.h2r[i] = a.take<T>((size_t)R * h->Hp); r.c2r[i] = a.take<float>((size_t)R * h->Hp); }
     r.logits = a.take<float>((size_t)R * h->Vp);
     r.tok[0] = a.take<int>(R); r.tok[1] = a.take<int>(R);
@@ -518,7 +585,7 @@ static void plan_roll(const s2vt_handle* h, Arena& a, int B, int R, Roll<T>& r) 
     r.pick_val = a.take<float>((size_t)R * r.pick_ld); r.pick_idx = a.take<int>((size_t)R * r.pick_ld);
 }
 
-// frames -> (LSTM1 all steps, G2x all steps, LSTM2 encoder steps).  Leaves the encoder state in h2e[Tv&1], c2e[Tv&1].
+// frames -> (LSTM1 all steps, G2x all steps, LSTM2 encoder steps).  Leaves the encoder state in h2_final, c2e[Tv&1].
 template <typename T>
 static int run_encoder(s2vt_handle* h, cudaStream_t st, const float* video, int B, Roll<T>& r) {
     const int Tv = h->Tv, T_ = h->T, Hp = h->Hp, Gp = h->Gp;
@@ -530,17 +597,19 @@ static int run_encoder(s2vt_handle* h, cudaStream_t st, const float* video, int 
         typename EpiStore<T>::Params ep = {r.G2x, nullptr, Gp, nullptr, T_ * B, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, r.f.h1_all + (size_t)B * Hp, Hp, h->W2xT, Hp, T_ * B, Gp, Hp, ep)));
     }
-    CUDA_TRY(h, cudaMemsetAsync(r.h2e[0], 0, (size_t)B * Hp * sizeof(T), st));
+    CUDA_TRY(h, cudaMemsetAsync(r.h2enc, 0, (size_t)B * Hp * sizeof(T), st));
     CUDA_TRY(h, cudaMemsetAsync(r.c2e[0], 0, (size_t)B * Hp * sizeof(float), st));
-    chain_begin(h, st);
+    StepChain<T, EpiLstmFwd<T>> ch;
+    ch.A = r.h2enc; ch.lda = Hp; ch.a_total_rows = (Tv + 1) * B; ch.a_row0 = 0; ch.a_row_stride = B;
+    ch.B = (const T*)h->W2hT; ch.ldb = Hp; ch.M = B; ch.N = Gp; ch.K = Hp;
     for (int t = 0; t < Tv; ++t) {   // :131-132 LSTM2 on concat([output1, padding]) -> the embedding rows see zeros (Q8)
         typename EpiLstmFwd<T>::Params ep;
         memset(&ep, 0, sizeof ep);
         ep.M = B; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp;
-        ep.c_prev = r.c2e[t & 1]; ep.c_out = r.c2e[(t + 1) & 1]; ep.h_out = r.h2e[(t + 1) & 1]; ep.keep = 1.f;
-        TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, r.h2e[t & 1], Hp, h->W2hT, Hp, B, Gp, Hp, ep)));
+        ep.c_prev = r.c2e[t & 1]; ep.c_out = r.c2e[(t + 1) & 1]; ep.h_out = r.h2enc + (size_t)(t + 1) * B * Hp; ep.keep = 1.f;
+        ch.eps.push_back(ep);
     }
-    chain_end(h, st);
+    TRY((run_chain<T, EpiLstmFwd<T>>(h, st, ch, r.chain)));
     return 0;
 }
 
@@ -556,7 +625,7 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
     plan_roll<T>(h, a, B, R, r);
     if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small: need %zu bytes", a.used);
     TRY(run_encoder<T>(h, st, video, B, r));
-    tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2e[Tv & 1], B, R, Hp, r.h2r[0]); KCHECK(h);
+    tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2_final, B, R, Hp, r.h2r[0]); KCHECK(h);
     tile_rows_kernel<float><<<R, 256, 0, st>>>(r.c2e[Tv & 1], B, R, Hp, r.c2r[0]); KCHECK(h);
     fill_int_kernel<<<(R + 255) / 256, 256, 0, st>>>(r.tok[0], R, 1); KCHECK(h);   // <bos> = 1 (:321-323)
     // tile width the vocabulary-projection GEMM will use (decides how many candidates per row the fused pick produces)
@@ -621,6 +690,7 @@ struct Train {
     T* dlogits; float* dout2; T* dG2; float* dc2; float* dout1; float* dEmb; float* dh1; T* dG1; float* dc1; float* dimgF; T* dimgT_src;
     T *tA, *tB;   // transposed operand scratch (largest: [Vp, Mp])
     T *tA2, *tB2; // same for the LSTM1 chain on the side stream
+    void *chain_f, *chain_b2, *chain_b1;   // per-step parameters of the persistent chains
     T* emb;
 };
 
@@ -638,6 +708,7 @@ static void plan_train(const s2vt_handle* h, Arena& a, int B, int N, bool backwa
     p.prev_tok = a.take<int>((size_t)Tc * N); p.target = a.take<int>((size_t)Tc * N);
     p.ca = a.take<float>((size_t)Tc * N); p.cb = a.take<float>((size_t)Tc * N); p.cc = a.take<float>((size_t)Tc * N);
     p.logp = a.take<float>((size_t)Tc * N); p.sumlsm = a.take<float>((size_t)Tc * N);
+    p.chain_f = a.take<char>((size_t)(T_ + 1) * 512); p.chain_b2 = a.take<char>((size_t)(T_ + 1) * 512); p.chain_b1 = a.take<char>((size_t)(T_ + 1) * 512);
     if (!backward) return;
     const size_t MpD = ru(Tc * N, S2VT_PAD), Mp2 = ru(T_ * N, S2VT_PAD), Mp1 = ru(T_ * B, S2VT_PAD);
     p.dlogits = a.take<T>((size_t)Tc * N * Vp);
@@ -705,19 +776,23 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     caption_tables_kernel<<<(Tc * N + 255) / 256, 256, 0, st>>>(captions, N, Tc, p.prev_tok, p.target); KCHECK(h);
     CUDA_TRY(h, cudaMemsetAsync(p.h2_all, 0, (size_t)N * Hp * sizeof(T), st));
     CUDA_TRY(h, cudaMemsetAsync(p.c2_all, 0, (size_t)N * Hp * sizeof(float), st));
-    chain_begin(h, st);
-    for (int t = 0; t < T_; ++t) {
-        typename EpiLstmFwd<T>::Params ep;
-        memset(&ep, 0, sizeof ep);
-        ep.M = N; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = p.G2x + (size_t)t * N * Gp;
-        if (t >= Tv) { ep.add1 = h->Etab; ep.tok = p.prev_tok + (size_t)(t - Tv) * N; ep.hdrop_out = p.out2d + (size_t)(t - Tv) * N * Hp; }
-        ep.c_prev = p.c2_all + (size_t)t * N * Hp; ep.c_out = p.c2_all + (size_t)(t + 1) * N * Hp;
-        ep.h_out = p.h2_all + (size_t)(t + 1) * N * Hp;
-        ep.gates_out = p.gates2 ? p.gates2 + (size_t)t * N * Gp : nullptr;
-        ep.seed = drop_seed; ep.stream = S2VT_STREAM_DROP2; ep.step = (uint32_t)t; ep.row_base = row_base; ep.keep = keep;
-        TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, p.h2_all + (size_t)t * N * Hp, Hp, h->W2hT, Hp, N, Gp, Hp, ep)));
+    {
+        StepChain<T, EpiLstmFwd<T>> ch;
+        ch.A = p.h2_all; ch.lda = Hp; ch.a_total_rows = (T_ + 1) * N; ch.a_row0 = 0; ch.a_row_stride = N;
+        ch.B = (const T*)h->W2hT; ch.ldb = Hp; ch.M = N; ch.N = Gp; ch.K = Hp;
+        for (int t = 0; t < T_; ++t) {
+            typename EpiLstmFwd<T>::Params ep;
+            memset(&ep, 0, sizeof ep);
+            ep.M = N; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = p.G2x + (size_t)t * N * Gp;
+            if (t >= Tv) { ep.add1 = h->Etab; ep.tok = p.prev_tok + (size_t)(t - Tv) * N; ep.hdrop_out = p.out2d + (size_t)(t - Tv) * N * Hp; }
+            ep.c_prev = p.c2_all + (size_t)t * N * Hp; ep.c_out = p.c2_all + (size_t)(t + 1) * N * Hp;
+            ep.h_out = p.h2_all + (size_t)(t + 1) * N * Hp;
+            ep.gates_out = p.gates2 ? p.gates2 + (size_t)t * N * Gp : nullptr;
+            ep.seed = drop_seed; ep.stream = S2VT_STREAM_DROP2; ep.step = (uint32_t)t; ep.row_base = row_base; ep.keep = keep;
+            ch.eps.push_back(ep);
+        }
+        TRY((run_chain<T, EpiLstmFwd<T>>(h, st, ch, p.chain_f)));
     }
-    chain_end(h, st);
     {   // logits for all decode steps at once (:163 / :286)
         typename EpiStore<T>::Params ep = {p.logits, nullptr, Vp, h->bo_p, Tc * N, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.out2d, Hp, h->WoT, Hp, Tc * N, Vp, Hp, ep)));
@@ -768,23 +843,27 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
     // LSTM2 BPTT
     CUDA_TRY(h, cudaMemsetAsync(p.dc2, 0, (size_t)N * Hp * sizeof(float), st));
-    chain_begin(h, st);
-    for (int t = T_ - 1; t >= 0; --t) {
-        LstmBwdArgs b;
-        memset(&b, 0, sizeof b);
-        b.M = N; b.Hp = Hp;
-        b.dh_ext = t >= Tv ? p.dout2 + (size_t)(t - Tv) * N * Hp : nullptr;
-        b.gates = p.gates2 + (size_t)t * N * Gp; b.c_prev = p.c2_all + (size_t)t * N * Hp; b.c_new = p.c2_all + (size_t)(t + 1) * N * Hp;
-        b.dc = p.dc2; b.seed = drop_seed; b.stream = S2VT_STREAM_DROP2; b.step = (uint32_t)t; b.row_base = row_base; b.keep = keep;
-        T* dg = p.dG2 + (size_t)t * N * Gp;
-        if (t == T_ - 1) {
-            lstm_bwd_elem_kernel<T><<<(N * Hp + 255) / 256, 256, 0, st>>>(b, dg); KCHECK(h);
-        } else {
-            typename EpiLstmBwd<T>::Params ep = {b, dg};
-            TRY((gemm<T, CfgStep, EpiLstmBwd<T>>(h, st, p.dG2 + (size_t)(t + 1) * N * Gp, Gp, h->W2h, Gp, N, Hp, Gp, ep)));
+    {
+        StepChain<T, EpiLstmBwd<T>> ch;       // step s of the chain is time t = T-2-s; its A operand is dG2 of time t+1
+        ch.A = p.dG2; ch.lda = Gp; ch.a_total_rows = T_ * N; ch.a_row0 = (T_ - 1) * N; ch.a_row_stride = -N;
+        ch.B = (const T*)h->W2h; ch.ldb = Gp; ch.M = N; ch.N = Hp; ch.K = Gp;
+        for (int t = T_ - 1; t >= 0; --t) {
+            LstmBwdArgs b;
+            memset(&b, 0, sizeof b);
+            b.M = N; b.Hp = Hp;
+            b.dh_ext = t >= Tv ? p.dout2 + (size_t)(t - Tv) * N * Hp : nullptr;
+            b.gates = p.gates2 + (size_t)t * N * Gp; b.c_prev = p.c2_all + (size_t)t * N * Hp; b.c_new = p.c2_all + (size_t)(t + 1) * N * Hp;
+            b.dc = p.dc2; b.seed = drop_seed; b.stream = S2VT_STREAM_DROP2; b.step = (uint32_t)t; b.row_base = row_base; b.keep = keep;
+            T* dg = p.dG2 + (size_t)t * N * Gp;
+            if (t == T_ - 1) {
+                lstm_bwd_elem_kernel<T><<<(N * Hp + 255) / 256, 256, 0, st>>>(b, dg); KCHECK(h);
+            } else {
+                typename EpiLstmBwd<T>::Params ep = {b, dg};
+                ch.eps.push_back(ep);
+            }
         }
+        TRY((run_chain<T, EpiLstmBwd<T>>(h, st, ch, p.chain_b2)));
     }
-    chain_end(h, st);
     {   // gradient flowing into LSTM1's (dropped, shared-per-video) output
         typename EpiStore<T>::Params ep = {p.dout1, nullptr, Hp, nullptr, M2, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2, Gp, h->W2x, Gp, M2, Hp, Gp, ep)));
@@ -797,19 +876,25 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
     // LSTM1 BPTT over the B shared rows (side stream)
     CUDA_TRY(h, cudaMemsetAsync(p.dc1, 0, (size_t)B * Hp * sizeof(float), s2));
-    for (int t = T_ - 1; t >= 0; --t) {
-        LstmBwdArgs b;
-        memset(&b, 0, sizeof b);
-        b.M = B; b.Hp = Hp; b.dh_ext = p.dh1 + (size_t)t * B * Hp;
-        b.gates = p.f.gates1 + (size_t)t * B * Gp; b.c_prev = p.f.c1_all + (size_t)t * B * Hp; b.c_new = p.f.c1_all + (size_t)(t + 1) * B * Hp;
-        b.dc = p.dc1; b.keep = 1.f;
-        T* dg = p.dG1 + (size_t)t * B * Gp;
-        if (t == T_ - 1) {
-            lstm_bwd_elem_kernel<T><<<(B * Hp + 255) / 256, 256, 0, s2>>>(b, dg); KCHECK(h);
-        } else {
-            typename EpiLstmBwd<T>::Params ep = {b, dg};
-            TRY((gemm<T, CfgStep, EpiLstmBwd<T>>(h, s2, p.dG1 + (size_t)(t + 1) * B * Gp, Gp, h->W1h, Gp, B, Hp, Gp, ep)));
+    {
+        StepChain<T, EpiLstmBwd<T>> ch;
+        ch.A = p.dG1; ch.lda = Gp; ch.a_total_rows = T_ * B; ch.a_row0 = (T_ - 1) * B; ch.a_row_stride = -B;
+        ch.B = (const T*)h->W1h; ch.ldb = Gp; ch.M = B; ch.N = Hp; ch.K = Gp;
+        for (int t = T_ - 1; t >= 0; --t) {
+            LstmBwdArgs b;
+            memset(&b, 0, sizeof b);
+            b.M = B; b.Hp = Hp; b.dh_ext = p.dh1 + (size_t)t * B * Hp;
+            b.gates = p.f.gates1 + (size_t)t * B * Gp; b.c_prev = p.f.c1_all + (size_t)t * B * Hp; b.c_new = p.f.c1_all + (size_t)(t + 1) * B * Hp;
+            b.dc = p.dc1; b.keep = 1.f;
+            T* dg = p.dG1 + (size_t)t * B * Gp;
+            if (t == T_ - 1) {
+                lstm_bwd_elem_kernel<T><<<(B * Hp + 255) / 256, 256, 0, s2>>>(b, dg); KCHECK(h);
+            } else {
+                typename EpiLstmBwd<T>::Params ep = {b, dg};
+                ch.eps.push_back(ep);
+            }
         }
+        TRY((run_chain<T, EpiLstmBwd<T>>(h, s2, ch, p.chain_b1)));
     }
     {   // LSTM1 kernel / bias gradients (side stream, own transpose scratch)
         float* gW1 = h->G_(h->iW1);
