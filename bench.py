@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--ref-videos', type=int, default=8, help='videos per step of the CPU reference arm / cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-backend', default='auto')
+    ap.add_argument('--overlap', type=int, default=-1, help='debug: side-stream overlap mask (s2vt_set_overlap)')
     ap.add_argument('--quick', action='store_true', help='timed region only (for ncu launch lists): no e2e / roofline / CPU passes')
     return ap.parse_args()
 
@@ -227,6 +228,8 @@ def run_b200(args):
     model = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=B,
                                               n_video_lstm_step=Tv, n_caption_lstm_step=35, bias_init_vector=bias, dropout_rate=0.9,
                                               precision=args.precision, max_videos=B, max_rows=K * B, seed=4, gemm_backend=args.gemm_backend)
+    if args.overlap >= 0:
+        model.lib.s2vt_set_overlap(model.h, args.overlap)
     model.variable('embed_word_W').mul_(3.0)
     model.refresh()
     scorer = s2vt_b200.cider.CiderD([by[v] for v in order], w2i)

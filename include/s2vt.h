@@ -141,6 +141,9 @@ long long s2vt_launch_count(const s2vt_handle* h);
 int s2vt_profile(s2vt_handle* h, int enable);
 int s2vt_profile_read(s2vt_handle* h, double* ms_out, double* flops_out, long long* launches_out);
 /* per (class, M, N, K) totals of the current records (call before s2vt_profile_read); returns the number of rows */
+/* tuning: which independent pieces use the library's internal side stream (bit 0: late half of s2vt_refresh, bit 1: the
+ * vocabulary weight gradient, bit 2: the LSTM1 backward chain); default 7 */
+int s2vt_set_overlap(s2vt_handle* h, int mask);
 /* debug: per-launch phase timestamps (%globaltimer) of CTA (0,0) of every tcgen05 GEMM; NULL disables */
 int s2vt_debug_probe(void* device_buffer);
 int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* K, double* ms, long long* count);

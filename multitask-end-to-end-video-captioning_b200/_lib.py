@@ -39,6 +39,7 @@ SIGNATURES = {
     's2vt_variable_info': (_i32, [_vp, _i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.POINTER(_i64 * 2), C.POINTER(_i32)]),
     's2vt_load_param': (_i32, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i32, _vp]),
     's2vt_refresh': (_i32, [_vp, _vp]),
+    's2vt_set_overlap': (_i32, [_vp, _i32]),
     's2vt_set_reuse_frontend': (_i32, [_vp, _i32]),
     's2vt_greedy': (_i32, [_vp, _vp, _i32, _vp, _vp]),
     's2vt_rollout': (_i32, [_vp, _vp, _i32, _i32, _u64, _u32, _vp, _vp, _vp]),

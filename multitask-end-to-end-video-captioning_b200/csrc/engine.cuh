@@ -64,7 +64,8 @@ struct s2vt_handle {
     int front_B = 0; const float* front_video = nullptr;
     // internal side stream for the LSTM1 backward chain (fork/join inside one call; invisible to the caller)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_refresh = nullptr;
-    bool copies_zeroed = false;             // tc::MapCache (TMA tensor maps keyed by pointer / shape)
+    bool copies_zeroed = false;
+    int overlap = 7;                      // bit 0: late refresh, bit 1: dWo, bit 2: LSTM1 backward chain run on the side stream             // tc::MapCache (TMA tensor maps keyed by pointer / shape)
     // variable indices
     int iWemb, iWe, ibe, iWo, ibo, iW1, ib1, iW2, ib2, iAW, iAb;
     mutable std::string err;

@@ -21,7 +21,10 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     return v;
 }
 
-template <int BN, class Epi, int KS>
+// WS (weights stationary, a_rows <= 64 and K/KS <= 16 K-blocks): this CTA's weight slab (BN x K/KS, <= 64 KB) is fetched once
+// and stays in shared memory for the whole chain; every A K-block of a step has its own stage (no ring, no `empty`
+// barriers: the end-of-step barrier frees all stages), so all loads of a step are in flight at once.
+template <int BN, class Epi, int KS, bool WS>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                             int K, int a_rows, int a_row0, int a_row_stride,
                                                                             const typename Epi::Params* __restrict__ steps, int nsteps,
@@ -31,11 +34,16 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
     static_assert(KS == 1 || KS == 4, "split-K cluster of 4 or none");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::PIPE_BYTES);
-    uint64_t* empty = full + C::STAGES;
-    uint64_t* tmem_full = empty + C::STAGES;
+    constexpr int WS_KB = 16;                                          // K-blocks per CTA in weights-stationary mode
+    constexpr int WS_A = 64 * 128;                                     // bytes of one A stage (64 rows x 64 bf16)
+    constexpr int MAIN = WS ? WS_KB * (WS_A + C::B_BYTES) : C::PIPE_BYTES;
+    constexpr int NBAR = WS ? WS_KB : C::STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + MAIN);
+    uint64_t* empty = full + NBAR;                                     // (ring mode only) / wfull in WS mode
+    uint64_t* tmem_full = empty + NBAR;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    float* recv = reinterpret_cast<float*>(smem + C::PIPE_BYTES + C::BAR_BYTES);   // [KS][32][BN] (KS > 1)
+    float* recv = reinterpret_cast<float*>(smem + MAIN + 512);          // [KS][32][BN] (KS > 1)
+    unsigned char* wsm = smem + WS_KB * WS_A;                          // WS: weight slab [WS_KB][BN x 64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * C::BM, n0 = blockIdx.x * BN;
@@ -47,9 +55,13 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < NBAR; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if constexpr (WS) {   // the whole weight slab, once (weights never depend on the previous kernel)
+            mbar_expect_tx(empty, (uint32_t)(KBL * C::B_BYTES));
+            for (int i = 0; i < KBL; ++i) tma_load_2d_raw(wsm + i * C::B_BYTES, &mapB, empty, (kb0 + i) * C::BK, n0);
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
@@ -66,7 +78,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
     for (int s = 0; s < nsteps; ++s) {
         const int g0 = s * KBL;   // running K-block counter at the start of this step (pipeline phases continue across steps)
         // ---- weight tiles of the first stages: independent of the previous step, requested before the barrier
-        if (warp == 0 && lane == 0) {
+        if (!WS && warp == 0 && lane == 0) {
             for (int i = 0; i < pre; ++i) {
                 const int g = g0 + i, st = g % C::STAGES;
                 if (g >= C::STAGES) mbar_wait(empty + st, ((g / C::STAGES) - 1) & 1);
@@ -97,6 +109,12 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
         if (warp == 0) {
             if (lane == 0) {
                 asm volatile("fence.proxy.async;" ::: "memory");   // rows written through the generic proxy by other SMs are read by TMA
+                if constexpr (WS) {
+                    for (int i = 0; i < KBL; ++i) {
+                        mbar_expect_tx(full + i, (uint32_t)(a_rows * 128));
+                        tma_load_2d_raw(smem + i * WS_A, &mapA, full + i, (kb0 + i) * C::BK, arow);
+                    }
+                } else
                 for (int i = 0; i < KBL; ++i) {
                     const int g = g0 + i, st = g % C::STAGES;
                     unsigned char* a = smem + st * C::STAGE_BYTES;
@@ -111,6 +129,16 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
             __syncwarp();
         } else if (warp == 1) {
             if (lane == 0) {
+                if constexpr (WS) {
+                    if (s == 0) mbar_wait(empty, 0);           // weight slab has landed
+                    for (int i = 0; i < KBL; ++i) {
+                        mbar_wait(full + i, s & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t adesc = make_desc(smem_u32(smem + i * WS_A)), bdesc = make_desc(smem_u32(wsm + i * C::B_BYTES));
+#pragma unroll
+                        for (int k = 0; k < C::BK / 16; ++k) mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (i | k) != 0);
+                    }
+                } else
                 for (int i = 0; i < KBL; ++i) {
                     const int g = g0 + i, st = g % C::STAGES;
                     mbar_wait(full + st, (g / C::STAGES) & 1);
@@ -183,18 +211,19 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
 
 // Host launcher.  A: one buffer of `a_total_rows` rows (row stride lda); step s reads rows [a_row0 + s * a_row_stride, + M).
 // Returns cudaErrorLaunchOutOfResources (without launching) if the grid cannot be co-resident.
-template <int BN, class Epi, int KS>
+template <int BN, class Epi, int KS, bool WS = false>
 inline cudaError_t launch_chain(MapCache& cache, cudaStream_t st, const bf16* A, int lda, int a_total_rows, int a_row0, int a_row_stride, const bf16* B,
                                 int ldb, int M, int N, int K, const typename Epi::Params* steps_dev, int nsteps, unsigned* gbar, bool pdl) {
     constexpr int NT = Threads<BN, Epi>::N;
     using C = Cfg<BN, NT>;
-    constexpr int SMEM = C::SMEM_BYTES + (KS > 1 ? KS * 32 * BN * 4 : 0);
+    constexpr int SMEM = (WS ? 16 * (64 * 128 + C::B_BYTES) + 512 + 1024 : C::SMEM_BYTES + 512) + (KS > 1 ? KS * 32 * BN * 4 : 0);
+    if (WS && (M > 64 || K / BK / KS > 16)) return cudaErrorLaunchOutOfResources;
     if (cache.size() > 32768) cache.clear();
     const int a_rows = M <= 64 ? ((M + 7) & ~7) : BM;
     const CUtensorMap* ma = get_map(cache, A, a_total_rows, K, lda, a_rows);
     const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN);
     if (!ma || !mb) return cudaErrorInvalidValue;
-    auto kern = gemm_tc_chain_kernel<BN, Epi, KS>;
+    auto kern = gemm_tc_chain_kernel<BN, Epi, KS, WS>;
     static int max_ctas = -1;
     if (max_ctas < 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);

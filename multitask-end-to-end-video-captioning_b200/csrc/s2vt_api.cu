@@ -160,6 +160,12 @@ extern "C" int s2vt_debug_probe(void* device_buffer) {
     unsigned long long* p = (unsigned long long*)device_buffer;
     return cudaMemcpyToSymbol(tc::g_probe, &p, sizeof p) == cudaSuccess ? 0 : S2VT_ECUDA;
 }
+// Debug / tuning: which independent pieces run on the internal side stream (bit 0 late refresh, 1 dWo, 2 LSTM1 backward).
+extern "C" int s2vt_set_overlap(s2vt_handle* h, int mask) {
+    if (!h) return S2VT_EINVAL;
+    h->overlap = mask;
+    return 0;
+}
 extern "C" int s2vt_set_reuse_frontend(s2vt_handle* h, int enable) {
     if (!h) return S2VT_EINVAL;
     h->reuse_front = enable != 0;
@@ -411,10 +417,18 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
             if constexpr (bwd) {
                 if ((c.K / tc::BK) % 4 != 0) e = cudaErrorLaunchOutOfResources;
                 else if (c.M > 128) e = tc::launch_chain<128, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
-                else e = tc::launch_chain<32, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                else {
+                    e = cudaErrorLaunchOutOfResources;
+                    if (c.M <= 64 && h->cfg.gemm_backend != 10) e = tc::launch_chain<32, Epi, 4, true>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                    if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true); }
+                }
             } else {
                 if (c.M > 128) e = tc::launch_chain<128, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
-                else e = tc::launch_chain<32, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                else {
+                    e = cudaErrorLaunchOutOfResources;   // weights-stationary variant first (rows <= 64, K <= 16 blocks)
+                    if (c.M <= 64 && h->cfg.gemm_backend != 10) e = tc::launch_chain<32, Epi, 1, true>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                    if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true); }
+                }
             }
             if (e == cudaSuccess) {
                 done = true;
@@ -474,7 +488,7 @@ static int refresh_impl(s2vt_handle* h, cudaStream_t st) {
     const float* W1 = h->P_(h->iW1); const float* W2 = h->P_(h->iW2);
     const int G = 4 * H;
     TRY(ensure_side(h));
-    cudaStream_t s2 = h->side;
+    cudaStream_t s2 = (h->overlap & 1) ? h->side : st;
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));                 // parameters (and the zeroing) are final on `st` here
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
     // early half, caller's stream: what the next call needs first (frame projection and LSTM1 forward)
@@ -832,7 +846,8 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     // ---- side stream 1/2: the vocabulary-projection weight gradient only needs dlogits / out2, so it runs (large GEMM, fills
     //      the idle SMs) while the main stream walks the latency-bound LSTM2 BPTT chain.
     TRY(ensure_side(h));
-    cudaStream_t s2 = h->side;
+    cudaStream_t s2 = (h->overlap & 2) ? h->side : st;
+    cudaStream_t s3 = (h->overlap & 4) ? h->side : st;   // stream of the LSTM1 backward chain
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
     {   // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums
@@ -873,9 +888,9 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     //      LSTM2 / vocabulary weight gradients (large GEMMs); joined before returning.
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));   // dWo done: tA / tB are free again
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
-    CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(s3, h->ev_fork, 0));
     // LSTM1 BPTT over the B shared rows (side stream)
-    CUDA_TRY(h, cudaMemsetAsync(p.dc1, 0, (size_t)B * Hp * sizeof(float), s2));
+    CUDA_TRY(h, cudaMemsetAsync(p.dc1, 0, (size_t)B * Hp * sizeof(float), s3));
     {
         StepChain<T, EpiLstmBwd<T>> ch;
         ch.A = p.dG1; ch.lda = Gp; ch.a_total_rows = T_ * B; ch.a_row0 = (T_ - 1) * B; ch.a_row_stride = -B;
@@ -888,31 +903,31 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
             b.dc = p.dc1; b.keep = 1.f;
             T* dg = p.dG1 + (size_t)t * B * Gp;
             if (t == T_ - 1) {
-                lstm_bwd_elem_kernel<T><<<(B * Hp + 255) / 256, 256, 0, s2>>>(b, dg); KCHECK(h);
+                lstm_bwd_elem_kernel<T><<<(B * Hp + 255) / 256, 256, 0, s3>>>(b, dg); KCHECK(h);
             } else {
                 typename EpiLstmBwd<T>::Params ep = {b, dg};
                 ch.eps.push_back(ep);
             }
         }
-        TRY((run_chain<T, EpiLstmBwd<T>>(h, s2, ch, p.chain_b1)));
+        TRY((run_chain<T, EpiLstmBwd<T>>(h, s3, ch, p.chain_b1)));
     }
     {   // LSTM1 kernel / bias gradients (side stream, own transpose scratch)
         float* gW1 = h->G_(h->iW1);
-        TRY(bias_grad<T>(h, s2, p.dG1, Gp, Gp, M1, 0, H, h->G_(h->ib1)));
+        TRY(bias_grad<T>(h, s3, p.dG1, Gp, Gp, M1, 0, H, h->G_(h->ib1)));
         EpiGradStore::Params e2 = {gW1 + (size_t)E * G, G, H, G, H, 1.f};
-        TRY(wgrad<T>(h, s2, p.f.h1_all, Hp, Hp, p.dG1, Gp, Gp, M1, e2, p.tA2, p.tB2, H));     // h1 before step t = h1_all[t]
+        TRY(wgrad<T>(h, s3, p.f.h1_all, Hp, Hp, p.dG1, Gp, Gp, M1, e2, p.tA2, p.tB2, H));     // h1 before step t = h1_all[t]
         // frame-embedding rows: encoder steps only
         EpiGradStore::Params e1 = {gW1, G, E, G, H, 1.f};
-        TRY(wgrad<T>(h, s2, p.f.img, Ep, Ep, p.dG1, Gp, Gp, ME, e1, p.tA2, p.tB2, E));
+        TRY(wgrad<T>(h, s3, p.f.img, Ep, Ep, p.dG1, Gp, Gp, ME, e1, p.tA2, p.tB2, E));
     }
     {   // frame projection gradients: dimg = dG1[enc] . W1[x rows]^T ; dWe = X^T . dimg ; dbe = column sums (side stream)
         typename EpiStore<T>::Params ep = {p.dimgF, p.dimgT_src, Ep, nullptr, ME, 0};
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, s2, p.dG1, Gp, h->W1x, Gp, ME, Ep, Gp, ep)));
-        TRY(bias_grad<T>(h, s2, p.dimgT_src, Ep, Ep, ME, E, 0, h->G_(h->ibe)));
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, s3, p.dG1, Gp, h->W1x, Gp, ME, Ep, Gp, ep)));
+        TRY(bias_grad<T>(h, s3, p.dimgT_src, Ep, Ep, ME, E, 0, h->G_(h->ibe)));
         EpiGradStore::Params e = {h->G_(h->iWe), E, D, E, 0, 1.f};
-        TRY(wgrad<T>(h, s2, p.f.Xc, Dp, Dp, p.dimgT_src, Ep, Ep, ME, e, p.tA2, p.tB2, D));
+        TRY(wgrad<T>(h, s3, p.f.Xc, Dp, Dp, p.dimgT_src, Ep, Ep, ME, e, p.tA2, p.tB2, D));
     }
-    CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
+    CUDA_TRY(h, cudaEventRecord(h->ev_join, s3));
     // ---- main stream meanwhile: embedding and LSTM2 weight gradients
     {   // word-embedding gradient
         typename EpiStore<T>::Params ee = {p.dEmb, nullptr, Ep, nullptr, MD, 0};
