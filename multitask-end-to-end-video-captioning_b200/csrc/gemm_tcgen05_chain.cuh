@@ -92,14 +92,13 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
         } else {
             __syncthreads();                       // this CTA's stores of step s-1 are issued
             if (threadIdx.x == 0) {
-                __threadfence();
-                atomicAdd(gbar, 1u);
+                // release: orders this CTA's stores (made visible to thread 0 by the bar.sync above, cumulativity) before the arrival
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(gbar), "r"(1u) : "memory");
                 const unsigned target = (unsigned)s * ncta;
                 long long t0 = clock64();
                 while (ld_acquire_gpu(gbar) < target) {
                     if (clock64() - t0 > 4000000000LL) { printf("s2vt: grid barrier timed out (step %d, block %d,%d,%d)\n", s, blockIdx.x, blockIdx.y, blockIdx.z); __trap(); }
                 }
-                __threadfence();
             }
             __syncthreads();
         }
