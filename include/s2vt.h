@@ -40,7 +40,15 @@ enum {
 };
 
 enum { S2VT_PREC_BF16 = 0, S2VT_PREC_FP32 = 1 };
-enum { S2VT_GEMM_AUTO = 0, S2VT_GEMM_MMA_SYNC = 1, S2VT_GEMM_TCGEN05 = 2 };
+enum { S2VT_GEMM_AUTO = 0, S2VT_GEMM_MMA_SYNC = 1, S2VT_GEMM_TCGEN05 = 2,
+       /* debugging / A-B variants of the tcgen05 path (tests/test_gpu_backends.py): */
+       S2VT_GEMM_TC_N128 = 3,        /* 128-wide batched tiles */
+       S2VT_GEMM_TC_MC2X2 = 4,       /* + 2x2 TMA multicast clusters */
+       S2VT_GEMM_STEP_MC8 = 5, S2VT_GEMM_STEP_MC4 = 6,   /* multicast the activations of the >128-row step kernels */
+       S2VT_GEMM_STEP_N64 = 7,       /* 64-wide tiles for the >128-row step kernels */
+       S2VT_GEMM_WGRAD_TRANSPOSED = 8,   /* weight gradients through explicit transposes instead of MN-major descriptors */
+       S2VT_GEMM_PER_STEP = 9,       /* one launch per time step instead of persistent chains */
+       S2VT_GEMM_CHAIN_RING = 10 };  /* persistent chains without the weights-stationary variant */
 
 /* Model dimensions: the "Train Parameters" constants of reinforcement_multisampling_tf_s2vt.py:505-511
  * (dim_image, word_dim, lstm_dim, n_video_lstm_step, n_caption_lstm_step) and n_words = len(wordtoix) (:617). */
