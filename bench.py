@@ -26,9 +26,10 @@ sys.path.insert(0, ROOT)
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 DIMS = dict(D=1536, E=500, H=1000, V=9972)
 METRIC = 'reinforce_train_videos_per_s'
-# dram__bytes_read.sum + dram__bytes_write.sum per recurrent-step launch under ncu (cache flushed before each kernel), mean over the
-# step kernels of one iteration -- profiles/r1_tc_metrics.md (457 launches)
-STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = 14812657
+# ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the persistent chain kernels at the bench configuration, keyed by
+# (rows, N, K) (profiles/r1_tc_metrics.md)
+STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = {(320, 1024, 4096): 799710000, (320, 4096, 1024): 1189090000,
+                                     (64, 4096, 1024): 119510000, (64, 1024, 4096): 163300000}
 
 
 def parse():
@@ -317,25 +318,39 @@ def run_b200(args):
     ach_tf = bfl / (bms * 1e-3) / 1e12 if bms > 0 else 0.0
     ach_gb = sby / (sms * 1e-3) / 1e9 if sms > 0 else 0.0
     hbm = peaks.get('hbm_gbs', 6650.0)
+    # dominant kernel by time: the recurrent-step shape with the largest total (the LSTM2 backward-through-time chain at the
+    # metric's configuration): one persistent launch walks all its time steps
+    dom = max([x for x in shapes if x[0] == 1], key=lambda x: x[4])
+    _, dM, dN, dK, dms, dcnt, dby, dln = dom
+    dname = 'EpiLstmBwd' if dK > dN else 'EpiLstmFwd'
+    d_ach = dby / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
+    roof = {'kernel': 'tc::gemm_tc_chain_kernel<BN, %s<bf16>> rows=%d N=%d K=%d (persistent chain: per time step h.W_h on tcgen05 + fused '
+                      'BasicLSTMCell %s, grid barrier between steps)' % (dname, dM, dN, dK, 'backward' if dK > dN else 'forward'),
+            'bound': 'hbm', 'achieved': d_ach, 'peak': hbm, 'unit': 'GB/s', 'frac': d_ach / hbm if hbm else None,
+            'traffic': STEP_KERNEL_DRAM_BYTES_PER_LAUNCH.get((dM, dN, dK)),
+            'traffic_source': 'ncu dram__bytes_read+write per launch, cache flushed (profiles/r1_tc_metrics.md)',
+            'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)',
+            'launches_per_step': dln / args.steps, 'recurrent_steps_per_launch': dcnt / dln if dln else None,
+            'us_per_launch': 1e3 * dms / dln if dln else None, 'ms_per_step': dms / args.steps,
+            'algorithmic_bytes_per_launch': dby / dln if dln else None,
+            'bytes_model': 'per recurrent step: bf16 W_h once + activation rows in + gate addends / saved gate activations / cell state / '
+                           'outputs (DESIGN.md section 4), times the steps one launch walks; weights and state stay L2-resident, the '
+                           'binding limits are the grid-barrier latency per step and the ~42 B/clk/SM L2->SM fill rate, not HBM',
+            'pass': 'separate instrumented pass of the same %d steps: CUDA events around each chain launch' % args.steps}
     out = {'metric': METRIC, 'value': value, 'unit': 'videos/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': workload_config(args, B, world),
            'clocks': clocks, 'e2e': {'value': e2e, 'unit': 'videos/s', 'h2d_bytes_per_step': int(feats_host.numel() * 4 + vidx_host.numel() * 4),
                                      'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps},
            'gpu_launches': int(launches), 'loss': loss, 'decode': beam,
-           'gemm_shapes': [{'class': 'batched' if c == 0 else 'step', 'M': M_, 'N': N_, 'K': K_, 'launches_per_step': n_ / args.steps,
-                            'us_per_launch': 1e3 * ms_ / n_, 'ms_per_step': ms_ / args.steps} for c, M_, N_, K_, ms_, n_ in sorted(shapes, key=lambda x: -x[4])],
-           # dominant kernel family by time: the per-time-step recurrent GEMM + fused LSTM cell (tcgen05, one launch per step)
-           'roofline': {'kernel': 'tc::gemm_tc_kernel<BN, EpiLstmFwd|EpiLstmBwd> (recurrent step: h.W_h on tcgen05 + fused BasicLSTMCell fwd/bwd)',
-                        'bound': 'hbm', 'achieved': ach_gb, 'peak': hbm, 'unit': 'GB/s', 'frac': ach_gb / hbm if hbm else None,
-                        'traffic': STEP_KERNEL_DRAM_BYTES_PER_LAUNCH, 'traffic_source': 'ncu dram__bytes_read+write per launch, cache flushed (profiles/)',
-                        'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)',
-                        'launches_per_step': sn / args.steps, 'ms_per_step': sms / args.steps, 'us_per_launch': 1e3 * sms / sn if sn else None,
-                        'algorithmic_bytes_per_launch': sby / sn if sn else None,
-                        'bytes_model': 'per launch: bf16 W_h (8.0 MB) + activation rows in + fp32 gate pre-activation addends, cell state, saved gate '
-                                       'activations and outputs (DESIGN.md section 4); weights and state are L2-resident, so the binding limit is the '
-                                       '~42 B/clk/SM L2->SM fill rate, not HBM',
-                        'pass': 'separate instrumented pass of the same %d steps: CUDA events around each chain of step launches' % args.steps},
+           'gemm_shapes': [{'class': 'batched' if c == 0 else 'step', 'M': M_, 'N': N_, 'K': K_, 'gemms_per_step': n_ / args.steps,
+                            'launches_per_step': l_ / args.steps, 'us_per_gemm': 1e3 * ms_ / n_, 'ms_per_step': ms_ / args.steps}
+                           for c, M_, N_, K_, ms_, n_, b_, l_ in sorted(shapes, key=lambda x: -x[4])],
+           'roofline': roof,
+           'roofline_recurrent_family': {'kernels': 'all recurrent-step kernels (persistent chains + the per-step launches of the sampling loops)',
+                                         'bound': 'hbm', 'achieved': ach_gb, 'peak': hbm, 'unit': 'GB/s', 'frac': ach_gb / hbm if hbm else None,
+                                         'recurrent_steps_per_iteration': sn / args.steps, 'ms_per_step': sms / args.steps,
+                                         'us_per_recurrent_step': 1e3 * sms / sn if sn else None},
            'roofline_batched_gemm': {'kernel': 'tc::gemm_tc_kernel<256, EpiStore|EpiGradStore> (128x256 tcgen05 tiles: projections, vocab logits, weight gradients)',
                                      'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach_tf / peak_tf if peak_tf else None,
                                      'peak_source': peak_src, 'launches_per_step': bn / args.steps, 'ms_per_step': bms / args.steps,

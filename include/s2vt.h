@@ -148,13 +148,16 @@ int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step,
 long long s2vt_launch_count(const s2vt_handle* h);
 int s2vt_profile(s2vt_handle* h, int enable);
 int s2vt_profile_read(s2vt_handle* h, double* ms_out, double* flops_out, long long* launches_out);
-/* per (class, M, N, K) totals of the current records (call before s2vt_profile_read); returns the number of rows */
+/* per (class, M, N, K) totals of the current records (call before s2vt_profile_read); returns the number of rows.
+ * count = GEMMs executed (recurrent steps for class 1), launches = kernel launches that executed them (a persistent
+ * chain runs many steps per launch), bytes = algorithmic bytes; bytes / launches may be NULL */
+int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* K, double* ms, long long* count, double* bytes,
+                        long long* launches);
 /* tuning: which independent pieces use the library's internal side stream (bit 0: late half of s2vt_refresh, bit 1: the
  * vocabulary weight gradient, bit 2: the LSTM1 backward chain); default 7 */
 int s2vt_set_overlap(s2vt_handle* h, int mask);
 /* debug: per-launch phase timestamps (%globaltimer) of CTA (0,0) of every tcgen05 GEMM; NULL disables */
 int s2vt_debug_probe(void* device_buffer);
-int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* K, double* ms, long long* count);
 
 /* ---- beam search: beam_probability + the host loop of final_beam_search.py:202-294 / e2e_beam_search.py:235-344,
  * batched over B videos on the device, semantics B1-B7 of SURVEY.md.

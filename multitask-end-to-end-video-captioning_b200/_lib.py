@@ -53,7 +53,7 @@ SIGNATURES = {
     's2vt_profile': (_i32, [_vp, _i32]),
     's2vt_profile_read': (_i32, [_vp, _vp, _vp, _vp]),
     's2vt_debug_probe': (_i32, [_vp]),
-    's2vt_profile_shapes': (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    's2vt_profile_shapes': (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     's2vt_beam_search': (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     's2vt_beam_init': (_i32, [_vp, _vp, _vp, _vp, _vp]),
     's2vt_beam_step': (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),

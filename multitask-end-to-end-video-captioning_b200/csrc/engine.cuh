@@ -53,7 +53,7 @@ struct s2vt_handle {
     // instrumentation (bench.py): launch counter and optional CUDA-event brackets around GEMM launches
     mutable long long launches = 0;
     bool prof = false;
-    struct ProfRec { cudaEvent_t a, b; double flops, bytes; int cls; int M, N, K; long long count; };
+    struct ProfRec { cudaEvent_t a, b; double flops, bytes; int cls; int M, N, K; long long count, launches; };
     // an open chain of per-step launches (bracketed as a whole so programmatic dependent launches keep overlapping)
     bool chain_open = false; ProfRec chain;
     std::vector<ProfRec> prof_recs;

@@ -277,7 +277,7 @@ static int chain_begin(s2vt_handle* h, cudaStream_t st) {
     if (!h->prof) return 0;
     h->chain = s2vt_handle::ProfRec();
     h->chain.a = prof_event(h); h->chain.b = prof_event(h);
-    h->chain.flops = h->chain.bytes = 0; h->chain.count = 0; h->chain.cls = 1; h->chain.M = h->chain.N = h->chain.K = 0;
+    h->chain.flops = h->chain.bytes = 0; h->chain.count = 0; h->chain.launches = 0; h->chain.cls = 1; h->chain.M = h->chain.N = h->chain.K = 0;
     h->chain_open = true;
     cudaEventRecord(h->chain.a, st);
     return 0;
@@ -300,9 +300,9 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
         rec.flops = 2.0 * lm * ln * lk;
         rec.bytes = (lm * lk + ln * lk) * sizeof(T) + EpiBytes<Epi>::get(h, ep, M);   // operands once + epilogue traffic
         rec.cls = Cfg::BM >= 128 ? 0 : 1;
-        rec.M = M; rec.N = N; rec.K = K; rec.count = 1;
+        rec.M = M; rec.N = N; rec.K = K; rec.count = 1; rec.launches = 1;
         if (in_chain) {
-            h->chain.flops += rec.flops; h->chain.bytes += rec.bytes; h->chain.count += 1;
+            h->chain.flops += rec.flops; h->chain.bytes += rec.bytes; h->chain.count += 1; h->chain.launches += 1;
             h->chain.M = M; h->chain.N = N; h->chain.K = K;
         } else {
             rec.a = prof_event(h); rec.b = prof_event(h);
@@ -364,7 +364,7 @@ static int wgrad(s2vt_handle* h, cudaStream_t st, const T* X, int ldx, int Mf, c
                 rec.a = prof_event(h); rec.b = prof_event(h);
                 rec.flops = 2.0 * logical_m * logical_dim(h, Nf) * (double)R;
                 rec.bytes = ((double)logical_m + logical_dim(h, Nf)) * R * sizeof(T);
-                rec.cls = 0; rec.M = Mf; rec.N = Nf; rec.K = R; rec.count = 1;
+                rec.cls = 0; rec.M = Mf; rec.N = Nf; rec.K = R; rec.count = 1; rec.launches = 1;
                 cudaEventRecord(rec.a, st);
             }
             h->launches++;
@@ -439,7 +439,7 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
                         h->chain.flops += 2.0 * lm * ln * lk;
                         h->chain.bytes += (lm * lk + ln * lk) * sizeof(T) + EpiBytes<Epi>::get(h, c.eps[s2], c.M);
                     }
-                    h->chain.count += n; h->chain.M = c.M; h->chain.N = c.N; h->chain.K = c.K;
+                    h->chain.count += n; h->chain.launches += 1; h->chain.M = c.M; h->chain.N = c.N; h->chain.K = c.K;
                 }
             } else if (e != cudaErrorLaunchOutOfResources) {
                 return h->fail(S2VT_ECUDA, "persistent chain launch failed: %s", cudaGetErrorString(e));
@@ -1082,7 +1082,8 @@ extern "C" int s2vt_profile(s2vt_handle* h, int enable) {
 // Synchronises the device, aggregates the bracketed GEMM launches per class (0: batched GEMMs, 1: recurrent-step GEMMs)
 // and clears the record list.
 // Per-shape breakdown of the bracketed launches (does not clear): up to `cap` distinct (cls, M, N, K) rows.
-extern "C" int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* K, double* ms, long long* count) {
+extern "C" int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* K, double* ms, long long* count, double* bytes,
+                                   long long* launches) {
     if (!h) return S2VT_EINVAL;
     CUDA_TRY(h, cudaDeviceSynchronize());
     int n = 0;
@@ -1091,8 +1092,10 @@ extern "C" int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, in
         cudaEventElapsedTime(&t, r.a, r.b);
         int i = 0;
         for (; i < n; ++i) if (cls[i] == r.cls && M[i] == r.M && N[i] == r.N && K[i] == r.K) break;
-        if (i == n) { if (n >= cap) continue; cls[n] = r.cls; M[n] = r.M; N[n] = r.N; K[n] = r.K; ms[n] = 0; count[n] = 0; ++n; }
+        if (i == n) { if (n >= cap) continue; cls[n] = r.cls; M[n] = r.M; N[n] = r.N; K[n] = r.K; ms[n] = 0; count[n] = 0; if (bytes) bytes[n] = 0; if (launches) launches[n] = 0; ++n; }
         ms[i] += t; count[i] += r.count;
+        if (bytes) bytes[i] += r.bytes;
+        if (launches) launches[i] += r.launches;
     }
     return n;
 }

@@ -238,11 +238,12 @@ class Video_Caption_Generator(object):
         self._check(self.lib.s2vt_profile(self.h, int(bool(enable))))
 
     def profile_shapes(self, cap=256):
-        """[(cls, M, N, K, total ms, launches)] of the GEMM launches recorded since the last profile_read."""
+        """[(cls, M, N, K, total ms, GEMMs, algorithmic bytes, kernel launches)] recorded since the last profile_read."""
         I = C.c_int * cap
         cls, M, N, K, ms, cnt = I(), I(), I(), I(), (C.c_double * cap)(), (C.c_longlong * cap)()
-        n = self.lib.s2vt_profile_shapes(self.h, cap, cls, M, N, K, ms, cnt)
-        return [(cls[i], M[i], N[i], K[i], ms[i], cnt[i]) for i in range(max(n, 0))]
+        by, ln = (C.c_double * cap)(), (C.c_longlong * cap)()
+        n = self.lib.s2vt_profile_shapes(self.h, cap, cls, M, N, K, ms, cnt, by, ln)
+        return [(cls[i], M[i], N[i], K[i], ms[i], cnt[i], by[i], ln[i]) for i in range(max(n, 0))]
 
     def profile_read(self):
         """-> {'batched': (ms, flops, launches), 'step': (...)} of the GEMM launches since the last read."""
