@@ -262,9 +262,34 @@ def run_b200(args):
 
     step_dev = lambda: trainer.step(feats_dev, vidx_dev)
 
-    def step_e2e():
-        out = trainer.step(feats_host, vidx_host)          # H2D of the step's features inside the step
+    def step_e2e_blocking():
+        out = trainer.step(feats_host, vidx_host)          # H2D of the step's features on the compute stream, inside the step
         return out.cpu()                                   # D2H of [grad norm, loss]
+
+    pipe = s2vt_b200.trainer.FeaturePipe(model.device, B, Tv, DIMS['D'])
+    res_host = torch.empty(2, 2, dtype=torch.float32).pin_memory()
+    res_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    results = []
+
+    def run_e2e(n):
+        """n steps through the public API with HOST feeds: every step's features + indices are copied from pinned memory
+        (staged one step ahead on the copy stream) and every step's [grad norm, loss] is read back (one step behind)."""
+        pipe.put(feats_host, vidx_host)
+        pending = None
+        for i in range(n):
+            if i + 1 < n:
+                pipe.put(feats_host, vidx_host)
+            v, vi, slot = pipe.get()
+            out = trainer.step(v, vi)
+            pipe.release(slot)
+            res_host[i % 2].copy_(out, non_blocking=True)
+            res_ev[i % 2].record()
+            if pending is not None:
+                res_ev[pending].synchronize()
+                results.append(res_host[pending].tolist())
+            pending = i % 2
+        res_ev[pending].synchronize()
+        results.append(res_host[pending].tolist())
 
     for _ in range(max(args.warmup, 3)):
         step_dev()
@@ -281,10 +306,12 @@ def run_b200(args):
             print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'videos/s', 'ms_per_step': ms / args.steps, 'gpu_launches': int(launches),
                               'quick': True}), flush=True)
         return
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(args.steps, step_e2e)
+    run_e2e(2)
+    ms_e2e = timed(1, lambda: run_e2e(args.steps))
     e2e = world * B * args.steps / (ms_e2e / 1e3)
+    for _ in range(2):
+        step_e2e_blocking()
+    ms_e2e_blk = timed(args.steps, step_e2e_blocking)
     # roofline pass: the same steps with CUDA-event brackets around every GEMM launch (separate from the timed region
     # above so the brackets do not perturb `value`)
     model.profile(True)
@@ -341,7 +368,9 @@ def run_b200(args):
            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic', 'config': workload_config(args, B, world),
            'clocks': clocks, 'e2e': {'value': e2e, 'unit': 'videos/s', 'h2d_bytes_per_step': int(feats_host.numel() * 4 + vidx_host.numel() * 4),
-                                     'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps},
+                                     'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps,
+                                     'mode': 'feed staged one step ahead on a copy stream (FeaturePipe), result read one step behind; every copy inside the timed region',
+                                     'blocking_feed_value': world * B * args.steps / (ms_e2e_blk / 1e3)},
            'gpu_launches': int(launches), 'loss': loss, 'decode': beam,
            'gemm_shapes': [{'class': 'batched' if c == 0 else 'step', 'M': M_, 'N': N_, 'K': K_, 'gemms_per_step': n_ / args.steps,
                             'launches_per_step': l_ / args.steps, 'us_per_gemm': 1e3 * ms_ / n_, 'ms_per_step': ms_ / args.steps}

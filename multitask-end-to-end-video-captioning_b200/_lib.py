@@ -62,6 +62,24 @@ SIGNATURES = {
     'ciderd_corpus_device_bytes': (_sz, [_vp]),
     'ciderd_corpus_serialize': (_i32, [_vp, _vp]),
     'ciderd_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    # include/s2vt_io.h (host only)
+    's2vt_io_last_error': (C.c_char_p, []),
+    's2vt_features_open': (_i32, [C.c_char_p, _i32, C.POINTER(_vp)]),
+    's2vt_features_open_memory': (_i32, [_vp, _sz, _i32, C.POINTER(_vp)]),
+    's2vt_features_close': (None, [_vp]),
+    's2vt_features_num_videos': (_i64, [_vp]),
+    's2vt_features_num_frames': (_i32, [_vp]),
+    's2vt_features_dim': (_i32, [_vp]),
+    's2vt_features_video_id': (C.c_char_p, [_vp, _i64]),
+    's2vt_features_find': (_i64, [_vp, C.c_char_p]),
+    's2vt_features_read': (_i32, [_vp, _vp, _i64, _vp, _i32]),
+    's2vt_ckpt_open': (_i32, [C.c_char_p, C.POINTER(_vp)]),
+    's2vt_ckpt_close': (None, [_vp]),
+    's2vt_ckpt_format': (_i32, [_vp]),
+    's2vt_ckpt_num_tensors': (_i32, [_vp]),
+    's2vt_ckpt_tensor_info': (_i32, [_vp, _i32, C.POINTER(C.c_char_p), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64 * 8)]),
+    's2vt_ckpt_find': (_i32, [_vp, C.c_char_p]),
+    's2vt_ckpt_read_f32': (_i32, [_vp, _i32, _vp, _i64]),
 }
 
 _lib = None
@@ -88,6 +106,13 @@ class S2vtError(RuntimeError):
     def __init__(self, code, msg):
         RuntimeError.__init__(self, 's2vt error %d: %s' % (code, msg))
         self.code = code
+
+
+def check_io(code):
+    """Return-code check for the host-only entry points of include/s2vt_io.h."""
+    if code != 0:
+        msg = load().s2vt_io_last_error()
+        raise S2vtError(code, msg.decode() if msg else '')
 
 
 def check(handle, code):

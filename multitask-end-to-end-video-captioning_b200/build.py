@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libs2vt_b200.so')
-SOURCES = ['s2vt_api.cu', 'ciderd.cu']
+SOURCES = ['s2vt_api.cu', 'ciderd.cu', 'ingest.cpp', 'tfckpt.cpp']      # .cpp: host-only C ABI of include/s2vt_io.h
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
 
@@ -21,7 +21,8 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 's2vt.h')]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith('.o')] + \
+        [os.path.join(HERE, '..', 'include', h) for h in ('s2vt.h', 's2vt_io.h')]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -35,8 +36,11 @@ def build(force=False, verbose=True):
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
-        obj = os.path.join(CSRC, src.replace('.cu', '.o'))
-        cmd = [_nvcc()] + NVCC_FLAGS + ['-c', path, '-o', obj]
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + '.o')
+        if src.endswith('.cu'):
+            cmd = [_nvcc()] + NVCC_FLAGS + ['-c', path, '-o', obj]
+        else:
+            cmd = [os.environ.get('CXX', 'g++'), '-O3', '-std=c++17', '-fPIC', '-pthread', '-Wall', '-c', path, '-o', obj]
         if verbose:
             print(' '.join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -45,7 +49,7 @@ def build(force=False, verbose=True):
         out, _ = p.communicate()
         if p.returncode != 0:
             sys.stderr.write(out.decode())
-            raise RuntimeError('nvcc failed on %s' % src)
+            raise RuntimeError('compiler failed on %s' % src)
         elif verbose and out.strip():
             print(out.decode())
     cmd = [_nvcc(), '-shared', '-o', LIB] + objs

@@ -37,18 +37,25 @@ def read_sentences(sent_file):
     return np.array(rows, dtype=object)
 
 
-def read_features(feature_file, dtype=np.float32):
+def read_features(feature_file, dtype=np.float32, n_threads=0):
     """The feature half (tf_s2vt.py:332-342): lines 'vid<id>_frame_<k>,f_1,...,f_D' grouped by the text before the first
-    '_'; every video must have the same number of frames (the reference asserts it).  Returns {vid: float32 [T_v, D]}."""
-    frames = {}
-    with _open(feature_file) as f:
-        for line in f:
-            head, _, rest = line.partition(',')
-            frames.setdefault(head.split('_')[0], []).append(np.array(rest.split(','), dtype=dtype))
-    feats = {v: np.stack(rows) for v, rows in frames.items()}
-    lengths = {a.shape[0] for a in feats.values()}
-    assert len(lengths) == 1, 'videos have different frame counts: %s' % sorted(lengths)
-    return feats
+    '_'; every video must have the same number of frames (the reference asserts it).  Returns {vid: float32 [T_v, D]},
+    parsed by the native multi-threaded reader (ingest.FeatureFile; `ingest.FeatureFile(path)` itself gives lazy
+    per-batch parsing into pinned memory)."""
+    from . import _lib, ingest
+    try:
+        ff = ingest.FeatureFile(feature_file, n_threads)
+    except _lib.S2vtError as e:
+        if 'frame counts' in str(e):
+            raise AssertionError(str(e))
+        raise ValueError(str(e))
+    try:
+        feats = ff.to_dict()
+    except _lib.S2vtError as e:
+        raise ValueError(str(e))
+    finally:
+        ff.close()
+    return feats if dtype == np.float32 else {v: a.astype(dtype) for v, a in feats.items()}
 
 
 def get_video_feature_caption_pair(sent_file, feature_file):

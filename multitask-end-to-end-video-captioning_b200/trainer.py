@@ -39,6 +39,58 @@ def allreduce_gradients(model, bucket_bytes=32 << 20):
         w.wait()
 
 
+class FeaturePipe(object):
+    """Double-buffered staging of the per-step feed (features [B, T_v, D] fp32 and the corpus index of each video) from
+    pinned host memory, on its own copy stream, so the copy of step i+1 runs under the kernels of step i.  The
+    reference feeds through feed_dict, i.e. a blocking copy before every sess.run (:823-826).
+
+        pipe.put(host_features, host_index)       # enqueue the copy of a future step (at most 2 outstanding)
+        v, vi, slot = pipe.get()                  # device tensors of the oldest staged step, ordered after its copy
+        ... launch the step ...
+        pipe.release(slot)                        # the step's kernels have been enqueued; the slot may be refilled
+    """
+
+    def __init__(self, device, batch, n_frames, dim_image, depth=2):
+        self.device = torch.device(device)
+        self.bufs = [(torch.empty(batch, n_frames, dim_image, dtype=torch.float32, device=self.device),
+                      torch.empty(batch, dtype=torch.int32, device=self.device)) for _ in range(depth)]
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [None] * depth
+        self.rows = [0] * depth
+        self.n_put = self.n_get = 0
+
+    def put(self, features, video_index):
+        i = self.n_put % len(self.bufs)
+        if self.n_put - self.n_get >= len(self.bufs):
+            raise RuntimeError('FeaturePipe: every slot holds a staged step; get() one first')
+        f = features if torch.is_tensor(features) else torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+        vi = video_index if torch.is_tensor(video_index) else torch.from_numpy(np.ascontiguousarray(video_index, dtype=np.int32))
+        v, x = self.bufs[i]
+        if self.free[i] is not None:
+            self.stream.wait_event(self.free[i])       # kernels of the step that last read this slot
+        with torch.cuda.stream(self.stream):
+            v[:f.shape[0]].copy_(f, non_blocking=True)
+            x[:vi.shape[0]].copy_(vi, non_blocking=True)
+            self.ready[i].record(self.stream)
+        self.rows[i] = f.shape[0]
+        self.n_put += 1
+
+    def get(self):
+        if self.n_get >= self.n_put:
+            raise RuntimeError('FeaturePipe: nothing staged')
+        i = self.n_get % len(self.bufs)
+        torch.cuda.current_stream(self.device).wait_event(self.ready[i])
+        self.n_get += 1
+        v, x = self.bufs[i]
+        return v[:self.rows[i]], x[:self.rows[i]], i
+
+    def release(self, slot):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[slot] = ev
+
+
 class ReinforceTrainer(object):
     """Stage-2 trainer (K-sample REINFORCE with CIDEr-D reward and greedy baseline).
 

@@ -122,3 +122,23 @@ def decode_captions_masks(captions, idx_to_word):
 def get_captions(captions, vid):
     """reinforcement_multisampling_tf_s2vt.py:600-601: all sentences of one video id (linear scan)."""
     return [y for x, y in captions if x == vid]
+
+
+def read_features(path):
+    """tf_s2vt.py:332-342 + the float32 feed of :487-497: group the lines 'vid<id>_frame_<k>,f_1,...,f_D' by the text
+    before the first '_', keep the STRING fields like the reference does, and convert them the way the feed does
+    (np.asarray(list of str lists, dtype=float32)).  -> ({vid: float32 [T_v, D]}, video order of first appearance)."""
+    import gzip
+    import numpy as np
+    op = gzip.open if str(path).endswith('.gz') else open
+    features = {}
+    with op(path, 'rt', newline='\n') as f:
+        for line in f:
+            splits = line.split(',')
+            video_id = splits[0].split('_')[0]
+            if video_id not in features:
+                features[video_id] = []
+            features[video_id].append(splits[1:])
+    feature_length = [len(v) for v in features.values()]
+    assert len(set(feature_length)) == 1
+    return {v: np.asarray(rows, dtype=np.float32) for v, rows in features.items()}, list(features)

@@ -1,4 +1,4 @@
-"""CPU checks of the C-ABI boundary: the library builds/loads, exports every symbol include/s2vt.h declares, and the
+"""CPU checks of the C-ABI boundary: the library builds/loads, exports every symbol include/*.h declares, and the
 host-only entry points (create / sizing / variable table) behave.  No compute is launched."""
 import ctypes as C
 import os
@@ -18,7 +18,10 @@ def lib():
 
 
 def declared_functions():
-    src = open(os.path.join(ROOT, 'include', 's2vt.h')).read()
+    src = ''
+    for h in sorted(os.listdir(os.path.join(ROOT, 'include'))):
+        if h.endswith('.h'):
+            src += open(os.path.join(ROOT, 'include', h)).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     names = re.findall(r'\b((?:s2vt|ciderd)_[a-z0-9_]+)\s*\(', src)
     return sorted(set(names))
