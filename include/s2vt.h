@@ -191,6 +191,24 @@ int ciderd_corpus_serialize(const ciderd_corpus* c, void* host_buffer);
 int ciderd_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, double* scores_out,
                  unsigned long long* counts_out, s2vt_stream st);
 
+/* ---- BLEU-4 / ROUGE-L rewards: the evaluate_captions_cider (sic) of bleu_evaluation.py:60-87 (Bleu(4).compute_score,
+ * reward = per-sentence scores[3]) and rouge_evaluation.py:60-87 (Rouge().compute_score per-sentence scores), used by
+ * bleu4_/rouge_reinforcement_multisampling_tf_s2vt.py:792-808.  pycocoevalcap arithmetic: BleuScorer(n=4) with
+ * option='closest', tiny 1e-15 / small 1e-9 smoothing and brevity penalty; Rouge with beta = 1.2 over LCS.
+ * Same token / key conventions as the CIDEr-D corpus; one corpus serves both scores. */
+typedef struct s2vt_reward_corpus s2vt_reward_corpus;
+int s2vt_reward_corpus_create(const int32_t* ref_tokens, const int64_t* ref_offsets, int64_t n_refs, const int64_t* video_ref_offsets,
+                              int64_t n_videos, s2vt_reward_corpus** out);
+void s2vt_reward_corpus_destroy(s2vt_reward_corpus* c);
+size_t s2vt_reward_corpus_device_bytes(const s2vt_reward_corpus* c);
+int s2vt_reward_corpus_serialize(const s2vt_reward_corpus* c, void* host_buffer);
+/* hyp int32 [N, T_c] (words before the first 0), video_of_row int32 [N]; bleu_out float64 [N, 4] = BLEU_1..BLEU_4. */
+int s2vt_bleu_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, double* bleu_out, s2vt_stream st);
+/* rouge_out float64 [N].  empty_token: the id the caller gave the empty word ''.split(" ") yields (an empty
+ * hypothesis is ONE empty token in the reference's Rouge); any id no reference uses if references hold no empty words. */
+int s2vt_rouge_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, int32_t empty_token,
+                     double* rouge_out, s2vt_stream st);
+
 #ifdef __cplusplus
 }
 #endif

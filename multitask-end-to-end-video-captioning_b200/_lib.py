@@ -62,6 +62,12 @@ SIGNATURES = {
     'ciderd_corpus_device_bytes': (_sz, [_vp]),
     'ciderd_corpus_serialize': (_i32, [_vp, _vp]),
     'ciderd_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    's2vt_reward_corpus_create': (_i32, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_vp)]),
+    's2vt_reward_corpus_destroy': (None, [_vp]),
+    's2vt_reward_corpus_device_bytes': (_sz, [_vp]),
+    's2vt_reward_corpus_serialize': (_i32, [_vp, _vp]),
+    's2vt_bleu_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    's2vt_rouge_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     # include/s2vt_io.h (host only)
     's2vt_io_last_error': (C.c_char_p, []),
     's2vt_features_open': (_i32, [C.c_char_p, _i32, C.POINTER(_vp)]),

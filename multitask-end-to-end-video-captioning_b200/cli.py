@@ -25,7 +25,8 @@ def build_parser(description, defaults):
              vocabulary_file='msvd_vocabulary1.txt', model_path='models', model_name='s2vt_model', restore=None, out_file='captions.txt',
              dim_image=1536, lstm_dim=1000, word_dim=500, n_video_lstm_step=5, n_caption_lstm_step=35, n_epochs=30, batch_size=64,
              start_learning_rate=1e-3, decay_steps=5000, clip_norm=10.0, dropout_rate=0.9, decay_value=5e-5, seed_num=4,
-             n_samples=8, beam_size=3, length_normalization_factor=0.0, alpha=0.5, precision='bf16', max_iters=0)
+             n_samples=8, beam_size=3, length_normalization_factor=0.0, alpha=0.5, precision='bf16', max_iters=0,
+             reward='cider')      # reward: cider (cider_evaluation.py) | bleu4 (bleu_evaluation.py) | rouge (rouge_evaluation.py)
     d.update({k: v for k, v in defaults.items() if k != 'task'})
     for k, v in d.items():
         ap.add_argument('--' + k, type=(type(v) if v is not None else str), default=v)
@@ -108,7 +109,7 @@ def run_rl(args):
     train_captions, train_features = pkg.text.get_video_feature_caption_pair(args.video_train_sent_file, args.video_train_feature_file)
     by, order = pkg.text.group_by_video(train_captions)
     vindex = {v: i for i, v in enumerate(order)}
-    scorer = pkg.cider.CiderD([by[v] for v in order], wordtoix)                        # CiderD(df=<train corpus>), cider_evaluation.py:12
+    scorer = pkg.rewards.make_scorer(args.reward, [by[v] for v in order], wordtoix)   # CiderD(df=<train corpus>), cider_evaluation.py:12
     trainer = pkg.trainer.ReinforceTrainer(model, scorer, n_samples=args.n_samples, start_learning_rate=args.start_learning_rate,
                                            decay_steps=args.decay_steps, clip_norm=args.clip_norm, seed=args.seed_num)
     it = 0
