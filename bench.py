@@ -331,6 +331,24 @@ def run_b200(args):
         gr_ms = timed(3, lambda: model.greedy(feats_dev))
         beam = {'beam5_captions_per_s': 3 * B / (bs_ms / 1e3), 'beam5_ms_per_batch': bs_ms / 3, 'greedy_captions_per_s': 3 * B / (gr_ms / 1e3),
                 'batch': B, 'T_v': Tv, 'beam_size': 5, 'length_normalization_factor': 1.0}
+        # BASELINE config 3: temporal-attention decoder (original_attention.py) greedy decode on MSR-VTT-shaped [B, 32, 1536] features
+        att = s2vt_b200.attention.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], dim_hidden=DIMS['H'], batch_size=B, n_video_lstm_steps=32,
+                                                          n_caption_lstm_steps=35, drop_out_rate=1.0, precision=args.precision)
+        feats32 = torch.from_numpy(features(B, 32, 4321)).cuda()
+        for _ in range(2):
+            att.build_generator(feats32)
+        at_ms = timed(3, lambda: att.build_generator(feats32))
+        beam.update({'attention_greedy_captions_per_s': 3 * B / (at_ms / 1e3), 'attention_ms_per_batch': at_ms / 3, 'attention_frames': 32})
+        del att
+        # reward kernels on the rollout's [K*B, 35] id matrix (CIDEr-D is the one inside the timed step; BLEU-4 / ROUGE-L are the
+        # rewards of bleu4_/rouge_reinforcement_multisampling_tf_s2vt.py)
+        ids = trainer.last['samples']
+        rows = vidx_dev.repeat(K)
+        rw = {}
+        for name, sc in (('ciderd', scorer), ('bleu4', s2vt_b200.rewards.Bleu4([by[v] for v in order], w2i)), ('rouge_l', s2vt_b200.rewards.RougeL([by[v] for v in order], w2i))):
+            sc.score_ids(ids, rows)
+            rw[name + '_us_per_%d_hyps' % ids.shape[0]] = 1e3 * timed(20, lambda: sc.score_ids(ids, rows)) / 20
+        beam['reward_kernels'] = rw
     if rank != 0:
         return
     peaks = {}

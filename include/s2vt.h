@@ -209,6 +209,46 @@ int s2vt_bleu_score(const void* corpus_device, const int32_t* hyp, const int32_t
 int s2vt_rouge_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, int32_t empty_token,
                      double* rouge_out, s2vt_stream st);
 
+/* ---- temporal-attention decoder (BASELINE config 3): class Video_Caption_Generator of
+ * original_attention.py:54-251 -- frame projection, additive attention over the n frame embeddings, one LSTM3, tanh MLP head.
+ * A separate handle with the same conventions as s2vt_handle (caller-owned state / workspace, explicit stream, codes).
+ * Variables by TF name: Wemb [V,H], encode_image_W [D,H], encode_image_b, embed_att_w [H,1], embed_att_Wa, embed_att_Ua,
+ * embed_att_ba, embed_word_W [H,V], embed_word_b, embed_nn_Wp [3H,H], embed_nn_bp, s2vt/LSTM3/basic_lstm_cell/{weights
+ * [3H,4H], biases}.  Built so far: the greedy sampler and the teacher-forced loss (forward); the backward pass is not. */
+typedef struct s2vt_att_handle s2vt_att_handle;
+typedef struct s2vt_att_config {
+    int32_t dim_image;        /* 1536 (:296) */
+    int32_t dim_hidden;       /* 1000 (:297): LSTM3 width = word embedding width = attention width */
+    int32_t n_words;
+    int32_t n_video_steps;    /* n frames attended over (5 / 32), <= 128 */
+    int32_t n_caption_steps;  /* 35 */
+    int32_t precision;        /* S2VT_PREC_BF16 | S2VT_PREC_FP32 */
+    float dropout_keep;       /* DropoutWrapper(output_keep_prob) of build_model: 0.9 (:417) */
+    float hinge_beta;         /* beta = 10 (:300) */
+    float hinge_m;            /* m = 0.5 (:299) */
+    int32_t reg_frames;       /* alphas_1 = temp_alphas[:, 0:8] (:123) */
+} s2vt_att_config;
+int s2vt_att_create(const s2vt_att_config* cfg, s2vt_att_handle** out);
+void s2vt_att_destroy(s2vt_att_handle* h);
+const char* s2vt_att_last_error(const s2vt_att_handle* h);
+size_t s2vt_att_num_params(const s2vt_att_handle* h);
+size_t s2vt_att_state_bytes(const s2vt_att_handle* h);
+size_t s2vt_att_workspace_bytes(const s2vt_att_handle* h, int n_videos, int n_rows);
+int s2vt_att_bind(s2vt_att_handle* h, void* state, size_t state_bytes, void* workspace, size_t workspace_bytes);
+float* s2vt_att_params(const s2vt_att_handle* h);
+int s2vt_att_num_variables(const s2vt_att_handle* h);
+int s2vt_att_variable_info(const s2vt_att_handle* h, int index, const char** tf_name, int64_t* offset, int64_t shape[2], int* ndim);
+int s2vt_att_load_param(s2vt_att_handle* h, const char* tf_name, const float* src_host, const int64_t* shape, int ndim, s2vt_stream st);
+int s2vt_att_refresh(s2vt_att_handle* h, s2vt_stream st);
+/* build_generator (:155-199) / build_sampler (:201-251): video [B, n, D] fp32 -> ids int32 [B, T_c] (arg-max words, no early
+ * stop) and, if alphas_out != NULL, saved_alphas float32 [T_c, n, B]. */
+int s2vt_att_greedy(s2vt_att_handle* h, const float* video, int B, int32_t* ids_out, float* alphas_out, s2vt_stream st);
+/* build_model (:88-152) forward: captions int32 [B, T_c], mask fp32 [B, T_c] -> loss_out[0] = loss, loss_out[1] = its
+ * regulariser part; logits_out (nullable) fp32 [T_c, B, V].  Dropout stream as in s2vt.h (drop_seed 0 = keep everything). */
+int s2vt_att_xe_loss(s2vt_att_handle* h, const float* video, int B, const int32_t* captions, const float* mask, uint64_t drop_seed, uint32_t row_base,
+                     float* loss_out, float* logits_out, s2vt_stream st);
+long long s2vt_att_launch_count(const s2vt_att_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,4 +6,4 @@ the C ABI of include/s2vt.h); there is no CPU fallback.
 """
 from . import _lib  # noqa: F401
 from .model import Video_Caption_Generator, LSTM1_W, LSTM1_B, LSTM2_W, LSTM2_B  # noqa: F401
-from . import text, cider, rewards, trainer, checkpoint, cli, ingest  # noqa: F401,E402
+from . import text, cider, rewards, trainer, checkpoint, cli, ingest, attention  # noqa: F401,E402

@@ -16,6 +16,12 @@ class S2vtConfig(C.Structure):
                 ('precision', C.c_int32), ('gemm_backend', C.c_int32), ('dropout_keep', C.c_float)]
 
 
+class S2vtAttConfig(C.Structure):
+    _fields_ = [('dim_image', C.c_int32), ('dim_hidden', C.c_int32), ('n_words', C.c_int32), ('n_video_steps', C.c_int32),
+                ('n_caption_steps', C.c_int32), ('precision', C.c_int32), ('dropout_keep', C.c_float), ('hinge_beta', C.c_float),
+                ('hinge_m', C.c_float), ('reg_frames', C.c_int32)]
+
+
 PREC_BF16, PREC_FP32 = 0, 1
 GEMM_AUTO, GEMM_MMA_SYNC, GEMM_TCGEN05 = 0, 1, 2
 S2VT_OK, S2VT_EINVAL, S2VT_ENOTFOUND, S2VT_ESHAPE, S2VT_ECUDA, S2VT_ENOSPACE, S2VT_ESTATE = 0, -1, -2, -3, -4, -5, -6
@@ -68,6 +74,21 @@ SIGNATURES = {
     's2vt_reward_corpus_serialize': (_i32, [_vp, _vp]),
     's2vt_bleu_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     's2vt_rouge_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    's2vt_att_create': (_i32, [C.POINTER(S2vtAttConfig), C.POINTER(_vp)]),
+    's2vt_att_destroy': (None, [_vp]),
+    's2vt_att_last_error': (C.c_char_p, [_vp]),
+    's2vt_att_num_params': (_sz, [_vp]),
+    's2vt_att_state_bytes': (_sz, [_vp]),
+    's2vt_att_workspace_bytes': (_sz, [_vp, _i32, _i32]),
+    's2vt_att_bind': (_i32, [_vp, _vp, _sz, _vp, _sz]),
+    's2vt_att_params': (_vp, [_vp]),
+    's2vt_att_num_variables': (_i32, [_vp]),
+    's2vt_att_variable_info': (_i32, [_vp, _i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.POINTER(_i64 * 2), C.POINTER(_i32)]),
+    's2vt_att_load_param': (_i32, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i32, _vp]),
+    's2vt_att_refresh': (_i32, [_vp, _vp]),
+    's2vt_att_greedy': (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
+    's2vt_att_xe_loss': (_i32, [_vp, _vp, _i32, _vp, _vp, _u64, _u32, _vp, _vp, _vp]),
+    's2vt_att_launch_count': (C.c_longlong, [_vp]),
     # include/s2vt_io.h (host only)
     's2vt_io_last_error': (C.c_char_p, []),
     's2vt_features_open': (_i32, [C.c_char_p, _i32, C.POINTER(_vp)]),

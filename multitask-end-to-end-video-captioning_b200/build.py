@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libs2vt_b200.so')
-SOURCES = ['s2vt_api.cu', 'ciderd.cu', 'rewards.cu', 'ingest.cpp', 'tfckpt.cpp']      # .cpp: host-only C ABI of include/s2vt_io.h
+SOURCES = ['s2vt_api.cu', 'ciderd.cu', 'rewards.cu', 'attention.cu', 'ingest.cpp', 'tfckpt.cpp']      # .cpp: host-only C ABI of include/s2vt_io.h
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
 

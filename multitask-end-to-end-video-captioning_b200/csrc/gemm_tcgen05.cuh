@@ -19,7 +19,7 @@ namespace tc {
 
 // Debug probe (s2vt_debug_probe): when set, CTA (0,0) of every tcgen05 GEMM launch records %globaltimer at its phase
 // boundaries into slot [launch*8 .. launch*8+7] of the buffer (slot 0 of the buffer is the launch counter).
-__device__ unsigned long long* g_probe = nullptr;
+static __device__ unsigned long long* g_probe = nullptr;   // static: one copy per translation unit (s2vt_debug_probe arms the S2VT engine's)
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 constexpr int BM = 128, BK = 64, NTHREADS = 192;   // NTHREADS: staged-epilogue kernels (2 role warps + 4 epilogue warps)

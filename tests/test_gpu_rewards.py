@@ -106,3 +106,13 @@ def test_reinforce_trainer_accepts_the_alternative_rewards(msvd):
         assert np.isfinite(out.cpu().numpy()).all()
         r = tr.last['rewards'].cpu().numpy()
         assert r.shape == (8,) and (r >= 0).all() and (r <= 1.0 + 1e-6).all()
+
+
+def test_rewards_match_committed_golden(msvd):
+    by, vids, w2i, i2w, bleu, rouge = msvd
+    g = np.load(os.path.join(G, 'next_rows_golden.npz'))
+    vidx = {v: i for i, v in enumerate(vids)}
+    hyps = [str(h) for h in g['reward_hyps']]
+    rows = np.array([vidx[str(v)] for v in g['reward_vids']], dtype=np.int32)
+    np.testing.assert_allclose(bleu.score_strings(hyps, rows).cpu().numpy(), g['bleu'][:, 3], rtol=1e-12)
+    np.testing.assert_allclose(rouge.score_strings(hyps, rows).cpu().numpy(), g['rouge'], rtol=0, atol=1e-15)
