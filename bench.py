@@ -210,7 +210,17 @@ def workload_config(args, videos_per_gpu, world):
 # ------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner from C), so the process's
+    fd 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, 'w')
+
+
 def run_b200(args):
+    out_stream = _claim_stdout()
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -304,7 +314,7 @@ def run_b200(args):
     if args.quick:
         if rank == 0:
             print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'videos/s', 'ms_per_step': ms / args.steps, 'gpu_launches': int(launches),
-                              'quick': True}), flush=True)
+                              'quick': True}), file=out_stream, flush=True)
         return
     run_e2e(2)
     ms_e2e = timed(1, lambda: run_e2e(args.steps))
@@ -408,7 +418,7 @@ def run_b200(args):
         t0 = time.perf_counter(); o.step(); dt = time.perf_counter() - t0
         out['cpu_baseline'] = {'value': args.ref_videos / dt, 'unit': 'videos/s', 'cores': cpu_threads(), 'kind': 'port',
                                'sample': '1 full iteration (after 1 warm-up) on %d videos x K=%d, T_v=%d, fp32 NumPy/OpenBLAS oracle' % (args.ref_videos, K, Tv)}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -202,8 +202,11 @@ int s2vt_reward_corpus_create(const int32_t* ref_tokens, const int64_t* ref_offs
 void s2vt_reward_corpus_destroy(s2vt_reward_corpus* c);
 size_t s2vt_reward_corpus_device_bytes(const s2vt_reward_corpus* c);
 int s2vt_reward_corpus_serialize(const s2vt_reward_corpus* c, void* host_buffer);
-/* hyp int32 [N, T_c] (words before the first 0), video_of_row int32 [N]; bleu_out float64 [N, 4] = BLEU_1..BLEU_4. */
-int s2vt_bleu_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, double* bleu_out, s2vt_stream st);
+/* hyp int32 [N, T_c] (words before the first 0), video_of_row int32 [N]; bleu_out float64 [N, 4] = BLEU_1..BLEU_4.
+ * comps_out (nullable) int32 [N, 10] = cook_test's {correct[4], guess[4], testlen, closest reflen}: their sums over a test set
+ * give the corpus-level BLEU of score_all (bleu_evaluation.py:14-30). */
+int s2vt_bleu_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, double* bleu_out, int32_t* comps_out,
+                    s2vt_stream st);
 /* rouge_out float64 [N].  empty_token: the id the caller gave the empty word ''.split(" ") yields (an empty
  * hypothesis is ONE empty token in the reference's Rouge); any id no reference uses if references hold no empty words. */
 int s2vt_rouge_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, int32_t empty_token,

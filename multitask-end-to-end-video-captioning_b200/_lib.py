@@ -72,7 +72,7 @@ SIGNATURES = {
     's2vt_reward_corpus_destroy': (None, [_vp]),
     's2vt_reward_corpus_device_bytes': (_sz, [_vp]),
     's2vt_reward_corpus_serialize': (_i32, [_vp, _vp]),
-    's2vt_bleu_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    's2vt_bleu_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     's2vt_rouge_score': (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     's2vt_att_create': (_i32, [C.POINTER(S2vtAttConfig), C.POINTER(_vp)]),
     's2vt_att_destroy': (None, [_vp]),

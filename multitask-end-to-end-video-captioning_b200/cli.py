@@ -198,9 +198,10 @@ def _decode_task(args, pkg, model, wordtoix, ixtoword, beam):
             f.write(v + '\t' + hyps[v] + '\n')
     if args.task == 'evaluate':
         keep = [v for v in vids if v in by]
-        scorer = pkg.cider.CiderD([by[v] for v in keep], wordtoix)
-        score = float(scorer.score_strings([hyps[v] for v in keep], np.arange(len(keep), dtype=np.int32)).mean().item())
-        print(json.dumps({'CIDEr-D': score, 'videos': len(keep)}))
+        # evaluate_for_particular_captions / score_all (cider_evaluation.py:14-58): corpus BLEU, ROUGE_L, CIDEr on the GPU scorers
+        metrics = pkg.rewards.evaluate_for_particular_captions({v: [hyps[v]] for v in keep}, {v: by[v] for v in keep}, wordtoix)
+        score = metrics['CIDEr']
+        print(json.dumps(dict(metrics, **{'CIDEr-D': score, 'videos': len(keep)})))
         return score
     return hyps
 

@@ -86,7 +86,7 @@ extern "C" int s2vt_reward_corpus_serialize(const s2vt_reward_corpus* c, void* h
 
 // ---- BLEU: BleuScorer.compute_score(option='closest') per-sentence list ----------------------------------------------
 __global__ void __launch_bounds__(128) bleu_score_kernel(const char* __restrict__ corpus, const int* __restrict__ hyp, const int* __restrict__ video_of_row,
-                                                         int Tc, double* __restrict__ bleu_out) {
+                                                         int Tc, double* __restrict__ bleu_out, int* __restrict__ comps_out) {
     const RewardHeader* hd = reinterpret_cast<const RewardHeader*>(corpus);
     const long long* video_ref = reinterpret_cast<const long long*>(corpus + hd->off_video_ref);
     const long long* ref_tok = reinterpret_cast<const long long*>(corpus + hd->off_ref_tok);
@@ -148,6 +148,11 @@ __global__ void __launch_bounds__(128) bleu_score_kernel(const char* __restrict_
         const double tiny = 1e-15, small = 1e-9;
         const double ratio = ((double)testlen + tiny) / ((double)reflen + small);
         const double bp = ratio < 1.0 ? exp(1.0 - 1.0 / ratio) : 1.0;
+        if (comps_out) {   // cook_test components: the corpus-level score sums them over the sentences (BleuScorer.compute_score totalcomps)
+            int* co = comps_out + (size_t)row * 10;
+            for (int k = 0; k < RW_N; ++k) { co[k] = correct[k]; co[4 + k] = testlen - k > 0 ? testlen - k : 0; }
+            co[8] = testlen; co[9] = (int)reflen;
+        }
         double bleu = 1.0;
         for (int k = 0; k < RW_N; ++k) {
             const int guess = testlen - k > 0 ? testlen - k : 0;
@@ -206,9 +211,10 @@ __global__ void __launch_bounds__(128) rouge_score_kernel(const char* __restrict
     }
 }
 
-extern "C" int s2vt_bleu_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, double* bleu_out, s2vt_stream st) {
+extern "C" int s2vt_bleu_score(const void* corpus_device, const int32_t* hyp, const int32_t* video_of_row, int N, int Tc, double* bleu_out, int32_t* comps_out,
+                               s2vt_stream st) {
     if (!corpus_device || !hyp || !video_of_row || !bleu_out || N <= 0 || Tc <= 0 || Tc > RW_MAXTOK) return S2VT_EINVAL;
-    bleu_score_kernel<<<N, 128, 0, (cudaStream_t)st>>>((const char*)corpus_device, hyp, video_of_row, Tc, bleu_out);
+    bleu_score_kernel<<<N, 128, 0, (cudaStream_t)st>>>((const char*)corpus_device, hyp, video_of_row, Tc, bleu_out, comps_out);
     return cudaGetLastError() == cudaSuccess ? S2VT_OK : S2VT_ECUDA;
 }
 

@@ -105,16 +105,37 @@ class Bleu4(_ReferenceScorer):
     """Bleu(4).compute_score(refe, hypo)[1][3]: per-sentence BLEU-4 ('closest' reference length)."""
     SPLIT = None
 
-    def score_all_orders(self, hyp_ids, video_of_row):
+    def score_all_orders(self, hyp_ids, video_of_row, want_comps=False):
         hyp = hyp_ids.to(self.device, torch.int32).contiguous()
         vid = torch.as_tensor(video_of_row).to(self.device, torch.int32).contiguous()
         N, Tc = hyp.shape
         out = torch.empty(N, 4, dtype=torch.float64, device=self.device)
+        comps = torch.empty(N, 10, dtype=torch.int32, device=self.device) if want_comps else None
         rc = self.lib.s2vt_bleu_score(C.c_void_p(self.table.data_ptr()), C.c_void_p(hyp.data_ptr()), C.c_void_p(vid.data_ptr()), N, Tc,
-                                      C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                      C.c_void_p(out.data_ptr()), C.c_void_p(comps.data_ptr()) if want_comps else None,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc != 0:
             raise _lib.S2vtError(rc, 's2vt_bleu_score failed')
-        return out
+        return (out, comps) if want_comps else out
+
+    def corpus_bleu(self, cands, video_of_row):
+        """Bleu(4).compute_score(ref, hypo)[0]: corpus-level [Bleu_1 .. Bleu_4] (totals of the per-sentence components)."""
+        rows = [self._ids(c) for c in cands]
+        L = max([len(r) for r in rows] + [1]) + 1
+        ids = np.zeros((len(rows), L), dtype=np.int32)
+        for i, r in enumerate(rows):
+            ids[i, :len(r)] = r
+        _, comps = self.score_all_orders(torch.from_numpy(ids), video_of_row, want_comps=True)
+        tot = comps.to(torch.int64).sum(0).cpu().numpy()
+        tiny, small = 1e-15, 1e-9
+        bleus, bleu = [], 1.0
+        for k in range(4):
+            bleu *= float(tot[k] + tiny) / (tot[4 + k] + small)
+            bleus.append(bleu ** (1.0 / (k + 1)))
+        ratio = (tot[8] + tiny) / (tot[9] + small)
+        if ratio < 1:
+            bleus = [b * float(np.exp(1 - 1 / ratio)) for b in bleus]
+        return bleus
 
     def _launch(self, hyp, vid, N, Tc, st):
         return self.score_all_orders(hyp, vid)[:, 3].contiguous()
@@ -144,3 +165,22 @@ def make_scorer(kind, ref_sets, wordtoix, device=None):
     if kind in ('rouge', 'rouge_l', 'rouge-l', 'rougel'):
         return RougeL(ref_sets, wordtoix, device=device)
     raise ValueError('unknown reward %r' % kind)
+
+
+def evaluate_for_particular_captions(cand, ref_captions, wordtoix, device=None):
+    """cider_evaluation.evaluate_for_particular_captions / score_all (cider_evaluation.py:14-58): cand {key: [caption]},
+    ref_captions {key: [references]} -> {'Bleu_1'..'Bleu_4' (corpus level), 'ROUGE_L' (mean), 'CIDEr'}.  coco-caption's Cider
+    is the clipped, length-penalised CIDEr-D with document frequencies taken from the scored reference sets, i.e. cider.CiderD
+    built on these references.  METEOR needs the external Java scorer and is not computed."""
+    from . import cider
+    keys = [k for k in cand]
+    ref_sets = [list(ref_captions[k]) for k in keys]
+    hyps = [cand[k][0] if isinstance(cand[k], (list, tuple)) else cand[k] for k in keys]
+    rows = np.arange(len(keys), dtype=np.int32)
+    out = {}
+    b = Bleu4(ref_sets, wordtoix, device=device)
+    for m, s in zip(('Bleu_1', 'Bleu_2', 'Bleu_3', 'Bleu_4'), b.corpus_bleu(hyps, rows)):
+        out[m] = float(s)
+    out['ROUGE_L'] = float(RougeL(ref_sets, wordtoix, device=device).score_strings(hyps, rows).mean().item())
+    out['CIDEr'] = float(cider.CiderD(ref_sets, wordtoix, device=device).score_strings(hyps, rows).mean().item())
+    return out

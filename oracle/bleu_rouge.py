@@ -76,6 +76,27 @@ def bleu_all_orders(ref, cand):
     return np.array([sentence_bleu(c, ref[i]) for i, c in enumerate(cand)], dtype=np.float64)
 
 
+def corpus_bleu(ref, cand, n=4):
+    """BleuScorer.compute_score(option='closest')[0] -- the corpus-level [Bleu_1..Bleu_n] of score_all
+    (cider_evaluation.py:14-30): per-sentence components summed, then the same smoothed product and brevity penalty."""
+    tot_c, tot_g, testlen, reflen = [0] * n, [0] * n, 0, 0
+    for i, c in enumerate(cand):
+        comps = cook_test(c, cook_refs(ref[i], n), n)
+        testlen += comps['testlen']
+        reflen += min((abs(l - comps['testlen']), l) for l in comps['reflen'])[1]
+        for k in range(n):
+            tot_c[k] += comps['correct'][k]
+            tot_g[k] += comps['guess'][k]
+    bleus, bleu = [], 1.0
+    for k in range(n):
+        bleu *= float(tot_c[k] + TINY) / (tot_g[k] + SMALL)
+        bleus.append(bleu ** (1.0 / (k + 1)))
+    ratio = (testlen + TINY) / (reflen + SMALL)
+    if ratio < 1:
+        bleus = [b * math.exp(1 - 1 / ratio) for b in bleus]
+    return bleus
+
+
 # ---- ROUGE-L ---------------------------------------------------------------------------------------------------------
 def my_lcs(string, sub):
     """rouge.my_lcs: length of the longest common subsequence of two token lists (dynamic programme)."""

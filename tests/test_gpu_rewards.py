@@ -116,3 +116,24 @@ def test_rewards_match_committed_golden(msvd):
     rows = np.array([vidx[str(v)] for v in g['reward_vids']], dtype=np.int32)
     np.testing.assert_allclose(bleu.score_strings(hyps, rows).cpu().numpy(), g['bleu'][:, 3], rtol=1e-12)
     np.testing.assert_allclose(rouge.score_strings(hyps, rows).cpu().numpy(), g['rouge'], rtol=0, atol=1e-15)
+
+
+def test_full_metric_evaluator_matches_oracle(msvd):
+    """score_all (cider_evaluation.py:14-30) on 40 videos: corpus BLEU_1..4, mean ROUGE_L, CIDEr with df from the scored refs."""
+    import s2vt_b200
+    from oracle import ciderd as ocider
+    by, vids, w2i, i2w, bleu, rouge = msvd
+    keys = vids[100:140]
+    cand = {k: [by[k][3 % len(by[k])] if j % 3 else 'a man is ' + by[k][0]] for j, k in enumerate(keys)}
+    ref = {k: by[k] for k in keys}
+    got = s2vt_b200.rewards.evaluate_for_particular_captions(cand, ref, w2i)
+    hyps = [cand[k][0] for k in keys]
+    oref = {i: by[k] for i, k in enumerate(keys)}
+    want_b = R.corpus_bleu(oref, hyps)
+    for m, w in zip(('Bleu_1', 'Bleu_2', 'Bleu_3', 'Bleu_4'), want_b):
+        assert abs(got[m] - w) < 1e-12 * max(1.0, w), m
+    assert abs(got['ROUGE_L'] - R.evaluate_captions_rouge(oref, hyps).mean()) < 1e-12
+    sc = ocider.CiderD([by[k] for k in keys])
+    want_c = ocider.evaluate_captions_cider(sc, oref, hyps).mean()
+    assert abs(got['CIDEr'] - want_c) < 1e-9
+    print('\n[score_all] %s' % {k: round(v, 4) for k, v in got.items()})
