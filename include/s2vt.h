@@ -217,7 +217,7 @@ int s2vt_rouge_score(const void* corpus_device, const int32_t* hyp, const int32_
  * A separate handle with the same conventions as s2vt_handle (caller-owned state / workspace, explicit stream, codes).
  * Variables by TF name: Wemb [V,H], encode_image_W [D,H], encode_image_b, embed_att_w [H,1], embed_att_Wa, embed_att_Ua,
  * embed_att_ba, embed_word_W [H,V], embed_word_b, embed_nn_Wp [3H,H], embed_nn_bp, s2vt/LSTM3/basic_lstm_cell/{weights
- * [3H,4H], biases}.  Built so far: the greedy sampler and the teacher-forced loss (forward); the backward pass is not. */
+ * [3H,4H], biases}.  One row per video (the reference has no multi-sample path for this model). */
 typedef struct s2vt_att_handle s2vt_att_handle;
 typedef struct s2vt_att_config {
     int32_t dim_image;        /* 1536 (:296) */
@@ -236,9 +236,13 @@ void s2vt_att_destroy(s2vt_att_handle* h);
 const char* s2vt_att_last_error(const s2vt_att_handle* h);
 size_t s2vt_att_num_params(const s2vt_att_handle* h);
 size_t s2vt_att_state_bytes(const s2vt_att_handle* h);
-size_t s2vt_att_workspace_bytes(const s2vt_att_handle* h, int n_videos, int n_rows);
+/* train != 0: room for the per-step operands the backward pass needs */
+size_t s2vt_att_workspace_bytes(const s2vt_att_handle* h, int n_videos, int train);
 int s2vt_att_bind(s2vt_att_handle* h, void* state, size_t state_bytes, void* workspace, size_t workspace_bytes);
 float* s2vt_att_params(const s2vt_att_handle* h);
+float* s2vt_att_grads(const s2vt_att_handle* h);   /* num_params + 8 floats: gradients | [slice sq-norm, loss, regulariser, sum(mask)] */
+float* s2vt_att_adam_m(const s2vt_att_handle* h);
+float* s2vt_att_adam_v(const s2vt_att_handle* h);
 int s2vt_att_num_variables(const s2vt_att_handle* h);
 int s2vt_att_variable_info(const s2vt_att_handle* h, int index, const char** tf_name, int64_t* offset, int64_t shape[2], int* ndim);
 int s2vt_att_load_param(s2vt_att_handle* h, const char* tf_name, const float* src_host, const int64_t* shape, int ndim, s2vt_stream st);
@@ -250,6 +254,14 @@ int s2vt_att_greedy(s2vt_att_handle* h, const float* video, int B, int32_t* ids_
  * regulariser part; logits_out (nullable) fp32 [T_c, B, V].  Dropout stream as in s2vt.h (drop_seed 0 = keep everything). */
 int s2vt_att_xe_loss(s2vt_att_handle* h, const float* video, int B, const int32_t* captions, const float* mask, uint64_t drop_seed, uint32_t row_base,
                      float* loss_out, float* logits_out, s2vt_stream st);
+/* build_model loss AND its gradients w.r.t. the 13 variables (what optimizer.compute_gradients(tf_loss) returns, :432), into the
+ * flat gradient block in TF layouts. */
+int s2vt_att_xe_backward(s2vt_att_handle* h, const float* video, int B, const int32_t* captions, const float* mask, uint64_t drop_seed, uint32_t row_base,
+                         float* loss_out, s2vt_stream st);
+/* tf.clip_by_global_norm(gradients, clip_norm) + AdamOptimizer.apply_gradients (:431-435; clip 10, lr 1e-4 halved every 10000
+ * steps by the caller); the Wemb term of the global norm is the IndexedSlices norm as in TF.  out[0] = global norm, out[1] = loss.
+ * Re-packs the operand copies (no separate refresh needed). */
+int s2vt_att_optimizer_step(s2vt_att_handle* h, float lr, float clip_norm, int64_t step, float* out, s2vt_stream st);
 long long s2vt_att_launch_count(const s2vt_att_handle* h);
 
 #ifdef __cplusplus

@@ -88,6 +88,11 @@ SIGNATURES = {
     's2vt_att_refresh': (_i32, [_vp, _vp]),
     's2vt_att_greedy': (_i32, [_vp, _vp, _i32, _vp, _vp, _vp]),
     's2vt_att_xe_loss': (_i32, [_vp, _vp, _i32, _vp, _vp, _u64, _u32, _vp, _vp, _vp]),
+    's2vt_att_grads': (_vp, [_vp]),
+    's2vt_att_adam_m': (_vp, [_vp]),
+    's2vt_att_adam_v': (_vp, [_vp]),
+    's2vt_att_xe_backward': (_i32, [_vp, _vp, _i32, _vp, _vp, _u64, _u32, _vp, _vp]),
+    's2vt_att_optimizer_step': (_i32, [_vp, _f32, _f32, _i64, _vp, _vp]),
     's2vt_att_launch_count': (C.c_longlong, [_vp]),
     # include/s2vt_io.h (host only)
     's2vt_io_last_error': (C.c_char_p, []),

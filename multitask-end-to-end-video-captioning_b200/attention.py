@@ -22,7 +22,7 @@ def _stream():
 
 class Video_Caption_Generator(object):
     def __init__(self, dim_image=1536, n_words=9972, dim_hidden=1000, batch_size=64, n_video_lstm_steps=5, n_caption_lstm_steps=35, drop_out_rate=0.9,
-                 bias_init_vector=None, beta=10.0, m=0.5, precision='bf16', device=None, seed=16):
+                 bias_init_vector=None, beta=10.0, m=0.5, precision='bf16', device=None, seed=16, train=True):
         if not torch.cuda.is_available():
             raise RuntimeError('multitask-end-to-end-video-captioning_b200 needs a CUDA device (sm_100a); there is no CPU path')
         self.lib = _lib.load()
@@ -38,13 +38,19 @@ class Video_Caption_Generator(object):
         self.h = h
         with torch.cuda.device(self.device):
             self._state = torch.zeros(self.lib.s2vt_att_state_bytes(h) + 256, dtype=torch.uint8, device=self.device)
-            self._ws = torch.empty(self.lib.s2vt_att_workspace_bytes(h, batch_size, batch_size) + 256, dtype=torch.uint8, device=self.device)
+            self._ws = torch.empty(self.lib.s2vt_att_workspace_bytes(h, batch_size, 1 if train else 0) + 256, dtype=torch.uint8, device=self.device)
             so, wo = (-self._state.data_ptr()) % 256, (-self._ws.data_ptr()) % 256
             self._check(self.lib.s2vt_att_bind(h, C.c_void_p(self._state.data_ptr() + so), self._state.numel() - so,
                                                C.c_void_p(self._ws.data_ptr() + wo), self._ws.numel() - wo))
         n = self.lib.s2vt_att_num_params(h)
         off = self.lib.s2vt_att_params(h) - self._state.data_ptr()
         self.params = self._state[off:off + 4 * n].view(torch.float32)
+        self.n_params = n
+        base = self._state.data_ptr()
+        view = lambda ptr, cnt: self._state[ptr - base:ptr - base + 4 * cnt].view(torch.float32)
+        self.grads = view(self.lib.s2vt_att_grads(h), n + 8)
+        self.adam_m, self.adam_v = view(self.lib.s2vt_att_adam_m(h), n), view(self.lib.s2vt_att_adam_v(h), n)
+        self.adam_step = 0
         self.variables = {}
         for i in range(self.lib.s2vt_att_num_variables(h)):
             name, o, shape, nd = C.c_char_p(), C.c_int64(), (C.c_int64 * 2)(), C.c_int32()
@@ -65,9 +71,9 @@ class Video_Caption_Generator(object):
         except Exception:
             pass
 
-    def variable(self, name):
+    def variable(self, name, grad=False):
         off, shp = self.variables[name]
-        return self.params[off:off + int(np.prod(shp))].view(*shp)
+        return (self.grads if grad else self.params)[off:off + int(np.prod(shp))].view(*shp)
 
     def refresh(self):
         self._check(self.lib.s2vt_att_refresh(self.h, _stream()))
@@ -141,6 +147,30 @@ class Video_Caption_Generator(object):
             raise ValueError('drop_seed must be non-zero when drop_out_rate < 1 (use a model built with drop_out_rate=1 for evaluation)')
         self._check(self.lib.s2vt_att_xe_loss(self.h, _ptr(v), B, _ptr(cap), _ptr(mk), int(drop_seed), int(row_base), _ptr(out), _ptr(logits), _stream()))
         return out, logits
+
+    def xe_backward(self, video, caption, caption_mask, drop_seed=0, row_base=0):
+        """optimizer.compute_gradients(tf_loss) (:432): loss [2] and the gradients of the 13 variables in `self.grads`."""
+        v = self._video(video)
+        cap = torch.as_tensor(caption).to(self.device, torch.int32).contiguous()
+        mk = torch.as_tensor(caption_mask).to(self.device, torch.float32).contiguous()
+        out = torch.empty(2, dtype=torch.float32, device=self.device)
+        if drop_seed == 0 and self.drop_out_rate < 1.0:
+            raise ValueError('drop_seed must be non-zero when drop_out_rate < 1')
+        self._check(self.lib.s2vt_att_xe_backward(self.h, _ptr(v), v.shape[0], _ptr(cap), _ptr(mk), int(drop_seed), int(row_base), _ptr(out), _stream()))
+        return out
+
+    def optimizer_step(self, lr, clip_norm=10.0):
+        """clip_by_global_norm(., 10) + Adam apply (:433-435) -> device tensor [global gradient norm, loss]."""
+        self.adam_step += 1
+        out = torch.empty(2, dtype=torch.float32, device=self.device)
+        self._check(self.lib.s2vt_att_optimizer_step(self.h, float(lr), float(clip_norm), self.adam_step, _ptr(out), _stream()))
+        return out
+
+    def train_step(self, video, caption, caption_mask, global_step, start_learning_rate=1e-4, drop_seed=1):
+        """sess.run([train_op, tf_loss]) (:468-476): lr = exponential_decay(1e-4, global_step, 10000, 0.5, staircase) (:429-430)."""
+        loss = self.xe_backward(video, caption, caption_mask, drop_seed=drop_seed).clone()
+        self.optimizer_step(start_learning_rate * 0.5 ** (global_step // 10000), 10.0)
+        return loss
 
     def launch_count(self):
         return int(self.lib.s2vt_att_launch_count(self.h))

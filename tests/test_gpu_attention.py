@@ -102,3 +102,51 @@ def test_attention_matches_committed_golden():
     ids, alphas = m.build_sampler(g['att_video'])
     assert (ids.cpu().numpy() == g['att_ids']).all()
     np.testing.assert_allclose(alphas.cpu().numpy(), g['att_alphas'], atol=1e-5)
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('bf16', 5e-2)])
+@pytest.mark.parametrize('n,keep', [(5, 1.0), (32, 0.9)])
+def test_attention_gradients_match_autograd_oracle(precision, tol, n, keep):
+    """optimizer.compute_gradients(tf_loss) (original_attention.py:432): all 13 gradients against torch.autograd of the float64
+    restatement (max-norm relative error per variable), plus the IndexedSlices square norm of the Wemb gradient."""
+    from oracle import attention_torch as AT
+    D, H, V, Tc, B = 96, 72, 300, 8, 6
+    p, m, video, cap, mask = _setup(D, H, V, n, Tc, B, precision, keep=keep)
+    seed, row_base = 31, 2
+    drop = None if keep >= 1.0 else np.stack([philox.dropout_mask(seed, philox.STREAM_DROP1, row_base + np.arange(B), t, H, keep) for t in range(Tc)])
+    loss, reg, grads, slice_sq = AT.loss_and_grads(p, video, cap, mask, drop)
+    out = m.xe_backward(video, cap, mask, drop_seed=seed if keep < 1.0 else 0, row_base=row_base).cpu().numpy()
+    assert abs(out[0] - loss) < (1e-5 if precision == 'fp32' else 5e-3) * abs(loss)
+    worst = {}
+    for name in m.variables:
+        got = m.variable(name, grad=True).cpu().numpy().astype(np.float64)
+        want = grads[name].reshape(got.shape)
+        worst[name] = np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+    print('\n[attention grads %s n=%d keep=%.1f] ' % (precision, n, keep) + ', '.join('%s %.1e' % (k.split('/')[-1], v) for k, v in worst.items()))
+    assert max(worst.values()) < tol, worst
+    if n == 32:
+        assert reg > 0                                               # the hinge regulariser contributes to the gradients checked above
+
+
+def test_attention_optimizer_step_matches_tf_adam_with_slice_norm():
+    from oracle import attention_torch as AT
+    D, H, V, n, Tc, B = 64, 40, 50, 12, 7, 5                        # small vocabulary: duplicate tokens -> slice norm != dense norm
+    p, m, video, cap, mask = _setup(D, H, V, n, Tc, B, 'fp32', keep=1.0)
+    state = {'t': 0, 'm': {}, 'v': {}}
+    params = {k: v.copy() for k, v in p.items()}
+    for step in range(2):
+        loss, reg, grads, slice_sq = AT.loss_and_grads(params, video, cap, mask, None)
+        dense_sq = float((grads['Wemb'] ** 2).sum())
+        assert abs(slice_sq - dense_sq) > 1e-3 * dense_sq
+        params, gn = AT.clip_and_adam(params, grads, slice_sq, state, lr=1e-2, clip_norm=0.05)      # clip active: gn >> 0.05
+        m.xe_backward(video, cap, mask)
+        out = m.optimizer_step(1e-2, clip_norm=0.05).cpu().numpy()
+        assert gn > 0.05 and abs(out[0] - gn) < 1e-4 * gn and abs(out[1] - loss) < 1e-5 * abs(loss)
+        for name in m.variables:
+            got = m.variable(name).cpu().numpy()
+            np.testing.assert_allclose(got, params[name].reshape(got.shape), rtol=0, atol=2e-5 * max(1.0, np.abs(params[name]).max()))
+    # the refreshed operand copies are in use: the next forward sees the updated weights
+    want_loss, _ = A.build_model_loss(params, video, cap, mask, None)
+    got_loss = m.build_model(video, cap, mask)[0].cpu().numpy()[0]
+    assert abs(got_loss - want_loss) < 1e-4 * abs(want_loss)
+    assert m.train_step(video, cap, mask, global_step=2, drop_seed=0).shape == (2,)

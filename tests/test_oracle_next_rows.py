@@ -58,3 +58,26 @@ def test_reward_oracle_reproduces_golden():
     np.testing.assert_allclose(R.bleu_all_orders(ref, hyps), g['bleu'], rtol=1e-13)
     np.testing.assert_array_equal(R.evaluate_captions_rouge(ref, hyps), g['rouge'])
     assert ((g['bleu'] >= 0) & (g['bleu'] <= 1 + 1e-9)).all() and ((g['rouge'] >= 0) & (g['rouge'] <= 1)).all()
+
+
+def test_attention_torch_restatement_equals_numpy_and_finite_differences():
+    from oracle import attention_torch as AT
+    D, H, V, n, Tc, B = 20, 12, 30, 24, 4, 3
+    p = A.init_params(D, H, V, seed=3)
+    rng = np.random.RandomState(2)
+    video = rng.rand(B, n, D); cap = rng.randint(0, V, (B, Tc)); mask = np.array([[1, 1, 1, 0], [1, 1, 0, 0], [1, 1, 1, 1]], dtype=np.float64)
+    drop = np.stack([philox.dropout_mask(8, philox.STREAM_DROP1, np.arange(B), t, H, 0.9) for t in range(Tc)])
+    want = A.build_model_loss(p, video, cap, mask, drop)
+    loss, reg, grads, slice_sq = AT.loss_and_grads(p, video, cap, mask, drop)
+    assert abs(loss - want[0]) < 1e-12 and abs(reg - want[1]) < 1e-12 and reg > 0
+    # central finite differences of the NumPy restatement on a few coordinates of every variable
+    for name in p:
+        flat = p[name].reshape(-1)
+        for idx in rng.choice(flat.size, size=min(3, flat.size), replace=False):
+            old = flat[idx]
+            flat[idx] = old + 1e-6; up = A.build_model_loss(p, video, cap, mask, drop)[0]
+            flat[idx] = old - 1e-6; dn = A.build_model_loss(p, video, cap, mask, drop)[0]
+            flat[idx] = old
+            fd = (up - dn) / 2e-6
+            assert abs(fd - grads[name].reshape(-1)[idx]) < 1e-6 + 1e-4 * abs(fd), (name, idx, fd, grads[name].reshape(-1)[idx])
+    assert slice_sq > 0
