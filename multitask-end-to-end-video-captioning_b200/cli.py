@@ -26,7 +26,7 @@ def build_parser(description, defaults):
              dim_image=1536, lstm_dim=1000, word_dim=500, n_video_lstm_step=5, n_caption_lstm_step=35, n_epochs=30, batch_size=64,
              start_learning_rate=1e-3, decay_steps=5000, clip_norm=10.0, dropout_rate=0.9, decay_value=5e-5, seed_num=4,
              n_samples=8, beam_size=3, length_normalization_factor=0.0, alpha=0.5, precision='bf16', max_iters=0,
-             reward='cider')      # reward: cider (cider_evaluation.py) | bleu4 (bleu_evaluation.py) | rouge (rouge_evaluation.py)
+             reward='cider', beta=10.0, m=0.5)      # beta / m: hinge regulariser of original_attention.py:299-300; reward: cider (cider_evaluation.py) | bleu4 (bleu_evaluation.py) | rouge (rouge_evaluation.py)
     d.update({k: v for k, v in defaults.items() if k != 'task'})
     for k, v in d.items():
         ap.add_argument('--' + k, type=(type(v) if v is not None else str), default=v)
@@ -212,3 +212,64 @@ def run_beam(args):
     _setup(args)
     wordtoix, ixtoword, model = _vocab_and_model(args, pkg, beam=args.beam_size)
     return _decode_task(args, pkg, model, wordtoix, ixtoword, beam=True)
+
+
+def run_attention(args):
+    """original_attention.py train() (:390-541) / test() (:544-): temporal-attention decoder -- teacher-forced XE with the hinge
+    regulariser on the alphas, Adam 1e-4 halved every 10000 steps, clip 10; per epoch greedy decode of the test split scored with
+    evaluate_for_particular_captions; --task test / evaluate decode with the saved alphas available from build_sampler."""
+    import s2vt_b200 as pkg
+    rank, world = _setup(args)
+    vocabulary = pkg.text.read_vocabulary(args.vocabulary_file)
+    wordtoix, ixtoword = pkg.text.preProBuildWordVocab(vocabulary, word_count_threshold=0)
+    train = args.task == 'train'
+    model = pkg.attention.Video_Caption_Generator(dim_image=args.dim_image, n_words=len(wordtoix), dim_hidden=args.lstm_dim, batch_size=args.batch_size,
+                                                  n_video_lstm_steps=args.n_video_lstm_step, n_caption_lstm_steps=args.n_caption_lstm_step,
+                                                  drop_out_rate=args.dropout_rate if train else 1.0, bias_init_vector=None, beta=args.beta, m=args.m,
+                                                  precision=args.precision, seed=args.seed_num, train=train)
+    if args.restore:
+        restored, _ = pkg.checkpoint.optimistic_restore(model, args.restore)
+        print('restored %d variables from %s' % (len(restored), args.restore))
+
+    def decode_test_split():
+        test_captions, test_features = pkg.text.get_video_feature_caption_pair(args.video_test_sent_file, args.video_test_feature_file)
+        by, _ = pkg.text.group_by_video(test_captions)
+        vids, hyps = [v for v in test_features], {}
+        for i in range(0, len(vids), args.batch_size):
+            chunk = vids[i:i + args.batch_size]
+            ids = model.build_generator(np.stack([test_features[v] for v in chunk]).astype(np.float32)).cpu().numpy()
+            for v, s_ in zip(chunk, pkg.text.decode_captions(ids, ixtoword)):
+                hyps[v] = s_
+        keep = [v for v in vids if v in by]
+        scores = pkg.rewards.evaluate_for_particular_captions({v: [hyps[v]] for v in keep}, {v: by[v] for v in keep}, wordtoix) if keep else {}
+        return vids, hyps, scores
+
+    if not train:
+        vids, hyps, scores = decode_test_split()
+        with open(args.out_file, 'w') as f:
+            for v in vids:
+                f.write(v + '\t' + hyps[v] + '\n')
+        print(json.dumps(scores))
+        return scores if args.task == 'evaluate' else hyps
+    train_captions, train_features = pkg.text.get_video_feature_caption_pair(args.video_train_sent_file, args.video_train_feature_file)
+    it = 0
+    for epoch in range(args.n_epochs):
+        index = list(range(len(train_captions))); random.shuffle(index)
+        for start in _batches(len(index), args.batch_size, rank, world):
+            t0 = time.time()
+            rows = index[start:start + args.batch_size]
+            vids, sents = train_captions[rows, 0], train_captions[rows, 1].tolist()
+            feats = np.stack([train_features[v] for v in vids])
+            ids, mask = pkg.text.sentence_padding_toix(sents, wordtoix, args.n_caption_lstm_step)
+            loss = model.train_step(feats, ids, mask, global_step=it, start_learning_rate=args.start_learning_rate, drop_seed=args.seed_num * 7919 + it + 1)
+            print('idx: ', start, ' Epoch: ', epoch, ' loss: ', float(loss[0].item()), ' Elapsed time: ', str(time.time() - t0))
+            it += 1
+            if args.max_iters and it >= args.max_iters:
+                break
+        _, _, scores = decode_test_split()
+        with open(args.out_file, 'a') as f:
+            f.write('Epoch %d\n\n' % epoch + ''.join('%s:%s\n' % (k, scores[k]) for k in ('Bleu_1', 'Bleu_2', 'Bleu_3', 'Bleu_4', 'ROUGE_L', 'CIDEr') if k in scores))
+        print('CIDEr: ', scores.get('CIDEr'))
+        pkg.checkpoint.save(model, os.path.join(args.model_path, 'batch_size%d%s-%d' % (args.batch_size, args.model_name, epoch)), it)
+        if args.max_iters and it >= args.max_iters:
+            break

@@ -118,3 +118,24 @@ def test_attribute_head_and_stage3_mix(precision, tol):
         assert rel(m.variable(k, grad=True).cpu().numpy(), want) < tol, k
     assert rel(m.variable('attr_W', grad=True).cpu().numpy(), alpha * g_at['attr_W']) < tol
     assert rel(m.variable('attr_b', grad=True).cpu().numpy(), alpha * g_at['attr_b']) < tol
+
+
+def test_attention_and_alternative_reward_scripts(tiny, monkeypatch):
+    """original_attention.py (train -> checkpoint -> evaluate with the full-metric evaluator) and the bleu4_ / rouge_ RL scripts."""
+    import s2vt_b200
+    d, D, Tv = tiny
+    monkeypatch.chdir(d)
+    cli = s2vt_b200.cli
+    a = _args(dict(model_name='_att', start_learning_rate=1e-2, decay_steps=10000, clip_norm=10.0, seed_num=16), d, D, Tv, max_iters=4)
+    cli.run_attention(a)
+    ck = str(d / 'models' / 'batch_size4_att-0')
+    assert os.path.exists(ck + '.npz')
+    rec = open(d / 'out.txt').read()
+    assert 'Epoch 0' in rec and 'Bleu_4:' in rec and 'CIDEr:' in rec                                  # per-epoch metric record (:481-520)
+    scores = cli.run_attention(_args(dict(), d, D, Tv, task='evaluate', restore=ck))
+    assert set(scores) >= {'Bleu_1', 'Bleu_4', 'ROUGE_L', 'CIDEr'} and all(np.isfinite(v) for v in scores.values())
+    lines = open(d / 'out.txt').read().split('\n')[:-1]
+    assert len(lines) == 5 and all(l.startswith('vid') and '\t' in l for l in lines)
+    for reward in ('bleu4', 'rouge'):
+        cli.run_rl(_args(dict(model_name='rl_' + reward, n_samples=2, start_learning_rate=1e-4, clip_norm=5.0, reward=reward), d, D, Tv))
+        assert os.path.exists(str(d / 'models' / ('rl_%s-0.npz' % reward)))
