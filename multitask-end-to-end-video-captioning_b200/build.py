@@ -38,7 +38,7 @@ def build(force=False, verbose=True):
             continue
         obj = os.path.join(CSRC, os.path.splitext(src)[0] + '.o')
         if src.endswith('.cu'):
-            cmd = [_nvcc()] + NVCC_FLAGS + ['-c', path, '-o', obj]
+            cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get('S2VT_NVCC_EXTRA', '').split() + ['-c', path, '-o', obj]     # e.g. -DS2VT_CHAIN_PROBE
         else:
             cmd = [os.environ.get('CXX', 'g++'), '-O3', '-std=c++17', '-fPIC', '-pthread', '-Wall', '-c', path, '-o', obj]
         if verbose:

@@ -50,18 +50,41 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t addr = smem_u32(bar), done = 0;
+// try_wait suspends the warp in hardware until the phase completes or a time limit passes, so the loop below wakes rarely; the
+// watchdog clock is read only every 256 wake-ups (a clock64 + compare per poll in the tcgen05.mma issuing thread and in the
+// epilogue warps spinning beside it cost more than the MMAs themselves for narrow tiles).
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    return done != 0;
+}
+static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
     long long t0 = clock64();
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) break;
-        if (clock64() - t0 > 4000000000LL) { printf("s2vt: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+    for (unsigned spins = 1;; ++spins) {
+        if (mbar_try(addr, parity)) return;
+        if ((spins & 255u) == 0 && clock64() - t0 > 4000000000LL) {
+            printf("s2vt: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    if (mbar_try(addr, parity)) return;
+    mbar_wait_slow(addr, parity);
+}
+// One lane of a converged warp.  The role loops below run on the WHOLE warp and only the tcgen05.mma / TMA / commit instructions are
+// predicated on the elected lane: descriptors and coordinates are then computed in warp-uniform code and stay in uniform registers.
+// Issued from inside `if (lane == 0)` the compiler had to move every operand into uniform registers with an ELECT / R2UR loop
+// before each UTCHMMA -- about as expensive as the 64-cycle MMA itself for tiles of N <= 128.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tma_load_2d_raw(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -172,6 +195,10 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
 // `empty` barrier of each CTA that sends to it, and `empty` counts CX + CY - 1 arrivals.
 // MN == true: both operands are MN-major -- C[Mf, Nf] = sum_r X[r, Mf] . Y[r, Nf] for row-major X, Y (the weight-gradient
 // products), so no transposed copies are needed; the contraction runs over rows and its tail is zero-filled by TMA.
+// Independent accumulators (see gemm_tcgen05_chain.cuh): with tiles of N <= 128 a K loop of tcgen05.mma into ONE accumulator is bound by
+// the accumulate latency of each instruction, so K-block i goes to accumulator tile (i mod NACC) and the epilogue adds the tiles.
+template <int BN> struct ChainAcc { static constexpr int N = BN <= 32 ? 8 : (BN <= 64 ? 4 : (BN <= 128 ? 4 : 1)); };
+
 template <int BN, class Epi, int KS, int CX = 1, int CY = 1, bool MN = false>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                       int K, int a_rows, typename Epi::Params ep) {
@@ -183,6 +210,9 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     static_assert(!MN || (KS == 1 && CX == 1 && CY == 1), "MN-major operands: plain kernel only");
     constexpr uint32_t IDESC = C::IDESC | (MN ? ((1u << 15) | (1u << 16)) : 0u);
     constexpr bool MC = CX * CY > 1;
+    constexpr int NACC = ChainAcc<BN>::N;
+    constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
+    static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation: power of two <= 512 columns");
     constexpr int A_ROWS = BM / CX, B_ROWS = BN / CY;   // rows this CTA fetches of each tile
     const uint32_t stage_tx = (uint32_t)((MC || MN) ? C::STAGE_BYTES : a_rows * 128 + C::B_BYTES);
     uint32_t crank = 0;
@@ -223,20 +253,21 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM allocation is warp-wide; the same warp frees it at the end
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    const int nacc = KBL < NACC ? KBL : NACC;           // accumulator tiles this launch writes
     if constexpr (KS > 1 || MC) cluster_sync_all();   // every CTA of the cluster is running and its barriers are initialised
 
     // Programmatic dependent launch: let the next kernel in the stream start its prologue now; the weight (B) tiles of the
     // first stages never depend on the previous kernel, so they are requested before waiting for it.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int pre = KBL < C::STAGES ? KBL : C::STAGES;
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         for (int i = 0; i < pre; ++i) {
             mbar_expect_tx(full + i, stage_tx);
             unsigned char* b = smem + i * C::STAGE_BYTES + C::A_BYTES + cy * B_ROWS * 128;
@@ -252,12 +283,13 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     if (probe && threadIdx.x == 0) probe[1] = gtimer();
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < KBL; ++i) {
-                const int s = i % C::STAGES;
-                unsigned char* a = smem + s * C::STAGE_BYTES;
-                if (i >= C::STAGES) {
-                    mbar_wait(empty + s, ((i / C::STAGES) - 1) & 1);
+        const bool leader = elect_one();
+        for (int i = 0; i < KBL; ++i) {
+            const int s = i % C::STAGES;
+            unsigned char* a = smem + s * C::STAGE_BYTES;
+            if (i >= C::STAGES) {
+                mbar_wait(empty + s, ((i / C::STAGES) - 1) & 1);
+                if (leader) {
                     mbar_expect_tx(full + s, stage_tx);
                     unsigned char* b = a + C::A_BYTES + cy * B_ROWS * 128;
                     if constexpr (MN) {
@@ -267,6 +299,8 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
                     else if constexpr (CY > 1) tma_load_2d_mc(b, &mapB, full + s, (kb0 + i) * C::BK, n0 + cy * B_ROWS, col_mask);
                     else tma_load_2d(b, &mapB, full + s, (kb0 + i) * C::BK, n0, BN);
                 }
+            }
+            if (leader) {
                 if constexpr (MN) {
                     tma_load_2d_raw(a, &mapA, full + s, m0, (kb0 + i) * C::BK);
                     tma_load_2d_raw(a + 8192, &mapA, full + s, m0 + 64, (kb0 + i) * C::BK);
@@ -277,21 +311,23 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            for (int i = 0; i < KBL; ++i) {
-                const int s = i % C::STAGES;
-                mbar_wait(full + s, (i / C::STAGES) & 1);
-                if (probe && i == 0) probe[2] = gtimer();
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a = smem_u32(smem + s * C::STAGE_BYTES);
-                const uint64_t adesc = MN ? make_desc_mn(a) : make_desc(a), bdesc = MN ? make_desc_mn(a + C::A_BYTES) : make_desc(a + C::A_BYTES);
-                constexpr int KADV = MN ? 128 : 2;      // K-major: +32 bytes per K=16 step inside the swizzle atom; MN-major: +16 rows = 2048 bytes
+        const bool leader = elect_one();
+        for (int i = 0; i < KBL; ++i) {
+            const int s = i % C::STAGES;
+            mbar_wait(full + s, (i / C::STAGES) & 1);
+            if (probe && i == 0 && leader) probe[2] = gtimer();
+            const uint32_t a = smem_u32(smem + s * C::STAGE_BYTES);
+            const uint64_t adesc = MN ? make_desc_mn(a) : make_desc(a), bdesc = MN ? make_desc_mn(a + C::A_BYTES) : make_desc(a + C::A_BYTES);
+            constexpr int KADV = MN ? 128 : 2;      // K-major: +32 bytes per K=16 step inside the swizzle atom; MN-major: +16 rows = 2048 bytes
+            if (leader) {
 #pragma unroll
                 for (int k = 0; k < C::BK / 16; ++k)
-                    mma_bf16(tmem_base, adesc + KADV * k, bdesc + KADV * k, IDESC, (i | k) != 0);
+                    mma_bf16(tmem_base + (uint32_t)((i % NACC) * BN), adesc + KADV * k, bdesc + KADV * k, IDESC, i >= NACC || k != 0);
                 if constexpr (MC) mma_commit_mc(empty + s, (uint16_t)(row_mask | col_mask));
                 else mma_commit(empty + s);             // implies tcgen05.fence::before_thread_sync
             }
+        }
+        if (leader) {
             mma_commit(tmem_full);
             if (probe) probe[3] = gtimer();
         }
@@ -311,6 +347,12 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float v[32];
             tmem_ld32(trow + (uint32_t)c0, v);
+            for (int a = 1; a < nacc; ++a) {
+                float w[32];
+                tmem_ld32(trow + (uint32_t)(a * BN + c0), w);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += w[j];
+            }
             direct_chunk<Epi>(ep, m0 + row, n0 + c0, v, pre, false);
         } else if constexpr (Epi::kDirect) {
             // split-K: final mapping of this thread = row (32 rank + t / (BN/8)), units [8 (t % (BN/8)), +8)
@@ -326,6 +368,12 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
                 const int c0 = (e >> 2) * 32;
                 float v[32];
                 tmem_ld32(trow + (uint32_t)c0, v);
+                for (int a = 1; a < nacc; ++a) {
+                    float w[32];
+                    tmem_ld32(trow + (uint32_t)(a * BN + c0), w);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += w[j];
+                }
                 const uint32_t base = cluster_map(smem_u32(recv), (uint32_t)q) + (uint32_t)(((rank * 32 + lane) * BN) * 4);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -353,6 +401,12 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
             for (int c0 = cbeg; c0 < cbeg + CPW; c0 += 32) {
                 float v[32];
                 tmem_ld32(trow + (uint32_t)c0, v);
+                for (int a = 1; a < nacc; ++a) {
+                    float w[32];
+                    tmem_ld32(trow + (uint32_t)(a * BN + c0), w);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += w[j];
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(Cs + row * C::LDC + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -372,7 +426,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
     if constexpr (MC) cluster_sync_all();   // peers may still signal this CTA's barriers: nobody leaves before everybody is done
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 

@@ -433,10 +433,27 @@ __global__ void colsum_grad_kernel(const T* __restrict__ Y, int ld, int R, int n
 
 // ---- optimiser --------------------------------------------------------------------------------------------------
 // sum of squares of a float range into a double accumulator (global-norm clip)
+// 128-bit loads, four in flight per thread: a scalar grid-stride loop keeps too few bytes in flight to reach HBM bandwidth.
 __global__ void sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ out) {
     __shared__ double red[32];
     double acc = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { float v = g[i]; acc += (double)v * v; }
+    size_t head = ((16 - ((uintptr_t)g & 15)) & 15) / 4;
+    if (head > n) head = n;
+    const float4* g4 = reinterpret_cast<const float4*>(g + head);
+    const size_t n4 = (n - head) / 4, stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 a = g4[i], b = g4[i + stride], c = g4[i + 2 * stride], d = g4[i + 3 * stride];
+        acc += (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z + (double)a.w * a.w;
+        acc += (double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z + (double)b.w * b.w;
+        acc += (double)c.x * c.x + (double)c.y * c.y + (double)c.z * c.z + (double)c.w * c.w;
+        acc += (double)d.x * d.x + (double)d.y * d.y + (double)d.z * d.z + (double)d.w * d.w;
+    }
+    for (; i < n4; i += stride) { const float4 a = g4[i]; acc += (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z + (double)a.w * a.w; }
+    if (blockIdx.x == 0) {   // unaligned head and the < 4 element tail
+        for (size_t j = threadIdx.x; j < head; j += blockDim.x) { float v = g[j]; acc += (double)v * v; }
+        for (size_t j = head + 4 * n4 + threadIdx.x; j < n; j += blockDim.x) { float v = g[j]; acc += (double)v * v; }
+    }
     acc = block_reduce(acc, [](double a, double b) { return a + b; }, red);
     if (threadIdx.x == 0) atomicAdd(out, acc);
 }
@@ -457,7 +474,20 @@ __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__
     float scale = 1.0f;
     if (clip > 0.f && gn > 0.f) scale = clip * fminf(1.0f / gn, 1.0f / clip);
     if (gnorm_out && blockIdx.x == 0 && threadIdx.x == 0) { gnorm_out[0] = gn; gnorm_out[1] = g[n + 1] * inv; }
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // the four blocks are 256-byte aligned arena allocations: 128-bit accesses over the bulk, scalars over the < 4 element tail
+    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
+    float4* t4 = reinterpret_cast<float4*>(theta); const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m); float4* v4 = reinterpret_cast<float4*>(v);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 gg = g4[i]; float4 mm = m4[i], vv = v4[i], tt = t4[i];
+        float gi;
+        gi = gg.x * inv * scale; mm.x = b1 * mm.x + (1.f - b1) * gi; vv.x = b2 * vv.x + (1.f - b2) * gi * gi; tt.x -= lr_t * mm.x / (sqrtf(vv.x) + eps);
+        gi = gg.y * inv * scale; mm.y = b1 * mm.y + (1.f - b1) * gi; vv.y = b2 * vv.y + (1.f - b2) * gi * gi; tt.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
+        gi = gg.z * inv * scale; mm.z = b1 * mm.z + (1.f - b1) * gi; vv.z = b2 * vv.z + (1.f - b2) * gi * gi; tt.z -= lr_t * mm.z / (sqrtf(vv.z) + eps);
+        gi = gg.w * inv * scale; mm.w = b1 * mm.w + (1.f - b1) * gi; vv.w = b2 * vv.w + (1.f - b2) * gi * gi; tt.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
+        m4[i] = mm; v4[i] = vv; t4[i] = tt;
+    }
+    for (size_t i = 4 * n4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float gi = g[i] * inv * scale;
         float mi = b1 * m[i] + (1.f - b1) * gi;
         float vi = b2 * v[i] + (1.f - b2) * gi * gi;

@@ -426,7 +426,10 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
                 if (c.M > 128) e = tc::launch_chain<128, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
                 else {
                     e = cudaErrorLaunchOutOfResources;   // weights-stationary variant first (rows <= 64, K <= 16 blocks)
-                    if (c.M <= 64 && h->cfg.gemm_backend != 10) e = tc::launch_chain<32, Epi, 1, true>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                    // weights stationary + the activation rows multicast over clusters of 8 column tiles (gemm_backend 11 / 12: clusters of 4 / none)
+                    if (c.M <= 64 && h->cfg.gemm_backend != 10 && h->cfg.gemm_backend != 11 && h->cfg.gemm_backend != 12) e = tc::launch_chain<32, Epi, 1, true, 8>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                    if (e == cudaErrorLaunchOutOfResources && c.M <= 64 && h->cfg.gemm_backend == 11) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1, true, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true); }
+                    if (e == cudaErrorLaunchOutOfResources && c.M <= 64 && h->cfg.gemm_backend != 10) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1, true>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true); }
                     if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true); }
                 }
             }

@@ -121,9 +121,9 @@ class ReinforceTrainer(object):
         row_base = rank * K * B
         samp, greedy = m.rollout(v, K, seed=self.seed + it, row_base=row_base)                    # :743-753
         mask, _ = m.caption_masks(samp)                                                           # :784
-        rows = vi.repeat(K)
-        r = self.scorer.score_ids(samp, rows).to(torch.float32)                                   # :806
-        b = self.scorer.score_ids(greedy, vi).to(torch.float32).repeat(K)                         # :790-795
+        scores = self.scorer.score_ids(torch.cat([samp, greedy]), vi.repeat(K + 1)).to(torch.float32)    # one launch for both calls
+        r = scores[:K * B]                                                                        # :806
+        b = scores[K * B:].repeat(K)                                                              # :790-795
         drop_seed = (self.seed * 7919 + it + 1) if self.dropout else 0
         m.rl_backward(v, samp, mask, r, b, norm=1.0, drop_seed=drop_seed, row_base=row_base)      # :643-650, norm deferred
         allreduce_gradients(m)
