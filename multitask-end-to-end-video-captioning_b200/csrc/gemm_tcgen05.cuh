@@ -90,6 +90,10 @@ __device__ __forceinline__ void tma_load_2d_raw(void* smem_dst, const CUtensorMa
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_raw(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 #ifdef S2VT_TMA_SPLIT
 // experiment: the tensor maps are built with 64-row boxes and every tile is fetched as rows/64 separate TMA instructions
 __device__ int g_split_rows_a, g_split_rows_b;
@@ -195,9 +199,11 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
 // `empty` barrier of each CTA that sends to it, and `empty` counts CX + CY - 1 arrivals.
 // MN == true: both operands are MN-major -- C[Mf, Nf] = sum_r X[r, Mf] . Y[r, Nf] for row-major X, Y (the weight-gradient
 // products), so no transposed copies are needed; the contraction runs over rows and its tail is zero-filled by TMA.
-// Independent accumulators (see gemm_tcgen05_chain.cuh): with tiles of N <= 128 a K loop of tcgen05.mma into ONE accumulator is bound by
-// the accumulate latency of each instruction, so K-block i goes to accumulator tile (i mod NACC) and the epilogue adds the tiles.
-template <int BN> struct ChainAcc { static constexpr int N = BN <= 32 ? 8 : (BN <= 64 ? 4 : (BN <= 128 ? 4 : 1)); };
+// Accumulator tiles per output tile.  Splitting the K loop over several independent TMEM accumulators was tried against the
+// hypothesis that back-to-back tcgen05.mma into one tile wait for each other: scripts/micro/mma_rate.cu shows they do not (a
+// 128 x N x 16 MMA costs ~64 cycles for every N <= 128, dependent or not), while every extra tile costs a full TMEM read in the
+// epilogue (64 B/clk: 0.5 us per 128 x 128 tile).  Kept at 1; the plumbing stays for experiments.
+template <int BN> struct ChainAcc { static constexpr int N = 1; };
 
 template <int BN, class Epi, int KS, int CX = 1, int CY = 1, bool MN = false>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -472,6 +478,25 @@ inline const CUtensorMap* get_map(MapCache& cache, const void* ptr, int rows, in
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nullptr;
+    return &cache.emplace(key, m).first->second;
+}
+
+// The same matrix seen as [K / 64 blocks][rows][64 columns]: one box {64, box_rows, kblocks} lands `kblocks` consecutive K-block tiles
+// (each box_rows x 128 bytes, 128-byte swizzle) in shared memory with ONE TMA instruction.  Key: box_rows carries the block count too.
+inline const CUtensorMap* get_map3d(MapCache& cache, const void* ptr, int rows, int cols, int ld, int box_rows, int kblocks) {
+    MapKey key = {ptr, rows, cols, ld, -(box_rows * 64 + kblocks)};
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return nullptr;
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)BK, (cuuint64_t)rows, (cuuint64_t)(cols / BK)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)BK * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)kblocks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return nullptr;
     return &cache.emplace(key, m).first->second;

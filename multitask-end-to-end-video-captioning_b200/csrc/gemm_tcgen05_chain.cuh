@@ -40,10 +40,6 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // ncta / CX times per step instead of ncta times (the step is bound by that broadcast, not by the per-SM fill rate: probe_chains.py).
 // A peer may multicast into this CTA before it has armed its own `full` barrier for the step: the transaction count simply goes
 // negative until the local expect_tx; it cannot run a phase ahead because peers pass the grid barrier only after this CTA's epilogue.
-// Independent accumulators.  A recurrent step is a chain of K/16 tcgen05.mma that all accumulate into one TMEM tile; with narrow tiles
-// (N = 32 ... 128: 16 ... 64 cycles of tensor work per instruction) each instruction waits for the accumulate latency of its
-// predecessor (~170 cycles measured: 64 dependent MMAs took 5.3 us, scripts/probe_chains.py), so the step was bound by that
-// latency, not by data movement.  K-block i therefore accumulates into tile (i mod NACC) and the epilogue adds the NACC tiles.
 // (ChainAcc<BN>::N, gemm_tcgen05.cuh, is shared with the per-step kernels so both sum in the same order.)
 template <int BN, class Epi, int KS, bool WS, int CX = 1>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -161,7 +157,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                         tma_load_2d_mc(smem + i * WS_A + crank * rows_per * 128, &mapA, full + i, (kb0 + i) * C::BK, arow + (int)crank * rows_per, (uint16_t)((1u << CX) - 1u));
                     }
             } else if constexpr (WS) {
-                if (leader)
+                if (leader)      // (3-D boxes fetching 4 K-block tiles per instruction were measured: no faster, the step is MMA-issue bound)
                     for (int i = 0; i < KBL; ++i) {
                         mbar_expect_tx(full + i, (uint32_t)(a_rows * 128));
                         tma_load_2d_raw(smem + i * WS_A, &mapA, full + i, (kb0 + i) * C::BK, arow);
@@ -222,7 +218,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                 typename Epi::Pre prf;
                 Epi::prefetch(ep, m0 + row, n0 + c0, prf);
                 mbar_wait(tmem_full, s & 1);
-                CHAIN_PROBE(if (probe && threadIdx.x == 64) probe[8 * s + 4] = gtimer());
+                CHAIN_PROBE(if (probe && threadIdx.x == 128) probe[8 * s + 4] = gtimer());
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float v[32];
                 tmem_ld32(trow + (uint32_t)c0, v);
@@ -233,7 +229,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                     for (int j = 0; j < 32; ++j) v[j] += w[j];
                 }
                 direct_chunk<Epi>(ep, m0 + row, n0 + c0, v, prf, false);
-                CHAIN_PROBE(if (probe && threadIdx.x == 64) probe[8 * s + 5] = gtimer());
+                CHAIN_PROBE(if (probe && threadIdx.x == 128) probe[8 * s + 5] = gtimer());
             } else {
                 constexpr int UPR = BN / 8;
                 const int t = threadIdx.x - 64;
@@ -241,7 +237,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                 typename Epi::Pre prf;
                 Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, prf);
                 mbar_wait(tmem_full, s & 1);
-                CHAIN_PROBE(if (probe && threadIdx.x == 64) probe[8 * s + 4] = gtimer());
+                CHAIN_PROBE(if (probe && threadIdx.x == 128) probe[8 * s + 4] = gtimer());
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 {
                     const int c0 = (e >> 2) * 32;
@@ -270,7 +266,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                     acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w; acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
                 }
                 Epi::direct(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, acc, prf);
-                CHAIN_PROBE(if (probe && threadIdx.x == 64) probe[8 * s + 5] = gtimer());
+                CHAIN_PROBE(if (probe && threadIdx.x == 128) probe[8 * s + 5] = gtimer());
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
