@@ -70,6 +70,17 @@ __device__ __forceinline__ float4 load_gates4(const bf16* p) {
     float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
     return make_float4(a.x, a.y, b.x, b.y);
 }
+// the same four activations kept packed (as stored) while they wait in registers: 2 registers instead of 4 in bf16 mode
+template <typename T> struct GateRaw;
+template <> struct GateRaw<float> { float4 v; };
+template <> struct GateRaw<bf16> { uint2 v; };
+__device__ __forceinline__ void load_gates_raw(const float* p, GateRaw<float>& r) { r.v = *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void load_gates_raw(const bf16* p, GateRaw<bf16>& r) { r.v = *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ float4 unpack_gates(const GateRaw<float>& r) { return r.v; }
+__device__ __forceinline__ float4 unpack_gates(const GateRaw<bf16>& r) {
+    float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.v.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ void store_gates4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void store_gates4(bf16* p, float4 v) {
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);

@@ -415,24 +415,19 @@ __device__ __forceinline__ void EpiLstmFwd<T>::direct(const Params& p, int gr, i
     const int u0 = gc >> 2;
     const float cp[8] = {pre.c[0].x, pre.c[0].y, pre.c[0].z, pre.c[0].w, pre.c[1].x, pre.c[1].y, pre.c[1].z, pre.c[1].w};
     float cn[8], hn[8];
-    float4 gt[8];
+    T* gsave = p.gates_out ? p.gates_out + (size_t)gr * G + gc : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float si = sigm<T>(v[4 * j] + pre.add[j].x), tj = tanh_<T>(v[4 * j + 1] + pre.add[j].y);
         float sf = sigm<T>(v[4 * j + 2] + pre.add[j].z + 1.0f), so = sigm<T>(v[4 * j + 3] + pre.add[j].w);
         cn[j] = cp[j] * sf + si * tj;
         hn[j] = tanh_<T>(cn[j]) * so;
-        gt[j] = make_float4(si, tj, sf, so);
+        if (gsave) store_gates4(gsave + 4 * j, make_float4(si, tj, sf, so));      // stored as produced: nothing but c', h' stays live
     }
     const size_t o = (size_t)gr * p.Hp + u0;
     store8(p.c_out + o, cn);
     store8(p.h_out + o, hn);
     if (p.h_outF) store8(p.h_outF + o, hn);
-    if (p.gates_out) {
-        T* g = p.gates_out + (size_t)gr * G + gc;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) store_gates4(g + 4 * j, gt[j]);
-    }
     if (p.hdrop_out) {
         if (p.keep < 1.0f) {
             float4 m0 = dropout_mult4(p.seed, p.stream, p.row_base + gr, p.step, u0, p.keep);
@@ -482,22 +477,28 @@ struct EpiLstmBwd {
     // Direct form: a thread owns one row and a chunk of 8 hidden units of dh_rec (the accumulator columns are units).
     static constexpr bool kDirect = true;
     static constexpr int kUnitsPerChunk = 8;
-    struct Pre { float4 g[8]; float4 cn[2], cp[2], dc[2], dh[2]; };
+    struct Pre { GateRaw<T> g[8]; float4 cn[2], cp[2], dc[2], dh[2]; };   // gates stay packed until used (register pressure of the split-K epilogue)
     struct Params {
         LstmBwdArgs a; T* dg_out;
     };
-    __device__ static void prefetch(const Params& p, int gr, int u0, Pre& pre) {
+    // part 0: everything; 1: what the split-K epilogue fetches before the mainloop ends (gates, dc, dh_ext); 2: the rest (c_new, c_prev),
+    // fetched after the partial tiles have been sent so that fewer registers are live while the 32-column partial is held
+    __device__ static void prefetch(const Params& p, int gr, int u0, Pre& pre, int part = 0) {
         const LstmBwdArgs& a = p.a;
         if (gr >= a.M) return;
         const size_t o = (size_t)gr * a.Hp + u0;
-        const T* g = reinterpret_cast<const T*>(a.gates) + (size_t)gr * 4 * a.Hp + 4 * u0;
+        if (part != 2) {
+            const T* g = reinterpret_cast<const T*>(a.gates) + (size_t)gr * 4 * a.Hp + 4 * u0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pre.g[j] = load_gates4(g + 4 * j);
-        const float4* cn = reinterpret_cast<const float4*>(a.c_new + o); pre.cn[0] = cn[0]; pre.cn[1] = cn[1];
-        const float4* cp = reinterpret_cast<const float4*>(a.c_prev + o); pre.cp[0] = cp[0]; pre.cp[1] = cp[1];
-        const float4* dc = reinterpret_cast<const float4*>(a.dc + o); pre.dc[0] = dc[0]; pre.dc[1] = dc[1];
-        if (a.dh_ext) { const float4* dh = reinterpret_cast<const float4*>(a.dh_ext + o); pre.dh[0] = dh[0]; pre.dh[1] = dh[1]; }
-        else { pre.dh[0] = pre.dh[1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            for (int j = 0; j < 8; ++j) load_gates_raw(g + 4 * j, pre.g[j]);
+            const float4* dc = reinterpret_cast<const float4*>(a.dc + o); pre.dc[0] = dc[0]; pre.dc[1] = dc[1];
+            if (a.dh_ext) { const float4* dh = reinterpret_cast<const float4*>(a.dh_ext + o); pre.dh[0] = dh[0]; pre.dh[1] = dh[1]; }
+            else { pre.dh[0] = pre.dh[1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        }
+        if (part != 1) {
+            const float4* cn = reinterpret_cast<const float4*>(a.c_new + o); pre.cn[0] = cn[0]; pre.cn[1] = cn[1];
+            const float4* cp = reinterpret_cast<const float4*>(a.c_prev + o); pre.cp[0] = cp[0]; pre.cp[1] = cp[1];
+        }
     }
     // v: dh_rec of the 8 units
     __device__ static void direct(const Params& p, int gr, int u0, const float* v, const Pre& pre) {
@@ -513,23 +514,29 @@ struct EpiLstmBwd {
             float4 m1 = dropout_mult4(a.seed, a.stream, a.row_base + gr, a.step, u0 + 4, a.keep);
             dhx[0] *= m0.x; dhx[1] *= m0.y; dhx[2] *= m0.z; dhx[3] *= m0.w; dhx[4] *= m1.x; dhx[5] *= m1.y; dhx[6] *= m1.z; dhx[7] *= m1.w;
         }
-        float dcp[8], dg[32];
+        float dcp[8];
+        T* d = p.dg_out + (size_t)gr * 4 * a.Hp + 4 * u0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float si = pre.g[j].x, tj = pre.g[j].y, sf = pre.g[j].z, so = pre.g[j].w;
-            float dh = v[j] + dhx[j];
-            float tc = tanh_<T>(cn[j]);
-            float d_o = dh * tc;
-            float dc = dcn[j] + dh * so * (1.0f - tc * tc);
-            dcp[j] = dc * sf;
-            dg[4 * j] = dc * tj * si * (1.0f - si);
-            dg[4 * j + 1] = dc * si * (1.0f - tj * tj);
-            dg[4 * j + 2] = dc * cp[j] * sf * (1.0f - sf);
-            dg[4 * j + 3] = d_o * so * (1.0f - so);
+        for (int j2 = 0; j2 < 8; j2 += 2) {      // two units = 8 gate gradients = one 16-byte (bf16) / two 16-byte (fp32) stores, issued as produced
+            float dg[8];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = j2 + jj;
+                const float4 gj = unpack_gates(pre.g[j]);
+                float si = gj.x, tj = gj.y, sf = gj.z, so = gj.w;
+                float dh = v[j] + dhx[j];
+                float tc = tanh_<T>(cn[j]);
+                float d_o = dh * tc;
+                float dc = dcn[j] + dh * so * (1.0f - tc * tc);
+                dcp[j] = dc * sf;
+                dg[4 * jj] = dc * tj * si * (1.0f - si);
+                dg[4 * jj + 1] = dc * si * (1.0f - tj * tj);
+                dg[4 * jj + 2] = dc * cp[j] * sf * (1.0f - sf);
+                dg[4 * jj + 3] = d_o * so * (1.0f - so);
+            }
+            store8(d + 4 * j2, dg);
         }
         store8(a.dc + o, dcp);
-        T* d = p.dg_out + (size_t)gr * 4 * a.Hp + 4 * u0;
-        store8(d, dg); store8(d + 8, dg + 8); store8(d + 16, dg + 16); store8(d + 24, dg + 24);
     }
     template <class Cfg>
     __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {

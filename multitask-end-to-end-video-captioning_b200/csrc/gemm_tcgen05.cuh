@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
             const int t = threadIdx.x - 64;
             const int frow = t / UPR, fc8 = t % UPR;
             typename Epi::Pre pre;
-            Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, pre);
+            Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, pre, 1);
             mbar_wait(tmem_full, 0);
             if (probe && threadIdx.x == 64) probe[4] = gtimer();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
                     st_cluster_f4(base + pos * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
+            Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, pre, 2);
             asm volatile("barrier.cluster.arrive.release;" ::: "memory");
             asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

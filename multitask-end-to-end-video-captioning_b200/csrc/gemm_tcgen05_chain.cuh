@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                 const int t = threadIdx.x - 64;
                 const int frow = t / UPR, fc8 = t % UPR;
                 typename Epi::Pre prf;
-                Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, prf);
+                Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, prf, 1);
                 mbar_wait(tmem_full, s & 1);
                 CHAIN_PROBE(if (probe && threadIdx.x == 128) probe[8 * s + 4] = gtimer());
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                         st_cluster_f4(base + pos * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                 }
+                Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, prf, 2);
                 cluster_sync_all();
                 float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
