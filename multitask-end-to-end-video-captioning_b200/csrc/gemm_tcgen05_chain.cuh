@@ -273,10 +273,12 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
         }
         if constexpr (KS > 1) {
             if (warp < 2) cluster_sync_all();      // pairs with the exchange barrier of the epilogue warps
-            cluster_sync_all();                    // recv buffers may be overwritten by the next step only after everybody has read them
+            // No second cluster barrier: a peer writes into this CTA's recv buffers again only after the NEXT grid barrier, which it
+            // passes only after every CTA -- this one included -- has finished the epilogue that reads them.
         }
     }
     __syncthreads();
+    if constexpr (KS > 1) cluster_sync_all();      // nobody leaves while a peer may still be reading its exchange buffers
     if constexpr (CX > 1) cluster_sync_all();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
