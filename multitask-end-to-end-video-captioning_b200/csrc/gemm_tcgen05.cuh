@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
         for (int i = 0; i < KBL; ++i) {
             const int s = i % C::STAGES;
             mbar_wait(full + s, (i / C::STAGES) & 1);
+            if (i == 0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (probe && i == 0 && leader) probe[2] = gtimer();
             const uint32_t a = smem_u32(smem + s * C::STAGE_BYTES);
             const uint64_t adesc = MN ? make_desc_mn(a) : make_desc(a), bdesc = MN ? make_desc_mn(a + C::A_BYTES) : make_desc(a + C::A_BYTES);
