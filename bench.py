@@ -27,10 +27,9 @@ GOLD = os.path.join(ROOT, 'tests', 'golden')
 DIMS = dict(D=1536, E=500, H=1000, V=9972)
 METRIC = 'reinforce_train_videos_per_s'
 # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the persistent chain kernels at the bench configuration, keyed by
-# (rows, N, K) (profiles/r1_tc_metrics.md)
-STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = {(320, 1024, 4096): 799710000, (320, 4096, 1024): 1189090000,
-                                     (64, 4096, 1024): 119510000, (64, 1024, 4096): 163300000}
-
+# (rows, N, K) (profiles/r1_chain_ncu_full_f.md; the two 64-row forward chains -- 115 and 80 steps -- are averaged)
+STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = {(320, 1024, 4096): 790878208, (320, 4096, 1024): 1189724160,
+                                     (64, 4096, 1024): 123086336, (64, 1024, 4096): 170185472}
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -383,7 +382,7 @@ def run_b200(args):
                       'BasicLSTMCell %s, grid barrier between steps)' % (dname, dM, dN, dK, 'backward' if dK > dN else 'forward'),
             'bound': 'hbm', 'achieved': d_ach, 'peak': hbm, 'unit': 'GB/s', 'frac': d_ach / hbm if hbm else None,
             'traffic': STEP_KERNEL_DRAM_BYTES_PER_LAUNCH.get((dM, dN, dK)),
-            'traffic_source': 'ncu dram__bytes_read+write per launch, cache flushed (profiles/r1_tc_metrics.md)',
+            'traffic_source': 'ncu --set full dram__bytes_read+write per launch, cold caches (profiles/r1_chain_ncu_full_f.md)',
             'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)',
             'launches_per_step': dln / args.steps, 'recurrent_steps_per_launch': dcnt / dln if dln else None,
             'us_per_launch': 1e3 * dms / dln if dln else None, 'ms_per_step': dms / args.steps,
