@@ -260,18 +260,34 @@ struct EpiLogitsPick {
                     }
                     cut = mx - 22.0f;
                 }
-                for (int c = cb; c < cb + PW; c += 4) {
-                    float4 x = *reinterpret_cast<const float4*>(row + c), b = *reinterpret_cast<const float4*>(p.bias + n0 + c);
-                    float e[4] = {x.x + b.x, x.y + b.y, x.z + b.z, x.w + b.w};
+                // up to 16 words per iteration: the Philox blocks are independent, so their 10-round multiply chains overlap (one block at
+                // a time left the warp waiting on its own dependent instructions -- issue slots 36 % busy in the ncu capture).  Noise is
+                // still skipped for groups that cannot win; adding it to hopeless words of a live group cannot change the winner.
+                constexpr int CH = PW % 16 == 0 ? 16 : (PW % 8 == 0 ? 8 : 4), NG = CH / 4;
+                for (int c = cb; c < cb + PW; c += CH) {
+                    float e[CH];
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const float4 x = *reinterpret_cast<const float4*>(row + c + 4 * g), b = *reinterpret_cast<const float4*>(p.bias + n0 + c + 4 * g);
+                        e[4 * g] = x.x + b.x; e[4 * g + 1] = x.y + b.y; e[4 * g + 2] = x.z + b.z; e[4 * g + 3] = x.w + b.w;
+                    }
                     if (sample) {
-                        if (fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])) < cut) continue;
-                        uint4 o = philox4x32_10((uint32_t)((n0 + c) >> 2), p.step, p.row_base + (uint32_t)gr, S2VT_STREAM_SAMPLE, (uint32_t)p.seed,
-                                                (uint32_t)(p.seed >> 32));
-                        e[0] += gumbel_fast(u32_to_uniform(o.x)); e[1] += gumbel_fast(u32_to_uniform(o.y));
-                        e[2] += gumbel_fast(u32_to_uniform(o.z)); e[3] += gumbel_fast(u32_to_uniform(o.w));
+                        float gm = e[0];
+#pragma unroll
+                        for (int k = 1; k < CH; ++k) gm = fmaxf(gm, e[k]);
+                        if (gm < cut) continue;
+                        uint4 o[NG];
+#pragma unroll
+                        for (int g = 0; g < NG; ++g)
+                            o[g] = philox4x32_10((uint32_t)((n0 + c + 4 * g) >> 2), p.step, p.row_base + (uint32_t)gr, S2VT_STREAM_SAMPLE, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            e[4 * g] += gumbel_fast(u32_to_uniform(o[g].x)); e[4 * g + 1] += gumbel_fast(u32_to_uniform(o[g].y));
+                            e[4 * g + 2] += gumbel_fast(u32_to_uniform(o[g].z)); e[4 * g + 3] += gumbel_fast(u32_to_uniform(o[g].w));
+                        }
                     }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < CH; ++k)
                         if (n0 + c + k < p.V) { ArgVal cand; cand.v = e[k]; cand.i = n0 + c + k; best = argmax_op(best, cand); }
                 }
             }

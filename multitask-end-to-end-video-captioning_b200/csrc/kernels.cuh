@@ -214,13 +214,10 @@ __global__ void __launch_bounds__(ROW_THREADS) softmax_rows_kernel(const float* 
         int v4 = threadIdx.x + i * ROW_THREADS;
         if (v4 * 4 < Vp) {
             int v = v4 * 4;
-            float e[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+            float e[4] = {x[i].x, x[i].y, x[i].z, x[i].w}, d[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float d = 0.f;
-                if (v + k < V) d = a * expf(e[k] - lse) - (v + k == w ? b : 0.f) - c;
-                dr[v + k] = from_f32<T>(d);
-            }
+            for (int k = 0; k < 4; ++k) d[k] = v + k < V ? a * expf(e[k] - lse) - (v + k == w ? b : 0.f) - c : 0.f;
+            store_gates4(dr + v, make_float4(d[0], d[1], d[2], d[3]));      // one 8-byte (bf16) / 16-byte (fp32) store instead of four scalar ones
         }
     }
 }
