@@ -37,7 +37,8 @@ def reference_run():
     return _run('mma_sync')
 
 
-@pytest.mark.parametrize('backend', ['auto', 'tcgen05_n128', 'tcgen05_mc2x2', 'step_mc8', 'step_n64', 'wgrad_transposed', 'per_step', 'chain_ring'])
+@pytest.mark.parametrize('backend', ['auto', 'tcgen05_n128', 'tcgen05_mc2x2', 'step_mc8', 'step_n64', 'wgrad_transposed', 'per_step', 'chain_ring', 'chain_mc4',
+                                     'chain_nomc'])
 def test_tcgen05_variants_match_mma_sync(backend, reference_run):
     ref, got = reference_run, _run(backend)
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
@@ -49,6 +50,14 @@ def test_tcgen05_variants_match_mma_sync(backend, reference_run):
         assert abs(got['loss'] - ref['loss']) < 2e-3 * max(1.0, abs(ref['loss']))
         assert rel(got['grads'], ref['grads']) < 2e-2
         assert rel(got['params'], ref['params']) < 1e-3
+
+
+def test_full_size_multicast_chain_equals_plain_chain():
+    """64 rows, H=1000: weights-stationary chains with the activation rows multicast over clusters of 4 vs without."""
+    dims = dict(D=1536, E=500, H=1000, V=9972)
+    a = _run('chain_mc4', dims, 5, 35, 64, 2)
+    b = _run('chain_nomc', dims, 5, 35, 64, 2)
+    assert torch.equal(a['greedy'], b['greedy']) and torch.equal(a['samp'], b['samp']) and torch.equal(a['logits'], b['logits'])
 
 
 def test_full_size_chain_equals_per_step_launches():

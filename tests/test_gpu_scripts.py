@@ -139,3 +139,27 @@ def test_attention_and_alternative_reward_scripts(tiny, monkeypatch):
     for reward in ('bleu4', 'rouge'):
         cli.run_rl(_args(dict(model_name='rl_' + reward, n_samples=2, start_learning_rate=1e-4, clip_norm=5.0, reward=reward), d, D, Tv))
         assert os.path.exists(str(d / 'models' / ('rl_%s-0.npz' % reward)))
+
+
+def test_feature_pipe_stages_batches_ahead():
+    """trainer.FeaturePipe: slots are filled on the copy stream, handed out in order, and refuse to be over-filled."""
+    import s2vt_b200
+    pipe = s2vt_b200.trainer.FeaturePipe('cuda:0', 4, 3, 8)
+    hosts = [torch.full((4, 3, 8), float(i)).pin_memory() for i in range(5)]
+    idx = [torch.full((4,), i, dtype=torch.int32).pin_memory() for i in range(5)]
+    pipe.put(hosts[0], idx[0]); pipe.put(hosts[1], idx[1])
+    with pytest.raises(RuntimeError):
+        pipe.put(hosts[2], idx[2])
+    for i in range(5):
+        v, vi, slot = pipe.get()
+        out = (v.sum() + vi.sum()).item()                       # consume on the compute stream
+        pipe.release(slot)
+        assert out == i * 96 + i * 4
+        if i + 2 < 5:
+            pipe.put(hosts[i + 2], idx[i + 2])
+    with pytest.raises(RuntimeError):
+        pipe.get()
+    short = torch.ones(2, 3, 8).pin_memory()                     # ragged last batch
+    pipe.put(short, torch.zeros(2, dtype=torch.int32))
+    v, vi, slot = pipe.get()
+    assert tuple(v.shape) == (2, 3, 8) and tuple(vi.shape) == (2,)
