@@ -173,7 +173,7 @@ extern "C" int s2vt_set_reuse_frontend(s2vt_handle* h, int enable) {
     return 0;
 }
 extern "C" void s2vt_destroy(s2vt_handle* h) {
-    if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_refresh); }
+    if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_refresh); cudaEventDestroy(h->ev_wo); }
     if (h && h->tc_cache) delete static_cast<tc::MapCache*>(h->tc_cache);
     delete h;
 }
@@ -465,6 +465,7 @@ static int ensure_side(s2vt_handle* h) {
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_refresh, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_wo, cudaEventDisableTiming));
     return 0;
 }
 // The "late" half of a refresh (everything but the frame projection / LSTM1 forward weights) runs on the side stream;
@@ -859,6 +860,10 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         TRY(bias_grad<T>(h, s2, p.dlogits, Vp, Vp, MD, V, 0, h->G_(h->ibo)));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
+    // Data-parallel hook: in the REINFORCE objective nothing touches these two gradients again (no weight decay, no accumulation
+    // pass), so a caller may start their all-reduce now, under the BPTT chains (s2vt_grad_segment_ready).
+    h->wo_grad_early = mode == 0 && !accumulate && grad_scale == 1.f;
+    if (h->wo_grad_early) CUDA_TRY(h, cudaEventRecord(h->ev_wo, s2));
     // LSTM2 BPTT
     CUDA_TRY(h, cudaMemsetAsync(p.dc2, 0, (size_t)N * Hp * sizeof(float), st));
     {
@@ -1031,6 +1036,17 @@ extern "C" int s2vt_attribute_backward(s2vt_handle* h, const float* video, int B
 }
 
 // ---- optimiser ----------------------------------------------------------------------------------------------------
+extern "C" int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int64_t* offset, int64_t* count) {
+    if (!h || !h->bound) return S2VT_ESTATE;
+    if (segment != 0 || !offset || !count) return h->fail(S2VT_EINVAL, "segment 0 (embed_word_W, embed_word_b) is the only early segment");
+    if (!h->wo_grad_early || !h->ev_wo) return h->fail(S2VT_ESTATE, "the last backward call did not finish this segment early");
+    CUDA_TRY(h, cudaStreamWaitEvent((cudaStream_t)stream, h->ev_wo, 0));
+    *offset = (int64_t)h->vars[h->iWo].off;
+    *count = (int64_t)(h->vars[h->iWo].count() + h->vars[h->ibo].count());
+    h->wo_grad_early = false;      // one hand-out per backward call
+    return S2VT_OK;
+}
+
 extern "C" int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int flags, float* gnorm_out, s2vt_stream st_) {
     const int wemb_slice_norm = flags & 1, normalize = (flags >> 1) & 1;
     if (!h || !h->bound) return S2VT_ESTATE;

@@ -226,6 +226,16 @@ class Video_Caption_Generator(object):
         self._check(self.lib.s2vt_optimizer_step(self.h, float(lr), float(clip_norm), self.adam_step, flags, _ptr(out), _stream()))
         return out
 
+    def grad_segment_ready(self, stream, segment=0):
+        """Make `stream` (torch.cuda.Stream) wait until the early-final gradient segment of the last rl_backward is complete; returns
+        (offset, count) in floats inside `self.grads`, or None when the last backward gives no early segment."""
+        off, cnt = C.c_int64(), C.c_int64()
+        rc = self.lib.s2vt_grad_segment_ready(self.h, int(segment), C.c_void_p(stream.cuda_stream), C.byref(off), C.byref(cnt))
+        if rc == _lib.S2VT_ESTATE:
+            return None
+        self._check(rc)
+        return off.value, cnt.value
+
     def set_reuse_frontend(self, enable=True):
         """Share the LSTM1 forward of a rollout with the training call that follows on the same video tensor."""
         self._check(self.lib.s2vt_set_reuse_frontend(self.h, int(bool(enable))))

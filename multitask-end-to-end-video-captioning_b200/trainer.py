@@ -25,16 +25,36 @@ def exponential_decay(lr0, global_step, decay_steps, rate=0.5):
     return lr0 * rate ** (global_step // decay_steps)
 
 
-def allreduce_gradients(model, bucket_bytes=32 << 20):
-    """Sum the flat fp32 gradient block (+ aux slots: slice norm, loss, sum(mask)) over the ranks.  Buckets are
-    launched back to back on NCCL's stream so the first ones overlap the tail of the previous kernels."""
+_AR_STREAMS = {}
+
+
+def allreduce_gradients(model, bucket_bytes=32 << 20, overlap=True):
+    """Sum the flat fp32 gradient block (+ aux slots: slice norm, loss, sum(mask)) over the ranks.
+
+    overlap: the gradients of embed_word_W / embed_word_b (a third of the bytes) are final before the BPTT chains start; their
+    all-reduce is enqueued on a stream that waits for exactly that point (`s2vt_grad_segment_ready`), so it runs under the chains.
+    The remaining ranges follow in buckets launched back to back once the backward call has finished."""
     rank, world = _world()
     if world == 1:
         return
     g = model.grads
     n = g.numel()
     step = max(1, bucket_bytes // 4)
-    works = [dist.all_reduce(g[i:min(n, i + step)], op=dist.ReduceOp.SUM, async_op=True) for i in range(0, n, step)]
+    works, ranges = [], [(0, n)]
+    if overlap and g.is_cuda and hasattr(model, 'grad_segment_ready'):
+        dev = g.device
+        st = _AR_STREAMS.get(dev)
+        if st is None:
+            st = _AR_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        seg = model.grad_segment_ready(st)
+        if seg is not None:
+            off, cnt = seg
+            with torch.cuda.stream(st):
+                works.append(dist.all_reduce(g[off:off + cnt], op=dist.ReduceOp.SUM, async_op=True))
+            ranges = [(0, off), (off + cnt, n)]
+    for lo, hi in ranges:
+        for i in range(lo, hi, step):
+            works.append(dist.all_reduce(g[i:min(hi, i + step)], op=dist.ReduceOp.SUM, async_op=True))
     for w in works:
         w.wait()
 
