@@ -381,12 +381,11 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += w[j];
                 }
-                const uint32_t base = cluster_map(smem_u32(recv), (uint32_t)q) + (uint32_t)(((rank * 32 + lane) * BN) * 4);
+                // exchange layout [source rank][16-byte column group][row]: one store instruction of a warp covers 512 contiguous bytes
+                const uint32_t base = cluster_map(smem_u32(recv), (uint32_t)q) + (uint32_t)(((rank * (BN / 4) + (c0 >> 2)) * 32) * 16);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int pos = ((c0 >> 2) + j) ^ (lane & 7);
-                    st_cluster_f4(base + pos * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                }
+                for (int j = 0; j < 8; ++j)      // row slot XOR-ed with the 8-unit group index: the reducer's 16 lanes of a row then spread over the banks
+                        st_cluster_f4(base + j * 512 + ((lane ^ ((((c0 >> 2) + j) >> 1) & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             Epi::prefetch(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, pre, 2);
             asm volatile("barrier.cluster.arrive.release;" ::: "memory");
@@ -394,9 +393,8 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __gr
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int src = 0; src < KS; ++src) {
-                const float* rp = recv + (src * 32 + frow) * BN;
-                const float4 x0 = *reinterpret_cast<const float4*>(rp + (((2 * fc8) ^ (frow & 7)) << 2));
-                const float4 x1 = *reinterpret_cast<const float4*>(rp + (((2 * fc8 + 1) ^ (frow & 7)) << 2));
+                const float4* rp = reinterpret_cast<const float4*>(recv) + (src * (BN / 4) + 2 * fc8) * 32 + (frow ^ (fc8 & 7));
+                const float4 x0 = rp[0], x1 = rp[32];
                 acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w; acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
             }
             Epi::direct(ep, m0 + 32 * rank + frow, n0 + 8 * fc8, acc, pre);
