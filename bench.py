@@ -45,6 +45,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-backend', default='auto')
     ap.add_argument('--overlap', type=int, default=-1, help='debug: side-stream overlap mask (s2vt_set_overlap)')
+    ap.add_argument('--workload', default='train', choices=['train', 'beam'],
+                    help="train: the REINFORCE iteration (headline metric); beam: BASELINE config 5, the beam-5 captioning sweep over batch 1..1024")
+    ap.add_argument('--beam-batches', default='1,2,4,8,16,32,64,128,256,512,1024')
     ap.add_argument('--quick', action='store_true', help='timed region only (for ncu launch lists): no e2e / roofline / CPU passes')
     return ap.parse_args()
 
@@ -218,6 +221,108 @@ def _claim_stdout():
     return os.fdopen(keep, 'w')
 
 
+def beam_sweep(s2vt_b200, torch, dist, args, bias, rank, world, batches, reps=3):
+    """BASELINE config 5 (e2e_beam_search.py after the CNN / final_beam_search.py): beam-5 captioning, length normalisation 1, of
+    `batch` videos per call, sharded over the ranks with no collective (decode paths are independent videos).
+    Device-resident features (`ms`) and host feeds (`e2e_ms`: pinned features -> device, sentences / lengths / scores -> host
+    inside the timed region), CUDA events, max over ranks."""
+    Tv = args.frames
+    per_max = (max(batches) + world - 1) // world
+    model = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=per_max,
+                                              n_video_lstm_step=Tv, n_caption_lstm_step=35, bias_init_vector=bias, dropout_rate=1.0, beam_size=5,
+                                              precision=args.precision, max_videos=per_max, max_rows=min(per_max, 64), seed=4,
+                                              gemm_backend=args.gemm_backend)
+    if args.overlap >= 0:
+        model.lib.s2vt_set_overlap(model.h, args.overlap)
+    model.variable('embed_word_W').mul_(3.0)
+    model.refresh()
+    host = torch.from_numpy(features(per_max, Tv, 99 + rank)).pin_memory()
+    dev = host.cuda()
+    rows = []
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / reps
+
+    for b in batches:
+        lo, hi = min(b, rank * ((b + world - 1) // world)), min(b, (rank + 1) * ((b + world - 1) // world))
+        n = hi - lo                      # this rank's videos of the batch (ranks beyond the batch idle)
+
+        def resident():
+            if n:
+                model.beam_search(dev[:n], 5, 1.0)
+
+        def fed():
+            if n:
+                out = model.beam_search(host[:n].cuda(non_blocking=True), 5, 1.0)
+                return [x.cpu() for x in out]
+
+        for _ in range(2):
+            resident()
+        ms = timed(resident)
+        fed()
+        ms_e2e = timed(fed)
+        rows.append({'batch': b, 'ms': ms, 'captions_per_s': b / (ms / 1e3), 'e2e_ms': ms_e2e, 'e2e_captions_per_s': b / (ms_e2e / 1e3)})
+    del model
+    return rows
+
+
+def run_beam(args):
+    """`--workload beam`: one JSON line for the secondary BASELINE metric (beam-5 decode captions/s), value = the largest batch."""
+    out_stream = _claim_stdout()
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1')); local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import s2vt_b200
+    vocab, by, order = load_corpus()
+    _, bias = peaked_bias(vocab, by)
+    batches = [int(x) for x in args.beam_batches.split(',')]
+    sampler = ClockSampler(local)
+    sampler.start()
+    rows = beam_sweep(s2vt_b200, torch, dist, args, bias, rank, world, batches, reps=max(args.steps, 3))
+    clocks = sampler.stop()
+    if rank == 0:
+        top = max(rows, key=lambda r: r['batch'])
+        Tv = args.frames
+        out = {'metric': 'beam5_decode_captions_per_s', 'value': top['captions_per_s'], 'unit': 'captions/s', 'n_gpus': world,
+               'steps': max(args.steps, 3), 'warmup': 2, 'ms_per_step': top['ms'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+               'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+               'config': {'workload': 'beam-5 captioning sweep (BASELINE config 5): batch %d videos per call split over the GPUs, T_v=%d, '
+                                      'length_normalization_factor 1, precomputed [B, T_v, 1536] features' % (top['batch'], Tv),
+                          'beam_size': 5, 'T_v': Tv, 'T_c': 35, 'n_words': DIMS['V'], 'lstm_dim': DIMS['H'], 'parallelism': 'dp%d' % world,
+                          'l2': 'no explicit flush: every call streams its own activations; weights (83 MB bf16) are meant to stay L2-resident'},
+               'clocks': clocks,
+               'e2e': {'value': top['e2e_captions_per_s'], 'unit': 'captions/s', 'h2d_bytes_per_step': top['batch'] * Tv * DIMS['D'] * 4,
+                       'd2h_bytes_per_step': top['batch'] * (35 + 3) * 4},
+               'sweep': rows}
+        print(json.dumps(out), file=out_stream, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200(args):
     out_stream = _claim_stdout()
     import torch
@@ -358,6 +463,10 @@ def run_b200(args):
             sc.score_ids(ids, rows)
             rw[name + '_us_per_%d_hyps' % ids.shape[0]] = 1e3 * timed(20, lambda: sc.score_ids(ids, rows)) / 20
         beam['reward_kernels'] = rw
+        del feats32
+        torch.cuda.empty_cache()
+        # BASELINE config 5: latency vs throughput of beam-5 captioning over the batch size (one GPU here; `--workload beam` shards it)
+        beam['beam5_sweep'] = beam_sweep(s2vt_b200, torch, dist, args, bias, rank, world, [int(x) for x in args.beam_batches.split(',')])
     if rank != 0:
         return
     peaks = {}
@@ -426,5 +535,7 @@ if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.workload == 'beam':
+        run_beam(a)
     else:
         run_b200(a)

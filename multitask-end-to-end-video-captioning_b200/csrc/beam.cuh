@@ -35,9 +35,7 @@ struct BeamState {
 
 // One thread per video: consume the top-k words of each live parent (rows j*B+b, already in descending score
 // order), update finals / exclude_num, and select the next k live beams.
-__global__ void beam_update_kernel(BeamState s, const int* __restrict__ top_idx, const float* __restrict__ top_lp, int step, int cur, double lnf) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= s.B) return;
+__device__ void beam_update_one(const BeamState& s, const int* top_idx, const float* top_lp, int step, int cur, double lnf, int b) {
     const int k = s.k, B = s.B, Tc = s.Tc;
     if (s.done[b]) { s.nlive[b] = 0; return; }
     double c_score[BEAM_MAXK * BEAM_MAXK];
@@ -94,6 +92,75 @@ __global__ void beam_update_kernel(BeamState s, const int* __restrict__ top_idx,
     }
     s.nlive[b] = taken;
     if (excl >= k) s.done[b] = 1;
+}
+__global__ void beam_update_kernel(BeamState s, const int* __restrict__ top_idx, const float* __restrict__ top_lp, int step, int cur, double lnf) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < s.B) beam_update_one(s, top_idx, top_lp, step, cur, lnf, b);
+}
+
+// Fused beam step (default): one CTA per video.
+//   1. warp j merges the per-part candidates of EpiLogitsTopK for live parent j: lse over the parts' (max, sum) pairs, then k
+//      rounds of warp arg-max, round q taking the best candidate that comes strictly after round q-1's winner in the
+//      (value descending, index ascending) order -- so no "taken" list is needed and ties resolve like tf.nn.top_k;
+//   2. thread 0 runs the reference's bookkeeping for the video (beam_update_one);
+//   3. the whole CTA copies the LSTM2 state rows of the chosen parents into the rows of their children (a video's children only
+//      ever descend from that video's parents, so no grid-wide dependency exists).
+static_assert(BEAM_MAXK == TOPK_MAX, "EpiLogitsTopK keeps BEAM_MAXK candidates per part");
+template <typename T>
+__global__ void __launch_bounds__(32 * BEAM_MAXK) beam_step_kernel(BeamState s, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
+                                                                   const float2* __restrict__ stat, int nparts, int V, int* top_idx, float* top_lp,
+                                                                   int step, int cur, double lnf, const T* __restrict__ h_new, T* __restrict__ h_next,
+                                                                   const float* __restrict__ c_new, float* __restrict__ c_next, int Hp) {
+    const int b = blockIdx.x, B = s.B, k = s.k;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nl = s.done[b] ? 0 : s.nlive[b];
+    if (warp < nl) {
+        const int row = warp * B + b;
+        const float2* sp = stat + (size_t)row * nparts;
+        float mx = -INFINITY;
+        for (int q = lane; q < nparts; q += 32) mx = fmaxf(mx, sp[q].x);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
+        for (int q = lane; q < nparts; q += 32) { const float2 t = sp[q]; se += t.y * expf(t.x - mx); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        const float lse = mx + logf(se);
+        const float* cv = cand_val + (size_t)row * nparts * BEAM_MAXK;
+        const int* ci = cand_idx + (size_t)row * nparts * BEAM_MAXK;
+        const int nc = nparts * BEAM_MAXK;
+        ArgVal prev; prev.v = INFINITY; prev.i = -1;
+        for (int j = 0; j < k; ++j) {
+            ArgVal best; best.v = -INFINITY; best.i = 0x7fffffff;
+            for (int c = lane; c < nc; c += 32) {
+                ArgVal x; x.v = cv[c]; x.i = ci[c];
+                const bool after = x.v < prev.v || (x.v == prev.v && x.i > prev.i);
+                if (after && x.i < V) best = argmax_op(best, x);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ArgVal t;
+                t.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+                t.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+                best = argmax_op(best, t);
+            }
+            if (lane == 0) { top_idx[row * k + j] = best.i; top_lp[row * k + j] = best.v - lse; }
+            prev = best;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) beam_update_one(s, top_idx, top_lp, step, cur, lnf, b);
+    __syncthreads();
+    constexpr int HV = 16 / sizeof(T);
+    for (int j = 0; j < k; ++j) {
+        const int row = j * B + b, prow = s.parent[row] * B + b;
+        const uint4* hs = reinterpret_cast<const uint4*>(h_new + (size_t)prow * Hp);
+        uint4* hd = reinterpret_cast<uint4*>(h_next + (size_t)row * Hp);
+        for (int c = threadIdx.x; c < Hp / HV; c += blockDim.x) hd[c] = hs[c];
+        const float4* cs = reinterpret_cast<const float4*>(c_new + (size_t)prow * Hp);
+        float4* cd = reinterpret_cast<float4*>(c_next + (size_t)row * Hp);
+        for (int c = threadIdx.x; c < Hp / 4; c += blockDim.x) cd[c] = cs[c];
+    }
 }
 
 // next-step LSTM2 state rows: out[j*B+b] = in[parent[j*B+b]*B + b]
@@ -153,6 +220,13 @@ static int beam_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B,
     tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2_final, B, R, Hp, r.h2r[0]); KCHECK(h);
     tile_rows_kernel<float><<<R, 256, 0, st>>>(r.c2e[Tv & 1], B, R, Hp, r.c2r[0]); KCHECK(h);
     int cur = 0;   // sentence ping-pong index
+    // fused step (default; s2vt_set_overlap bit 3 keeps the un-fused launches as the A/B checker): the candidate arrays live in
+    // the logits buffer, which the fused path never writes (nparts * (2 * BEAM_MAXK + 2) floats per row < Vp)
+    const bool fused = !(h->overlap & 8);
+    const int nparts = Vp / (logits_tile_bn<T>(h) / EpiLogitsTopK<T>::PARTS);
+    float* cand_val = r.logits;
+    int* cand_idx = reinterpret_cast<int*>(cand_val + (size_t)R * nparts * BEAM_MAXK);
+    float2* cand_stat = reinterpret_cast<float2*>(cand_idx + (size_t)R * nparts * BEAM_MAXK);
     for (int i = 0; i < Tc; ++i) {
         const int t = Tv + i;
         const int rows = i == 0 ? B : R;
@@ -162,6 +236,16 @@ static int beam_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B,
         ep.add1 = h->Etab; ep.tok = s.tok;
         ep.c_prev = r.c2r[0]; ep.c_out = r.c2r[1]; ep.h_out = r.h2r[1]; ep.keep = 1.f;
         TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, r.h2r[0], Hp, h->W2hT, Hp, rows, Gp, Hp, ep)));
+        if (fused) {
+            // :213-217 logits -> softmax -> top_k, fused: per-part candidates + soft-max statistics instead of the [rows, V] logits
+            typename EpiLogitsTopK<T>::Params el = {rows, h->V, h->bo_p, cand_val, cand_idx, cand_stat, nparts};
+            TRY((gemm<T, CfgBig, EpiLogitsTopK<T>>(h, st, r.h2r[1], Hp, h->WoT, Hp, rows, Vp, Hp, el)));
+            beam_step_kernel<T><<<B, 32 * BEAM_MAXK, 0, st>>>(s, cand_val, cand_idx, cand_stat, nparts, h->V, top_idx, top_lp, i, cur, (double)lnf,
+                                                             r.h2r[1], r.h2r[0], r.c2r[1], r.c2r[0], Hp); KCHECK(h);
+            h->launches++;
+            cur ^= 1;
+            continue;
+        }
         typename EpiStore<T>::Params el = {r.logits, nullptr, Vp, h->bo_p, rows, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, r.h2r[1], Hp, h->WoT, Hp, rows, Vp, Hp, el)));
         topk_rows_kernel<<<rows, ROW_THREADS, 0, st>>>(r.logits, Vp, h->V, k, top_idx, top_lp); KCHECK(h);

@@ -306,6 +306,72 @@ struct EpiLogitsPick {
     }
 };
 
+// Vocabulary projection fused with the beam step's word ranking (final_beam_search.py:213-217: softmax + top_k): the
+// logits never reach HBM.  A tile row is scanned in PARTS column parts; each part emits its TOPK_MAX best words in
+// (value descending, index ascending) order -- tf.nn.top_k's order -- and its soft-max statistics (max, sum exp(l - max)).
+// beam_step_kernel merges the parts: a row's top-k words are among the parts' top-k, and lse = log sum_p s_p e^{m_p}.
+#define TOPK_MAX 8
+template <typename T>
+struct EpiLogitsTopK {
+    static constexpr bool kDirect = false;
+    static constexpr int PARTS = 4;
+    struct Params {
+        int M, V; const float* bias;
+        float* cand_val; int* cand_idx;   // [M, nparts, TOPK_MAX]
+        float2* stat;                     // [M, nparts]
+        int nparts;                       // Vp / (BN / PARTS)
+    };
+    static constexpr int kEpiWarps = 16;
+    template <class Cfg>
+    __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
+        constexpr int PW = Cfg::BN / PARTS;
+        static_assert(PW % 4 == 0, "part width");
+        for (int u = threadIdx.x; u < Cfg::BM * PARTS; u += Cfg::NTHREADS) {
+            const int r = u % Cfg::BM, part = u / Cfg::BM, gr = m0 + r;   // consecutive threads -> consecutive rows
+            if (gr >= p.M) continue;
+            const int c0 = n0 + part * PW;                                // first word of the part
+            const float* row = Cs + r * Cfg::LDC + part * PW;
+            const float* bias = p.bias + c0;
+            float mx = -INFINITY;
+            for (int c = 0; c < PW; c += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(row + c), b = *reinterpret_cast<const float4*>(bias + c);
+                if (c0 + c + 0 < p.V) mx = fmaxf(mx, x.x + b.x);
+                if (c0 + c + 1 < p.V) mx = fmaxf(mx, x.y + b.y);
+                if (c0 + c + 2 < p.V) mx = fmaxf(mx, x.z + b.z);
+                if (c0 + c + 3 < p.V) mx = fmaxf(mx, x.w + b.w);
+            }
+            float tv[TOPK_MAX]; int ti[TOPK_MAX];
+#pragma unroll
+            for (int q = 0; q < TOPK_MAX; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
+            float se = 0.f;
+            for (int c = 0; c < PW; c += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(row + c), b = *reinterpret_cast<const float4*>(bias + c);
+                const float e[4] = {x.x + b.x, x.y + b.y, x.z + b.z, x.w + b.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (c0 + c + k >= p.V) continue;
+                    se += expf(e[k] - mx);
+                    if (e[k] > tv[TOPK_MAX - 1]) {          // ascending scan + strict compares: the lower index stays ahead on ties
+                        tv[TOPK_MAX - 1] = e[k]; ti[TOPK_MAX - 1] = c0 + c + k;
+#pragma unroll
+                        for (int q = TOPK_MAX - 1; q > 0; --q)
+                            if (tv[q] > tv[q - 1]) {
+                                const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
+                                const int fi = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = fi;
+                            }
+                    }
+                }
+            }
+            const size_t o = (size_t)gr * p.nparts + c0 / PW;
+            float4* cv = reinterpret_cast<float4*>(p.cand_val + o * TOPK_MAX);
+            int4* ci = reinterpret_cast<int4*>(p.cand_idx + o * TOPK_MAX);
+            cv[0] = make_float4(tv[0], tv[1], tv[2], tv[3]); cv[1] = make_float4(tv[4], tv[5], tv[6], tv[7]);
+            ci[0] = make_int4(ti[0], ti[1], ti[2], ti[3]); ci[1] = make_int4(ti[4], ti[5], ti[6], ti[7]);
+            p.stat[o] = make_float2(mx, se);
+        }
+    }
+};
+
 // Weight-gradient store into the fp32 TF-layout gradient block:  grad[(row0 + r) * ldg + colmap(c)] += scale * acc.
 // gate_h > 0 : columns are in packed gate order (c = 4u+g) and map to the TF order g*gate_h + u (u < gate_h).
 // gate_h == 0: identity columns, valid while c < ncols.   Rows valid while r < nrows.

@@ -160,7 +160,8 @@ extern "C" int s2vt_debug_probe(void* device_buffer) {
     unsigned long long* p = (unsigned long long*)device_buffer;
     return cudaMemcpyToSymbol(tc::g_probe, &p, sizeof p) == cudaSuccess ? 0 : S2VT_ECUDA;
 }
-// Debug / tuning: which independent pieces run on the internal side stream (bit 0 late refresh, 1 dWo, 2 LSTM1 backward).
+// Debug / tuning: which independent pieces run on the internal side stream (bit 0 late refresh, 1 dWo, 2 LSTM1 backward);
+// bit 3 keeps beam search on its un-fused step (materialised logits, separate top-k / update / gather launches).
 extern "C" int s2vt_set_overlap(s2vt_handle* h, int mask) {
     if (!h) return S2VT_EINVAL;
     h->overlap = mask;
@@ -631,6 +632,13 @@ static int run_encoder(s2vt_handle* h, cudaStream_t st, const float* video, int 
     return 0;
 }
 
+// tile width the vocabulary-projection GEMM will use (decides how many candidates per row the fused pick / top-k epilogues produce)
+template <typename T>
+static int logits_tile_bn(const s2vt_handle* h) {
+    const bool tc_path = std::is_same<T, bf16>::value && h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC;
+    return tc_path && h->cfg.gemm_backend != 3 && h->cfg.gemm_backend != 4 && h->Vp % 256 == 0 ? 256 : 128;
+}
+
 template <typename T>
 static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B, int K, uint64_t seed, uint32_t row_base, int32_t* sampled_out,
                         int32_t* greedy_out) {
@@ -646,9 +654,7 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
     tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2_final, B, R, Hp, r.h2r[0]); KCHECK(h);
     tile_rows_kernel<float><<<R, 256, 0, st>>>(r.c2e[Tv & 1], B, R, Hp, r.c2r[0]); KCHECK(h);
     fill_int_kernel<<<(R + 255) / 256, 256, 0, st>>>(r.tok[0], R, 1); KCHECK(h);   // <bos> = 1 (:321-323)
-    // tile width the vocabulary-projection GEMM will use (decides how many candidates per row the fused pick produces)
-    const bool tc_path = std::is_same<T, bf16>::value && h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC;
-    const int logits_bn = tc_path && h->cfg.gemm_backend != 3 && h->cfg.gemm_backend != 4 && Vp % 256 == 0 ? 256 : 128;
+    const int logits_bn = logits_tile_bn<T>(h);
     const int nt = Vp / logits_bn;
     for (int i = 0; i < Tc; ++i) {
         const int t = Tv + i;

@@ -171,3 +171,32 @@ def test_beam_search_bf16_runs_and_mostly_agrees():
     same = sum(sent[v, :lens[v]].tolist() == gold[v]['sentence'] for v in range(2))
     print('\n[beam bf16] %d / 2 sentences identical to the fp64 oracle; logprob diff %s' % (same, [float(lp[v] - gold[v]['logprob']) for v in range(2)]))
     assert all(abs(lp[v] - gold[v]['logprob']) < 0.2 for v in range(2))
+
+
+@pytest.mark.parametrize('precision,Tv,B', [('fp32', 5, 8), ('bf16', 5, 8), ('bf16', 80, 64)])
+def test_fused_beam_step_equals_unfused_launches(precision, Tv, B):
+    """The fused step (vocabulary GEMM with the per-part top-k epilogue + one merge / bookkeeping / state-gather kernel per step)
+    against the un-fused launches it replaces (materialised logits, topk_rows_kernel, beam_update_kernel, two gathers;
+    s2vt_set_overlap bit 3).  Same GEMM mainloop -> the candidate logits are bit-identical; lse is summed in a different order."""
+    import s2vt_b200
+    g = np.load(os.path.join(G, 'oracle_golden.npz'))
+    dims = dict(D=1536, E=500, H=1000, V=9972)
+    p = M.init_params(seed=4, dtype=np.float32, peaked_bias=g['peaked_bias'], logit_scale=3.0, **dims)
+    m = s2vt_b200.Video_Caption_Generator(dim_image=dims['D'], n_words=dims['V'], word_dim=dims['E'], lstm_dim=dims['H'], batch_size=B,
+                                          n_video_lstm_step=Tv, n_caption_lstm_step=35, dropout_rate=1.0, precision=precision, beam_size=8,
+                                          max_videos=B, max_rows=B)
+    m.load_variables(p)
+    video = M.synthetic_features(B, Tv)
+    for k, lnf in ((5, 1.0), (5, 0.0), (3, 1.0), (8, 0.0), (1, 0.0)):
+        m.lib.s2vt_set_overlap(m.h, 7)
+        fused = [x.cpu().numpy() for x in m.beam_search(video, k, lnf)]
+        m.lib.s2vt_set_overlap(m.h, 7 | 8)
+        plain = [x.cpu().numpy() for x in m.beam_search(video, k, lnf)]
+        m.lib.s2vt_set_overlap(m.h, 7)
+        same = [v for v in range(B) if fused[1][v] == plain[1][v] and (fused[0][v] == plain[0][v]).all()]
+        print('\n[beam fused vs un-fused %s T_v=%d k=%d lnf=%g] %d / %d sentences identical, max |logprob diff| %.2e'
+              % (precision, Tv, k, lnf, len(same), B, np.abs(fused[2][same] - plain[2][same]).max()))
+        assert len(same) >= B - B // 32          # a reordered fp32 lse may flip an exact near-tie between two hypotheses
+        np.testing.assert_allclose(fused[2][same], plain[2][same], atol=2e-5)
+        np.testing.assert_allclose(fused[3][same], plain[3][same], atol=2e-5)
+        assert (fused[1] > 0).all()
