@@ -246,12 +246,21 @@ def beam_sweep(s2vt_b200, torch, dist, args, bias, rank, world, batches, reps=3)
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn):
+    pipe = s2vt_b200.trainer.FeaturePipe(model.device, per_max, Tv, DIMS['D'])
+    idx_host = torch.zeros(per_max, dtype=torch.int32).pin_memory()
+    res_host = [[torch.empty(per_max, 35, dtype=torch.int32).pin_memory(), torch.empty(per_max, dtype=torch.int32).pin_memory(),
+                 torch.empty(per_max, dtype=torch.float32).pin_memory(), torch.empty(per_max, dtype=torch.float32).pin_memory()] for _ in range(2)]
+    res_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def timed(fn, whole=False):
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(reps):
-            fn()
+        if whole:
+            fn()                          # fn runs the `reps` calls itself
+        else:
+            for _ in range(reps):
+                fn()
         e1.record()
         sync()
         ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
@@ -272,12 +281,35 @@ def beam_sweep(s2vt_b200, torch, dist, args, bias, rank, world, batches, reps=3)
                 out = model.beam_search(host[:n].cuda(non_blocking=True), 5, 1.0)
                 return [x.cpu() for x in out]
 
+        def piped():
+            """a stream of calls: the features of call i+1 are staged on the copy stream under call i, results read one call behind"""
+            if not n:
+                return
+            pipe.put(host[:n], idx_host[:n])
+            pending = None
+            for i in range(reps):
+                if i + 1 < reps:
+                    pipe.put(host[:n], idx_host[:n])
+                v, _, slot = pipe.get()
+                out = model.beam_search(v, 5, 1.0)
+                pipe.release(slot)
+                for dst, src in zip(res_host[i % 2], out):
+                    dst[:n].copy_(src, non_blocking=True)
+                res_ev[i % 2].record()
+                if pending is not None:
+                    res_ev[pending].synchronize()
+                pending = i % 2
+            res_ev[pending].synchronize()
+
         for _ in range(2):
             resident()
         ms = timed(resident)
         fed()
         ms_e2e = timed(fed)
-        rows.append({'batch': b, 'ms': ms, 'captions_per_s': b / (ms / 1e3), 'e2e_ms': ms_e2e, 'e2e_captions_per_s': b / (ms_e2e / 1e3)})
+        piped()
+        ms_pipe = timed(piped, whole=True)
+        rows.append({'batch': b, 'ms': ms, 'captions_per_s': b / (ms / 1e3), 'e2e_ms': ms_e2e, 'e2e_captions_per_s': b / (ms_e2e / 1e3),
+                     'e2e_pipelined_ms': ms_pipe, 'e2e_pipelined_captions_per_s': b / (ms_pipe / 1e3)})
     del model
     return rows
 
@@ -315,8 +347,11 @@ def run_beam(args):
                           'beam_size': 5, 'T_v': Tv, 'T_c': 35, 'n_words': DIMS['V'], 'lstm_dim': DIMS['H'], 'parallelism': 'dp%d' % world,
                           'l2': 'no explicit flush: every call streams its own activations; weights (83 MB bf16) are meant to stay L2-resident'},
                'clocks': clocks,
-               'e2e': {'value': top['e2e_captions_per_s'], 'unit': 'captions/s', 'h2d_bytes_per_step': top['batch'] * Tv * DIMS['D'] * 4,
-                       'd2h_bytes_per_step': top['batch'] * (35 + 3) * 4},
+               'e2e': {'value': top['e2e_pipelined_captions_per_s'], 'unit': 'captions/s', 'h2d_bytes_per_step': top['batch'] * Tv * DIMS['D'] * 4,
+                       'd2h_bytes_per_step': top['batch'] * (35 + 3) * 4, 'ms_per_step': top['e2e_pipelined_ms'],
+                       'mode': 'a stream of calls with HOST feeds: features of call i+1 staged from pinned memory on a copy stream under call i '
+                               '(trainer.FeaturePipe), sentences / lengths / log-probs / scores read back one call behind; every copy inside the timed region',
+                       'blocking_feed_value': top['e2e_captions_per_s']},
                'sweep': rows}
         print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:

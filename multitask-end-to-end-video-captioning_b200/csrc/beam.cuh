@@ -35,7 +35,10 @@ struct BeamState {
 
 // One thread per video: consume the top-k words of each live parent (rows j*B+b, already in descending score
 // order), update finals / exclude_num, and select the next k live beams.
-__device__ void beam_update_one(const BeamState& s, const int* top_idx, const float* top_lp, int step, int cur, double lnf, int b) {
+// The top-k arrays are indexed [(j * tB + tb) * k + c]: (B, b) for the global [rows, k] arrays, (1, 0) for a per-video copy.
+// COPY_SENT = false leaves the children's word histories to the caller (beam_step_kernel copies them with the whole CTA).
+template <bool COPY_SENT>
+__device__ void beam_update_one(const BeamState& s, const int* top_idx, const float* top_lp, int tB, int tb, int step, int cur, double lnf, int b) {
     const int k = s.k, B = s.B, Tc = s.Tc;
     if (s.done[b]) { s.nlive[b] = 0; return; }
     double c_score[BEAM_MAXK * BEAM_MAXK];
@@ -48,8 +51,8 @@ __device__ void beam_update_one(const BeamState& s, const int* top_idx, const fl
         const int row = j * B + b;
         const int nchild = step == 0 ? k : k - excl;          // range(beam_size - exclude_num) evaluated once per parent
         for (int c = 0; c < nchild; ++c) {
-            int w = top_idx[row * k + c];
-            double lp = s.live_lp[row] + (double)top_lp[row * k + c];
+            int w = top_idx[(j * tB + tb) * k + c];
+            double lp = s.live_lp[row] + (double)top_lp[(j * tB + tb) * k + c];
             int len = s.live_len[row] + 1;
             if (step > 0 && w == 0) {                         // finished hypothesis -> final_captions.push
                 double sc = lp;
@@ -80,11 +83,12 @@ __device__ void beam_update_one(const BeamState& s, const int* top_idx, const fl
         c_par[best] = -1;
         ++taken;
     }
-    for (int j = 0; j < taken; ++j) {
-        const int row = j * B + b, prow = new_par[j] * B + b;
-        for (int t = 0; t < new_len[j] - 1; ++t) sent_nxt[(size_t)row * Tc + t] = sent_cur[(size_t)prow * Tc + t];
-        sent_nxt[(size_t)row * Tc + new_len[j] - 1] = new_word[j];
-    }
+    if (COPY_SENT)
+        for (int j = 0; j < taken; ++j) {
+            const int row = j * B + b, prow = new_par[j] * B + b;
+            for (int t = 0; t < new_len[j] - 1; ++t) sent_nxt[(size_t)row * Tc + t] = sent_cur[(size_t)prow * Tc + t];
+            sent_nxt[(size_t)row * Tc + new_len[j] - 1] = new_word[j];
+        }
     for (int j = 0; j < k; ++j) {
         const int row = j * B + b;
         if (j < taken) { s.live_lp[row] = new_lp[j]; s.live_len[row] = new_len[j]; s.parent[row] = new_par[j]; s.tok[row] = new_word[j]; }
@@ -95,23 +99,27 @@ __device__ void beam_update_one(const BeamState& s, const int* top_idx, const fl
 }
 __global__ void beam_update_kernel(BeamState s, const int* __restrict__ top_idx, const float* __restrict__ top_lp, int step, int cur, double lnf) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < s.B) beam_update_one(s, top_idx, top_lp, step, cur, lnf, b);
+    if (b < s.B) beam_update_one<true>(s, top_idx, top_lp, s.B, b, step, cur, lnf, b);
 }
 
 // Fused beam step (default): one CTA per video.
 //   1. warp j merges the per-part candidates of EpiLogitsTopK for live parent j: lse over the parts' (max, sum) pairs, then k
 //      rounds of warp arg-max, round q taking the best candidate that comes strictly after round q-1's winner in the
 //      (value descending, index ascending) order -- so no "taken" list is needed and ties resolve like tf.nn.top_k;
-//   2. thread 0 runs the reference's bookkeeping for the video (beam_update_one);
-//   3. the whole CTA copies the LSTM2 state rows of the chosen parents into the rows of their children (a video's children only
-//      ever descend from that video's parents, so no grid-wide dependency exists).
+//   2. thread 0 runs the reference's bookkeeping for the video (beam_update_one) on the shared-memory copy of the top-k lists;
+//   3. the whole CTA copies the word histories and the LSTM2 state rows of the chosen parents into the rows of their children
+//      (a video's children only ever descend from that video's parents, so no grid-wide dependency exists).
+// The next step's cell kernel is a programmatic dependent: it may start its prologue and weight prefetch at once.
 static_assert(BEAM_MAXK == TOPK_MAX, "EpiLogitsTopK keeps BEAM_MAXK candidates per part");
 template <typename T>
 __global__ void __launch_bounds__(32 * BEAM_MAXK) beam_step_kernel(BeamState s, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
-                                                                   const float2* __restrict__ stat, int nparts, int V, int* top_idx, float* top_lp,
+                                                                   const float2* __restrict__ stat, int nparts, int V,
                                                                    int step, int cur, double lnf, const T* __restrict__ h_new, T* __restrict__ h_next,
                                                                    const float* __restrict__ c_new, float* __restrict__ c_next, int Hp) {
-    const int b = blockIdx.x, B = s.B, k = s.k;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __shared__ int top_idx[BEAM_MAXK * BEAM_MAXK];
+    __shared__ float top_lp[BEAM_MAXK * BEAM_MAXK];
+    const int b = blockIdx.x, B = s.B, k = s.k, Tc = s.Tc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nl = s.done[b] ? 0 : s.nlive[b];
     if (warp < nl) {
@@ -144,13 +152,23 @@ __global__ void __launch_bounds__(32 * BEAM_MAXK) beam_step_kernel(BeamState s, 
                 t.i = __shfl_xor_sync(0xffffffffu, best.i, o);
                 best = argmax_op(best, t);
             }
-            if (lane == 0) { top_idx[row * k + j] = best.i; top_lp[row * k + j] = best.v - lse; }
+            if (lane == 0) { top_idx[warp * k + j] = best.i; top_lp[warp * k + j] = best.v - lse; }
             prev = best;
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) beam_update_one(s, top_idx, top_lp, step, cur, lnf, b);
+    if (threadIdx.x == 0) beam_update_one<false>(s, top_idx, top_lp, 1, 0, step, cur, lnf, b);
     __syncthreads();
+    {   // word histories of the surviving children: parent's words + the new one
+        const int taken = s.nlive[b];
+        const int* sent_cur = s.sent[cur];
+        int* sent_nxt = s.sent[cur ^ 1];
+        for (int u = threadIdx.x; u < taken * Tc; u += blockDim.x) {
+            const int j = u / Tc, t = u % Tc, row = j * B + b, len = s.live_len[row];
+            if (t < len - 1) sent_nxt[(size_t)row * Tc + t] = sent_cur[(size_t)(s.parent[row] * B + b) * Tc + t];
+            else if (t == len - 1) sent_nxt[(size_t)row * Tc + t] = s.tok[row];
+        }
+    }
     constexpr int HV = 16 / sizeof(T);
     for (int j = 0; j < k; ++j) {
         const int row = j * B + b, prow = s.parent[row] * B + b;
@@ -240,7 +258,7 @@ static int beam_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B,
             // :213-217 logits -> softmax -> top_k, fused: per-part candidates + soft-max statistics instead of the [rows, V] logits
             typename EpiLogitsTopK<T>::Params el = {rows, h->V, h->bo_p, cand_val, cand_idx, cand_stat, nparts};
             TRY((gemm<T, CfgBig, EpiLogitsTopK<T>>(h, st, r.h2r[1], Hp, h->WoT, Hp, rows, Vp, Hp, el)));
-            beam_step_kernel<T><<<B, 32 * BEAM_MAXK, 0, st>>>(s, cand_val, cand_idx, cand_stat, nparts, h->V, top_idx, top_lp, i, cur, (double)lnf,
+            beam_step_kernel<T><<<B, 32 * BEAM_MAXK, 0, st>>>(s, cand_val, cand_idx, cand_stat, nparts, h->V, i, cur, (double)lnf,
                                                              r.h2r[1], r.h2r[0], r.c2r[1], r.c2r[0], Hp); KCHECK(h);
             h->launches++;
             cur ^= 1;

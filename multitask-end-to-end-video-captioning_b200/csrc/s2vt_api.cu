@@ -290,6 +290,11 @@ static int chain_end(s2vt_handle* h, cudaStream_t st) {
     h->chain_open = false;
     return 0;
 }
+// The vocabulary projection of a decode loop (fused pick / top-k epilogues) always follows that step's cell kernel, which never
+// writes W_o: launched as a programmatic dependent, its prologue and the first W_o tiles overlap the cell kernel's tail.
+template <class Epi> struct kPdlLogits { static constexpr bool value = false; };
+template <typename T> struct kPdlLogits<EpiLogitsPick<T>> { static constexpr bool value = true; };
+template <typename T> struct kPdlLogits<EpiLogitsTopK<T>> { static constexpr bool value = true; };
 template <typename T, class Cfg, class Epi>
 static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const typename Epi::Params& ep,
                 int logical_k = 0, int logical_m = 0) {
@@ -324,7 +329,7 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
                 // slower on B200: at cluster sizes <= 4 multicast does not reduce L2 traffic).
                 if (h->cfg.gemm_backend == 4 && (N / 128) % 2 == 0) CUDA_TRY(h, (tc::launch<128, Epi, 1, 2, 2>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
                 else if (h->cfg.gemm_backend == 3 || N % 256 != 0) CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
-                else CUDA_TRY(h, (tc::launch<256, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
+                else CUDA_TRY(h, (tc::launch<256, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, kPdlLogits<Epi>::value)));
             }
             else if constexpr (std::is_same<Epi, EpiLstmBwd<bf16>>::value) {
                 // cell backward: K = 4H is long and N = H gives few tiles -> split K over a cluster of 4 CTAs (DSMEM reduction)
