@@ -500,6 +500,15 @@ def run_b200(args):
         beam['reward_kernels'] = rw
         del feats32
         torch.cuda.empty_cache()
+        # BASELINE config 1: tf_s2vt.py cross-entropy train step (teacher-forced forward with dropout, label-smoothed CE + L2, BPTT,
+        # clip 10, Adam) on [B, T_v, 1536] features and the first reference sentence of each video; measured last, it moves the weights
+        unk = dict(w2i); unk.setdefault('<en_unk>', 2)
+        cap_ids, cap_mask = s2vt_b200.text.sentence_padding_toix([by[order[(rank * B + j) % len(order)]][0] for j in range(B)], unk, 35)
+        cap_ids, cap_mask = torch.from_numpy(cap_ids).cuda(), torch.from_numpy(cap_mask).cuda()
+        for _ in range(2):
+            model.xe_step(feats_dev, cap_ids, cap_mask, 1e-4)
+        xe_ms = timed(5, lambda: model.xe_step(feats_dev, cap_ids, cap_mask, 1e-4))
+        beam.update({'xe_train_videos_per_s': 5 * B / (xe_ms / 1e3), 'xe_ms_per_step': xe_ms / 5})
         # BASELINE config 5: latency vs throughput of beam-5 captioning over the batch size (one GPU here; `--workload beam` shards it)
         beam['beam5_sweep'] = beam_sweep(s2vt_b200, torch, dist, args, bias, rank, world, [int(x) for x in args.beam_batches.split(',')])
     if rank != 0:

@@ -173,7 +173,7 @@ def test_beam_search_bf16_runs_and_mostly_agrees():
     assert all(abs(lp[v] - gold[v]['logprob']) < 0.2 for v in range(2))
 
 
-@pytest.mark.parametrize('precision,Tv,B', [('fp32', 5, 8), ('bf16', 5, 8), ('bf16', 80, 64)])
+@pytest.mark.parametrize('precision,Tv,B', [('fp32', 5, 8), ('bf16', 5, 8), ('bf16', 5, 1), ('bf16', 5, 3), ('bf16', 80, 64)])
 def test_fused_beam_step_equals_unfused_launches(precision, Tv, B):
     """The fused step (vocabulary GEMM with the per-part top-k epilogue + one merge / bookkeeping / state-gather kernel per step)
     against the un-fused launches it replaces (materialised logits, topk_rows_kernel, beam_update_kernel, two gathers;
