@@ -56,6 +56,10 @@ struct s2vt_att_handle {
 // ---- kernels ---------------------------------------------------------------------------------------------------------
 // dst[(cb * Cbp + c) * ldd + rb * Rbp + r] = src[(rb * Rb + r) * lds + cb * Cb + c]: TF-layout matrix whose rows / columns are
 // blocks of Rb / Cb (concatenated inputs, gate blocks) -> K-major operand with every block padded to Rbp / Cbp.
+// Per-step element-wise kernels let the GEMM that follows (a programmatic dependent, att_gemm) start its prologue at once; that
+// GEMM touches activations only after griddepcontrol.wait, i.e. after this kernel has completed.
+#define ATT_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+
 template <typename T>
 __global__ void att_pack_kernel(const float* __restrict__ src, int lds, int R, int C, T* __restrict__ dst, int ldd, int Rb, int Cb, int Rbp, int Cbp, int transpose) {
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)R * C; idx += (size_t)gridDim.x * blockDim.x) {
@@ -89,6 +93,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) att_attend_kernel(const float* __restrict__ q, const float* __restrict__ part, const float* __restrict__ emb,
                                                          const float* __restrict__ w, int B, int n, int Hp, T* __restrict__ x3, T* __restrict__ x4,
                                                          float* __restrict__ alphas_out, int R, float m_hinge, int reg_frames, float* __restrict__ hinge, float* __restrict__ alpha_rows) {
+    ATT_PDL_TRIGGER();
     __shared__ float e[128];
     __shared__ float red[32];
     const int r = blockIdx.x, v = r % B, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(256) att_attend_kernel(const float* __restrict
 template <typename T>
 __global__ void att_cell_kernel(const float* __restrict__ g, const float* __restrict__ c_in, float* __restrict__ c_out, int R, int Hp, T* __restrict__ x3_next,
                                 T* __restrict__ x4, T* __restrict__ hq_next, unsigned long long seed, uint32_t step, uint32_t row_base, float keep) {
+    ATT_PDL_TRIGGER();
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)R * Hp; idx += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(idx / Hp), u = (int)(idx % Hp);
         const float* gr = g + (size_t)r * 4 * Hp;
@@ -149,6 +155,7 @@ __global__ void att_cell_kernel(const float* __restrict__ g, const float* __rest
 }
 template <typename T>
 __global__ void att_tanh_kernel(const float* __restrict__ x, size_t count, T* __restrict__ out, float* __restrict__ outF) {
+    ATT_PDL_TRIGGER();
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < count; idx += (size_t)gridDim.x * blockDim.x) {
         const float t = tanh_<T>(x[idx]);
         out[idx] = from_f32<T>(t);
@@ -157,6 +164,7 @@ __global__ void att_tanh_kernel(const float* __restrict__ x, size_t count, T* __
 }
 // tf.argmax(logit_words, 1) (:190): lowest index among equal maxima; also the id matrix column.
 __global__ void __launch_bounds__(256) att_argmax_kernel(const float* __restrict__ logits, int ld, int V, int* __restrict__ tok, int* __restrict__ ids, int Tc, int t) {
+    ATT_PDL_TRIGGER();
     __shared__ ArgVal red[32];
     const int r = blockIdx.x;
     ArgVal best; best.v = -INFINITY; best.i = 0x7fffffff;
@@ -168,6 +176,7 @@ __global__ void __launch_bounds__(256) att_argmax_kernel(const float* __restrict
 template <typename T>
 __global__ void att_gather_kernel(const float* __restrict__ Wemb, int H, int Hp, const int* __restrict__ tok, int tok_ld, int tok_col, int R, T* __restrict__ x3,
                                   T* __restrict__ x4) {
+    ATT_PDL_TRIGGER();
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)R * H; idx += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(idx / H), e = (int)(idx % H);
         const T t = from_f32<T>(Wemb[(size_t)tok[(size_t)r * tok_ld + tok_col] * H + e]);
@@ -179,6 +188,7 @@ __global__ void att_gather_kernel(const float* __restrict__ Wemb, int H, int Hp,
 // acc[0] += sum(ce * mask + reg), acc[1] += sum(reg), acc[2] += sum(mask)
 __global__ void __launch_bounds__(256) att_ce_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ cap, const float* __restrict__ mask, int Tc,
                                                      int t, const float* __restrict__ hinge, float beta, double* __restrict__ acc) {
+    ATT_PDL_TRIGGER();
     __shared__ float red[32];
     const int r = blockIdx.x;
     const float* row = logits + (size_t)r * ld;
@@ -236,6 +246,7 @@ template <typename T>
 __global__ void att_cell_bwd_kernel(const float* __restrict__ dx4, const float* __restrict__ dhq_next, const float* __restrict__ dx3_next, const float* __restrict__ g,
                                     const float* __restrict__ c_prev, const float* __restrict__ c_new, float* __restrict__ dc, int R, int Hp, T* __restrict__ dg,
                                     unsigned long long seed, uint32_t step, uint32_t row_base, float keep) {
+    ATT_PDL_TRIGGER();
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)R * Hp; idx += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(idx / Hp), u = (int)(idx % Hp);
         float do1 = dx4[(size_t)r * 3 * Hp + u];
@@ -265,6 +276,7 @@ __global__ void __launch_bounds__(256) att_attend_bwd_kernel(const float* __rest
                                                              const float* __restrict__ alpha_rows, const float* __restrict__ hinge, const float* __restrict__ mask,
                                                              int Tc, int t, const double* __restrict__ acc, float beta, int reg_frames, int B, int n, int Hp,
                                                              T* __restrict__ dq, float* __restrict__ d_part, float* __restrict__ d_emb, float* __restrict__ dw) {
+    ATT_PDL_TRIGGER();
     extern __shared__ float sm[];
     float* da = sm;              // [Hp]
     float* dal = sm + Hp;        // [n] d alpha, then de
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(256) att_attend_bwd_kernel(const float* __rest
 // the un-deduplicated IndexedSlices square norm tf.clip_by_global_norm sees in sq[2].
 __global__ void att_scatter_emb_kernel(const float* __restrict__ dx4, const float* __restrict__ dx3, const int* __restrict__ cap, int Tc, int t, int R, int H, int Hp,
                                        float* __restrict__ gW, double* __restrict__ sq) {
+    ATT_PDL_TRIGGER();
     __shared__ double red[32];
     double acc = 0.0;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)R * H; idx += (size_t)gridDim.x * blockDim.x) {
@@ -556,7 +569,9 @@ static int att_gemm(s2vt_att_handle* h, cudaStream_t st, const void* A, int lda,
         if (!h->maps) h->maps = new tc::MapCache();
         if (M > 128) e = N % 256 == 0 ? tc::launch<256, EpiStore<bf16>>(*h->maps, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)
                                       : tc::launch<128, EpiStore<bf16>>(*h->maps, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false);
-        else e = tc::launch<32, EpiStore<bf16>>(*h->maps, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false);
+        // per-step GEMMs: B is always a packed weight matrix (written only by s2vt_att_refresh), so they run as programmatic dependents --
+        // prologue, TMEM allocation and the first weight tiles overlap the element-wise kernel before them (which triggers early)
+        else e = tc::launch<32, EpiStore<bf16>>(*h->maps, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true);
     } else {
         if (M > 64) e = launch_gemm<float, CfgBig, EpiStore<float>>(st, (const float*)A, lda, (const float*)B, ldb, M, N, K, ep);
         else e = launch_gemm<float, CfgStep, EpiStore<float>>(st, (const float*)A, lda, (const float*)B, ldb, M, N, K, ep);
