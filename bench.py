@@ -527,7 +527,7 @@ def run_b200(args):
     hbm = peaks.get('hbm_gbs', 6650.0)
     # dominant kernel by time: the recurrent-step shape with the largest total (the LSTM2 backward-through-time chain at the
     # metric's configuration): one persistent launch walks all its time steps
-    dom = max([x for x in shapes if x[0] == 1], key=lambda x: x[4])
+    dom = max([x for x in shapes if x[0] == 1 and (x[1], x[2], x[3]) in STEP_KERNEL_DRAM_BYTES_PER_LAUNCH] or [x for x in shapes if x[0] == 1], key=lambda x: x[4])
     _, dM, dN, dK, dms, dcnt, dby, dln = dom
     dname = 'EpiLstmBwd' if dK > dN else 'EpiLstmFwd'
     d_ach = dby / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
