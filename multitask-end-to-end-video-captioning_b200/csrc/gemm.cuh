@@ -235,13 +235,18 @@ struct EpiLogitsPick {
         float* pick_val; int* pick_idx; int pick_ld;     // [M, pick_ld] candidates, column = tile index
     };
     static constexpr int kEpiWarps = 16;   // tcgen05 kernel: 16 epilogue warps (the Philox / log work needs the lanes)
+    // apply_on: the functor run by threads [t0, t0 + NTH) of the CTA only, synchronised through named barrier 1 (the persistent
+    // sampling chain keeps its TMA / MMA warps busy with the next step's cell GEMM meanwhile); apply: by the whole CTA.
     template <class Cfg>
-    __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
+    __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) { apply_on<Cfg, 0, Cfg::NTHREADS>(p, Cs, m0, n0); }
+    template <class Cfg, int T0, int NTH>
+    __device__ static void apply_on(const Params& p, const float* Cs, int m0, int n0) {
         constexpr int PARTS = 4, PW = Cfg::BN / PARTS;          // each row's tile columns are scanned by 4 threads
         __shared__ float part_v[PARTS][Cfg::BM];
         __shared__ int part_i[PARTS][Cfg::BM];
         const int tile = n0 / Cfg::BN;
-        for (int u = threadIdx.x; u < Cfg::BM * PARTS; u += Cfg::NTHREADS) {
+        const int tid = (int)threadIdx.x - T0;
+        for (int u = tid; u < Cfg::BM * PARTS; u += NTH) {
             const int r = u % Cfg::BM, part = u / Cfg::BM, gr = m0 + r;   // consecutive threads -> consecutive rows (conflict-free float4 reads)
             ArgVal best; best.v = -INFINITY; best.i = 0x7fffffff;
             if (gr < p.M) {
@@ -293,8 +298,9 @@ struct EpiLogitsPick {
             }
             part_v[part][r] = best.v; part_i[part][r] = best.i;
         }
-        __syncthreads();
-        for (int r = threadIdx.x; r < Cfg::BM; r += Cfg::NTHREADS) {
+        if constexpr (T0 == 0 && NTH == Cfg::NTHREADS) __syncthreads();
+        else asm volatile("bar.sync 1, %0;" ::"n"(NTH) : "memory");
+        for (int r = tid; r < Cfg::BM; r += NTH) {
             const int gr = m0 + r;
             if (gr >= p.M) continue;
             ArgVal best; best.v = part_v[0][r]; best.i = part_i[0][r];

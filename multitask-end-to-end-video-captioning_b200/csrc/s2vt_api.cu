@@ -692,7 +692,9 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
             CUDA_TRY(h, cudaMemcpyAsync(dev, cells.data(), Tc * sizeof(cells[0]), cudaMemcpyHostToDevice, st));
             CUDA_TRY(h, cudaMemcpyAsync(dev + pick_off, picks.data(), Tc * sizeof(picks[0]), cudaMemcpyHostToDevice, st));
             chain_begin(h, st);
-            cudaError_t e = tc::launch_sample_chain<EpiLstmFwd<bf16>, EpiLogitsPick<bf16>>(
+            auto launcher = (h->overlap & 32) ? tc::launch_sample_chain<EpiLstmFwd<bf16>, EpiLogitsPick<bf16>, false>      // bit 5: without the overlap
+                                              : tc::launch_sample_chain<EpiLstmFwd<bf16>, EpiLogitsPick<bf16>, true>;
+            cudaError_t e = launcher(
                 mc, st, (const bf16*)r.h2r[0], (const bf16*)r.h2r[1], Hp, R, (const bf16*)h->W2hT, Hp, Gp, (const bf16*)h->WoT, Hp, Vp, Hp,
                 (const typename EpiLstmFwd<bf16>::Params*)dev, (const typename EpiLogitsPick<bf16>::Params*)(dev + pick_off), Tc, h->gbar + (st == h->side ? 16 : 0), true);
             if (e == cudaSuccess) {

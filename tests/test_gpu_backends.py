@@ -83,13 +83,13 @@ def test_sampling_chain_equals_per_step_launches(b, k, tv):
     m.load_variables(p)
     video = M.synthetic_features(b, tv)
     out = {}
-    for name, mask in (('chain', 7 | 16), ('steps', 7), ('chain2', 7 | 16)):
+    for name, mask in (('chain', 7 | 16), ('steps', 7), ('chain2', 7 | 16), ('plain_chain', 7 | 16 | 32)):    # bit 5: chain without the MMA / epilogue overlap
         m.lib.s2vt_set_overlap(m.h, mask)
         n0 = m.launch_count()
         samp, greedy = m.rollout(video, k, seed=11)
         out[name] = (samp.cpu(), greedy.cpu(), m.launch_count() - n0)
     m.lib.s2vt_set_overlap(m.h, 7)
     assert out['chain'][2] < out['steps'][2] - 60, (out['chain'][2], out['steps'][2])      # 1 launch instead of 70
-    for name in ('steps', 'chain2'):
+    for name in ('steps', 'chain2', 'plain_chain'):
         assert torch.equal(out['chain'][0], out[name][0]) and torch.equal(out['chain'][1], out[name][1]), name
     assert len(np.unique(out['chain'][0].numpy())) > 50      # not a degenerate rollout
