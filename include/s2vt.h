@@ -165,7 +165,7 @@ int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int
  * vocabulary weight gradient, bit 2: the LSTM1 backward chain); default 7.  Bit 3 (debug) makes s2vt_beam_search use its un-fused
  * step -- materialised logits and separate top-k / bookkeeping / state-gather launches -- the checker of the fused one; bit 4 (debug)
  * makes s2vt_rollout run its decode loop (> 128 rows) as one persistent sampling chain instead of two launches per step (measured
- * slower on B200, kept for A/B runs) */
+ * slower on B200, kept for A/B runs; bit 5 selects its variant without the MMA / epilogue overlap) */
 int s2vt_set_overlap(s2vt_handle* h, int mask);
 /* debug: per-launch phase timestamps (%globaltimer) of CTA (0,0) of every tcgen05 GEMM; NULL disables */
 int s2vt_debug_probe(void* device_buffer);
