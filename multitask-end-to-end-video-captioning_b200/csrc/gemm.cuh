@@ -475,8 +475,25 @@ template <class P>
 __device__ __forceinline__ int resolve_token(const P& p, int gr, int gc) {
     if (!p.pick_val) return p.tok[gr];
     const float* pv = p.pick_val + (size_t)gr * p.pick_ld;
-    float bv = pv[0]; int bt = 0;
-    for (int t = 1; t < p.pick_nt; ++t) { float v = pv[t]; if (v > bv) { bv = v; bt = t; } }   // first maximum = lowest word index
+    const int nt = p.pick_nt;
+    float bv = pv[0]; int bt = 0;                            // first maximum = lowest word index
+    if ((p.pick_ld & 1) == 0) {
+        // 16 candidates per round, every load issued before the first compare: one L2 round trip per round instead of one per 32-byte
+        // sector (this scan sits on the token -> Etab row -> gate pre-activation chain that nothing can overlap)
+        const float2* pv2 = reinterpret_cast<const float2*>(pv);
+        for (int t0 = 0; t0 < nt; t0 += 16) {
+            float2 c[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c[q] = t0 + 2 * q < nt ? pv2[(t0 >> 1) + q] : make_float2(-INFINITY, -INFINITY);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (c[q].x > bv) { bv = c[q].x; bt = t0 + 2 * q; }
+                if (t0 + 2 * q + 1 < nt && c[q].y > bv) { bv = c[q].y; bt = t0 + 2 * q + 1; }
+            }
+        }
+    } else {
+        for (int t = 1; t < nt; ++t) { float v = pv[t]; if (v > bv) { bv = v; bt = t; } }
+    }
     const int w = p.pick_idx[(size_t)gr * p.pick_ld + bt];
     if (gc == 0) { if (p.tok_out) p.tok_out[gr] = w; if (p.ids_out) p.ids_out[(size_t)gr * p.ids_ld + p.ids_col] = w; }
     return w;
@@ -487,12 +504,15 @@ __device__ __forceinline__ void EpiLstmFwd<T>::prefetch(const Params& p, int gr,
     const size_t G = 4 * (size_t)p.Hp;
     const float4* b = reinterpret_cast<const float4*>(p.bias + gc);
     const float4* a0 = p.add0 ? reinterpret_cast<const float4*>(p.add0 + (size_t)(p.add0_mod > 0 ? gr % p.add0_mod : gr) * G + gc) : nullptr;
-    const float4* a1 = p.add1 ? reinterpret_cast<const float4*>(p.add1 + (size_t)resolve_token(p, gr, gc) * G + gc) : nullptr;
     const float4* c = reinterpret_cast<const float4*>(p.c_prev + (size_t)gr * p.Hp + (gc >> 2));
     float4 x0[8], x1[8];
+    // everything that does not depend on the word first: these loads are in flight while the candidates are resolved
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { pre.add[j] = b[j]; x0[j] = a0 ? a0[j] : make_float4(0.f, 0.f, 0.f, 0.f); x1[j] = a1 ? a1[j] : make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int j = 0; j < 8; ++j) { pre.add[j] = b[j]; x0[j] = a0 ? a0[j] : make_float4(0.f, 0.f, 0.f, 0.f); }
     pre.c[0] = c[0]; pre.c[1] = c[1];
+    const float4* a1 = p.add1 ? reinterpret_cast<const float4*>(p.add1 + (size_t)resolve_token(p, gr, gc) * G + gc) : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x1[j] = a1 ? a1[j] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) pre.add[j] = f4add(pre.add[j], f4add(x0[j], x1[j]));
 }

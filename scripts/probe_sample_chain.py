@@ -33,7 +33,8 @@ rec = a[8:8 * (n + 1)].reshape(n, 8)
 rows = []
 for s in range(1, n - 1):
     t = rec[s]
-    if t[0] == 0 or t[5] == 0 or rec[s + 1][0] == 0 or t[0] < rec[s - 1][5]:
+    # the LSTM chains of the encoder share the probe buffer: their slot 6 holds a shape code, the sampling chain's a timestamp
+    if t[0] == 0 or t[5] == 0 or rec[s + 1][0] == 0 or t[0] < rec[s - 1][5] or t[6] < 10 ** 18 or rec[s + 1][6] < 10 ** 18 or rec[s - 1][6] < 10 ** 18:
         continue
     rows.append((t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[5], rec[s + 1][0] - t[0]))
 v = np.array(rows, dtype=np.float64)
