@@ -176,6 +176,53 @@ def cpu_threads():
         return os.cpu_count()
 
 
+def oracle_beam_captions_per_s(args, bias, n_videos, warm=1):
+    """final_beam_search.py:248-294 (= e2e_beam_search.py:301-344) as the reference runs it: one video at a time, beam 5, length
+    normalisation 1, one beam_probability call per hypothesis and step; NumPy fp32 restatement (oracle/beam.py, oracle/s2vt_numpy.py)."""
+    from oracle import beam as obeam
+    from oracle import s2vt_numpy as M
+    p = M.init_params(seed=4, dtype=np.float32, peaked_bias=bias, logit_scale=3.0, **DIMS)
+    video = features(n_videos + warm, args.frames, 99)
+    step = M.beam_step_fn(p, 5)
+
+    def one(v):
+        s1, s2 = M.beam_initial_states(p, video[v:v + 1])
+        return obeam.beam_search(step, s1, s2, 5, 35, 1.0)
+
+    for v in range(warm):
+        one(v)
+    t0 = time.perf_counter()
+    for v in range(warm, warm + n_videos):
+        one(v)
+    return n_videos / (time.perf_counter() - t0)
+
+
+def run_reference_beam(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vocab, by, order = load_corpus()
+    _, bias = peaked_bias(vocab, by)
+    n = max(1, min(args.ref_videos, 8)) * max(args.steps, 1)
+    val = oracle_beam_captions_per_s(args, bias, n, warm=max(args.warmup, 1))
+    sample = '%d videos, one at a time (the reference loop), beam 5, T_v=%d, fp32 NumPy/OpenBLAS' % (n, args.frames)
+    out = {'impl': 'reference', 'metric': 'beam5_decode_captions_per_s', 'value': val, 'unit': 'captions/s', 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': 1e3 / val, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+           'data': 'synthetic',
+           'config': {'workload': 'beam-5 captioning (BASELINE config 5), batch 1 as in final_beam_search.py / e2e_beam_search.py, T_v=%d, '
+                                  'length_normalization_factor 1, precomputed [1, T_v, 1536] features' % args.frames,
+                      'beam_size': 5, 'T_v': args.frames, 'T_c': 35, 'n_words': DIMS['V'], 'lstm_dim': DIMS['H'], 'parallelism': 'dp1'},
+           'cpu_baseline': {'value': val, 'unit': 'captions/s', 'cores': cpu_threads(), 'kind': 'port', 'sample': sample},
+           'e2e': {'value': val, 'unit': 'captions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out), flush=True)
+
+
+def shard_range(batch, rank, world):
+    """Videos [lo, hi) of a batch that `rank` decodes: contiguous blocks of ceil(batch / world); ranks beyond the batch get nothing."""
+    per = (batch + world - 1) // world
+    return min(batch, rank * per), min(batch, (rank + 1) * per)
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -269,7 +316,7 @@ def beam_sweep(s2vt_b200, torch, dist, args, bias, rank, world, batches, reps=3)
         return float(ms.item()) / reps
 
     for b in batches:
-        lo, hi = min(b, rank * ((b + world - 1) // world)), min(b, (rank + 1) * ((b + world - 1) // world))
+        lo, hi = shard_range(b, rank, world)
         n = hi - lo                      # this rank's videos of the batch (ranks beyond the batch idle)
 
         def resident():
@@ -353,6 +400,10 @@ def run_beam(args):
                                '(trainer.FeaturePipe), sentences / lengths / log-probs / scores read back one call behind; every copy inside the timed region',
                        'blocking_feed_value': top['e2e_captions_per_s']},
                'sweep': rows}
+        if world == 1 and not args.no_cpu_baseline:
+            n = 2
+            out['cpu_baseline'] = {'value': oracle_beam_captions_per_s(args, bias, n), 'unit': 'captions/s', 'cores': cpu_threads(), 'kind': 'port',
+                                   'sample': '%d videos, one at a time (the reference loop), beam 5, T_v=%d, fp32 NumPy/OpenBLAS' % (n, args.frames)}
         print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -577,7 +628,9 @@ def run_b200(args):
 
 if __name__ == '__main__':
     a = parse()
-    if a.impl == 'reference':
+    if a.impl == 'reference' and a.workload == 'beam':
+        run_reference_beam(a)
+    elif a.impl == 'reference':
         run_reference(a)
     elif a.workload == 'beam':
         run_beam(a)
