@@ -95,7 +95,12 @@ int s2vt_refresh(s2vt_handle* h, s2vt_stream st);
 
 /* Opt-in: let the next s2vt_rl_backward / s2vt_xe_backward reuse the frame projection and LSTM1 forward that the
  * preceding s2vt_rollout computed for the SAME video buffer (LSTM1 never sees a word and its state is not affected by the
- * output dropout, so the two passes are identical).  The caller promises not to modify the buffer in between. */
+ * output dropout, so the two passes are identical).
+ * HAZARD: the cache is keyed on the (pointer, B) pair only -- the library cannot see the buffer's contents.  A caller that
+ * REWRITES the same device buffer between the rollout and the backward call (e.g. a staging buffer refilled in place) would train
+ * on the stale LSTM1 pass.  With the option enabled the caller promises not to modify the buffer in between; any call that takes
+ * a different pointer or B, s2vt_refresh / s2vt_optimizer_step, and s2vt_set_reuse_frontend itself drop the cache.
+ * trainer.ReinforceTrainer.step is the one user: rollout and backward run back to back on one tensor. */
 int s2vt_set_reuse_frontend(s2vt_handle* h, int enable);
 
 /* ---- decoding -------------------------------------------------------------------------------------------------
@@ -129,6 +134,13 @@ int s2vt_rl_backward(s2vt_handle* h, const float* video, int B, const int32_t* c
 int s2vt_xe_backward(s2vt_handle* h, const float* video, int B, const int32_t* captions, const float* mask, int N, float label_smoothing,
                      float decay, float norm, float grad_scale, int accumulate, uint64_t drop_seed, uint32_t row_base, float* loss_out,
                      s2vt_stream st);
+/* The same objective for a SHARD of the batch (data parallel): Q3 couples the rows of a batch -- the step loss is
+ * mean_b(CE_b) * sum_b mask[b, i] -- so the shard needs the global per-step mask sums mask_colsum_global fp32 [T_c] (device), the
+ * global row count and norm = the global sum(mask) (> 0, required).  Per-rank gradients and losses then ADD up to the single-process
+ * ones (sum all-reduce, no averaging); pass decay on one rank only. */
+int s2vt_xe_backward_sharded(s2vt_handle* h, const float* video, int B, const int32_t* captions, const float* mask, int N, float label_smoothing,
+                             float decay, float norm, const float* mask_colsum_global, int n_rows_global, float grad_scale, int accumulate,
+                             uint64_t drop_seed, uint32_t row_base, float* loss_out, s2vt_stream st);
 /* Attribute head (reinforce_multitask_e2e_attribute_loss.py:375-380): sigmoid CE of mean_t(video) . attr_W + attr_b
  * against labels fp32 {0,1} [B, n_attributes], / (n_attributes * B).  Adds grad_scale * gradient to attr_W / attr_b. */
 int s2vt_attribute_backward(s2vt_handle* h, const float* video, int B, const float* labels, float grad_scale, float* loss_out,

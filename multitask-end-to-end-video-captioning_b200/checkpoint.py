@@ -15,7 +15,10 @@ IGNORED_PREFIXES = ('InceptionResnetV2/',)
 IGNORED_NAMES = ('Variable', 'g_step', 'beta1_power', 'beta2_power')
 
 
-def save(model, path, global_step=0, with_optimizer=True):
+def save(model, path, global_step=0, with_optimizer=True, step_name='global_step'):
+    """step_name: the TF name of the script's step counter -- `Variable` (tf_s2vt.py:441, an unnamed tf.Variable) or `g_step`
+    (reinforcement_multisampling_tf_s2vt.py:638) -- so that, as in the reference, a restore picks the counter up only when the
+    checkpoint was written by the same kind of script."""
     out = dict(model.state_dict())
     if with_optimizer:
         for name, (off, shp) in model.variables.items():
@@ -23,7 +26,10 @@ def save(model, path, global_step=0, with_optimizer=True):
             out[name + '/Adam'] = model.adam_m[off:off + n].view(*shp).cpu().numpy()
             out[name + '/Adam_1'] = model.adam_v[off:off + n].view(*shp).cpu().numpy()
         out['adam_step'] = np.asarray(model.adam_step, dtype=np.int64)
-    out['global_step'] = np.asarray(global_step, dtype=np.int64)
+        # TF's own bookkeeping: beta powers start at beta and are multiplied after every apply -> beta^(t+1) after t updates
+        out['beta1_power'] = np.asarray(0.9 ** (model.adam_step + 1), dtype=np.float32)
+        out['beta2_power'] = np.asarray(0.999 ** (model.adam_step + 1), dtype=np.float32)
+    out[step_name] = np.asarray(global_step, dtype=np.int64)
     os.makedirs(os.path.dirname(os.path.abspath(path)) or '.', exist_ok=True)
     np.savez(path, **out)
     return path if path.endswith('.npz') else path + '.npz'
@@ -97,33 +103,49 @@ def load_tf_checkpoint(prefix, skip_unreadable=True):
     return out
 
 
-def optimistic_restore(model, path, with_optimizer=False):
+def adam_step_from_beta1_power(beta1_power, beta1=0.9):
+    """Number of Adam updates already applied.  TF initialises beta1_power to beta1 and multiplies it by beta1 AFTER every apply
+    (AdamOptimizer._finish), so after t updates it holds beta1^(t+1)."""
+    b = float(np.asarray(beta1_power).reshape(-1)[0])
+    if not (0.0 < b < 1.0):
+        return 0
+    return max(0, int(round(np.log(b) / np.log(beta1))) - 1)
+
+
+def optimistic_restore(model, path, with_optimizer=False, step_name=None):
     """Load what matches by name and shape; return (restored names, global_step).  `path` is an .npz written by save()
-    or a TensorFlow checkpoint prefix (what the reference hands to saver.restore)."""
+    or a TensorFlow checkpoint prefix (what the reference hands to saver.restore).
+
+    The reference restores over tf.global_variables() (:47-61), which besides the model variables holds the optimiser's
+    `<var>/Adam`, `<var>/Adam_1` slots and `beta1_power` / `beta2_power`: with_optimizer=True restores those too (slots by name and
+    shape, the Adam time step from beta1_power).  The step counter is a global variable as well but its NAME differs between the
+    scripts (`Variable` in tf_s2vt.py:441, `g_step` in the RL scripts :638), so it is restored only under `step_name`
+    (None: any of `global_step`, `Variable`, `g_step`)."""
     if not path.endswith('.npz') and os.path.exists(path + '.npz'):
         path = path + '.npz'
     if is_tf_checkpoint(path):
-        tf_vars = load_tf_checkpoint(path)
-        for alias in ('Variable', 'g_step'):                    # the reference's global_step variables (tf_s2vt.py:441)
-            if alias in tf_vars and 'global_step' not in tf_vars:
-                tf_vars['global_step'] = tf_vars[alias].astype(np.int64).reshape(())
-        if 'beta1_power' in tf_vars and 0.0 < float(tf_vars['beta1_power'].reshape(-1)[0]) < 1.0:
-            tf_vars['adam_step'] = np.asarray(int(round(np.log(float(tf_vars['beta1_power'].reshape(-1)[0])) / np.log(0.9))), dtype=np.int64)
-        data = _Arrays(tf_vars)
+        data = _Arrays(load_tf_checkpoint(path))
     else:
         data = np.load(path)
+    skip = IGNORED_NAMES + ('global_step', 'adam_step')
     named = {k: data[k] for k in data.files
-             if not k.endswith('/Adam') and not k.endswith('/Adam_1') and k not in IGNORED_NAMES + ('global_step', 'adam_step')
-             and not k.startswith(IGNORED_PREFIXES)}
+             if not k.endswith('/Adam') and not k.endswith('/Adam_1') and k not in skip and not k.startswith(IGNORED_PREFIXES)}
     restored = model.load_variables(named)
-    if with_optimizer and 'adam_step' in data.files:
+    if with_optimizer:
         import torch
         for name in restored:
             off, shp = model.variables[name]
             n = int(np.prod(shp))
-            if name + '/Adam' in data.files and data[name + '/Adam'].shape == tuple(shp):
-                model.adam_m[off:off + n].copy_(torch.from_numpy(data[name + '/Adam'].reshape(-1)))
-                model.adam_v[off:off + n].copy_(torch.from_numpy(data[name + '/Adam_1'].reshape(-1)))
-        model.adam_step = int(data['adam_step'])
-    step = int(data['global_step']) if 'global_step' in data.files else 0
+            for slot, dst in (('/Adam', model.adam_m), ('/Adam_1', model.adam_v)):      # each slot is a variable of its own: name + shape rule
+                if name + slot in data.files and tuple(data[name + slot].shape) == tuple(shp):
+                    dst[off:off + n].copy_(torch.from_numpy(np.ascontiguousarray(data[name + slot], dtype=np.float32).reshape(-1)))
+        if 'adam_step' in data.files:
+            model.adam_step = int(data['adam_step'])
+        elif 'beta1_power' in data.files:
+            model.adam_step = adam_step_from_beta1_power(data['beta1_power'])
+    step = 0
+    for k in ((step_name,) if step_name else ('global_step', 'Variable', 'g_step')):
+        if k in data.files and np.asarray(data[k]).size == 1:
+            step = int(np.asarray(data[k]).reshape(-1)[0])
+            break
     return restored, step

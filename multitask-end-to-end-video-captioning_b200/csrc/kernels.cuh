@@ -294,7 +294,7 @@ __global__ void caption_tables_kernel(const int* __restrict__ cap, int N, int Tc
 //  mode 1 (XE, Q3)       : c = scale * S_i / (N * norm) ; ca = c ; cb = (1-ls) c ; cc = c * ls / V
 __global__ void loss_coef_kernel(int mode, const float* __restrict__ mask, const float* __restrict__ rewards, const float* __restrict__ base, int N, int Tc,
                                  const float* __restrict__ norm_p, float scale, float ls, int V, float* __restrict__ ca, float* __restrict__ cb,
-                                 float* __restrict__ cc) {
+                                 float* __restrict__ cc, const float* __restrict__ colsum_global = nullptr, int n_global = 0) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * Tc) return;
     const float norm = norm_p[0];
@@ -303,9 +303,11 @@ __global__ void loss_coef_kernel(int mode, const float* __restrict__ mask, const
         float c = scale * (rewards[n] - base[n]) * mask[(size_t)n * Tc + i] / norm;
         ca[idx] = c; cb[idx] = c; cc[idx] = 0.f;
     } else {
+        // Q3: step loss = mean_b(CE_b) * sum_b mask[b, i] over the WHOLE batch; a data-parallel caller passes the global column sums
         float S = 0.f;
-        for (int m = 0; m < N; ++m) S += mask[(size_t)m * Tc + i];
-        float c = scale * S / ((float)N * norm);
+        if (colsum_global) S = colsum_global[i];
+        else for (int m = 0; m < N; ++m) S += mask[(size_t)m * Tc + i];
+        float c = scale * S / ((float)(colsum_global ? n_global : N) * norm);
         ca[idx] = c; cb[idx] = (1.f - ls) * c; cc[idx] = c * ls / (float)V;
     }
 }
@@ -313,7 +315,8 @@ __global__ void loss_coef_kernel(int mode, const float* __restrict__ mask, const
 // Scalar losses from the per-row statistics.  out[0] = RL sum_loss (:646) or XE loss without weight decay (:159-166).
 __global__ void loss_reduce_kernel(int mode, const float* __restrict__ logp, const float* __restrict__ sumlsm, const float* __restrict__ mask,
                                    const float* __restrict__ rewards, const float* __restrict__ base, int N, int Tc, const float* __restrict__ norm_p,
-                                   float ls, int V, float* __restrict__ out, float* __restrict__ logp_masked) {
+                                   float ls, int V, float* __restrict__ out, float* __restrict__ logp_masked,
+                                   const float* __restrict__ colsum_global = nullptr, int n_global = 0) {
     __shared__ float red[32];
     const float norm = norm_p[0];
     float acc = 0.f;
@@ -334,7 +337,8 @@ __global__ void loss_reduce_kernel(int mode, const float* __restrict__ logp, con
                 S += mask[(size_t)n * Tc + i];
                 ce += -((1.f - ls) * logp[i * N + n] + (ls / (float)V) * sumlsm[i * N + n]);
             }
-            acc += ce / (float)N * S;
+            if (colsum_global) S = colsum_global[i];          // this rank's share of mean_b(CE) * sum_b mask; the shares add up over ranks
+            acc += ce / (float)(colsum_global ? n_global : N) * S;
         }
         acc = block_reduce(acc, [](float a, float b) { return a + b; }, red);
         if (threadIdx.x == 0) out[0] = acc / norm;

@@ -827,7 +827,7 @@ static int transpose(s2vt_handle* h, cudaStream_t st, const T* src, int lds, int
 template <typename T>
 static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* video, int B, const int32_t* captions, const float* mask, const float* rewards,
                       const float* base_line, int N, float norm, float grad_scale, int accumulate, float ls, float decay, uint64_t drop_seed,
-                      uint32_t row_base, float* loss_out, float* logp_out, float* logits_out) {
+                      uint32_t row_base, float* loss_out, float* logp_out, float* logits_out, const float* xe_colsum = nullptr, int xe_nglobal = 0) {
     const int Tv = h->Tv, Tc = h->Tc, T_ = h->T, Hp = h->Hp, Gp = h->Gp, Vp = h->Vp, Ep = h->Ep, Dp = h->Dp;
     const int H = h->H, E = h->E, V = h->V, D = h->D, G = 4 * h->H;
     const bool backward = mode != 2;
@@ -889,10 +889,10 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     sum_kernel<<<1, 256, 0, st>>>(mask, N * Tc, h->scal + 1); KCHECK(h);
     set_norm_kernel<<<1, 1, 0, st>>>(nrm, h->scal + 1, norm); KCHECK(h);
     if (!accumulate) CUDA_TRY(h, cudaMemsetAsync(h->grads, 0, (h->P + 8) * sizeof(float), st));
-    loss_coef_kernel<<<(Tc * N + 255) / 256, 256, 0, st>>>(mode, mask, rewards, base_line, N, Tc, nrm, grad_scale, ls, V, p.ca, p.cb, p.cc); KCHECK(h);
+    loss_coef_kernel<<<(Tc * N + 255) / 256, 256, 0, st>>>(mode, mask, rewards, base_line, N, Tc, nrm, grad_scale, ls, V, p.ca, p.cb, p.cc, xe_colsum, xe_nglobal); KCHECK(h);
     softmax_rows_kernel<T><<<Tc * N, ROW_THREADS, 0, st>>>(p.logits, Vp, V, Vp, p.target, p.ca, p.cb, p.cc, p.logp, p.sumlsm, p.dlogits, logp_out, N, Tc);
     KCHECK(h);
-    loss_reduce_kernel<<<1, 256, 0, st>>>(mode, p.logp, p.sumlsm, mask, rewards, base_line, N, Tc, nrm, ls, V, h->scal + 4, nullptr); KCHECK(h);
+    loss_reduce_kernel<<<1, 256, 0, st>>>(mode, p.logp, p.sumlsm, mask, rewards, base_line, N, Tc, nrm, ls, V, h->scal + 4, nullptr, xe_colsum, xe_nglobal); KCHECK(h);
     if (loss_out) {   // loss_out[0] (+)= grad_scale * objective, so a sequence of accumulate calls yields the mixed loss
         if (!accumulate) CUDA_TRY(h, cudaMemsetAsync(loss_out, 0, sizeof(float), st));
         add_scaled_scalar_kernel<<<1, 1, 0, st>>>(loss_out, h->scal + 4, grad_scale); KCHECK(h);
@@ -1025,6 +1025,8 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
             sumsq_kernel<<<148 * 2, 256, 0, st>>>(h->params + v.off, v.count(), h->sq + 3); KCHECK(h);
         }
         if (loss_out) { xe_total_kernel<<<1, 1, 0, st>>>(loss_out, h->sq, decay, grad_scale); KCHECK(h); }
+    } else if (mode == 1 && loss_out) {
+        CUDA_TRY(h, cudaMemsetAsync(loss_out + 1, 0, sizeof(float), st));   // no weight-decay part (decay 0: e.g. every rank but one of a sharded batch)
     }
     return 0;
 }
@@ -1058,6 +1060,19 @@ extern "C" int s2vt_xe_backward(s2vt_handle* h, const float* video, int B, const
     cudaStream_t s = (cudaStream_t)st;
     return DISPATCH(h, (train_impl<bf16>(h, s, 1, video, B, captions, mask, nullptr, nullptr, N, norm, grad_scale, accumulate, label_smoothing, decay, drop_seed, row_base, loss_out, nullptr, nullptr)),
                     (train_impl<float>(h, s, 1, video, B, captions, mask, nullptr, nullptr, N, norm, grad_scale, accumulate, label_smoothing, decay, drop_seed, row_base, loss_out, nullptr, nullptr)));
+}
+
+// Data-parallel form of the XE objective: Q3 couples the rows of a batch (mean_b(CE_b) * sum_b mask[b, i]), so a rank that holds a
+// shard needs the GLOBAL per-step mask sums and the global row count; with them the per-rank gradients and losses simply add up.
+extern "C" int s2vt_xe_backward_sharded(s2vt_handle* h, const float* video, int B, const int32_t* captions, const float* mask, int N, float label_smoothing,
+                                        float decay, float norm, const float* mask_colsum_global, int n_rows_global, float grad_scale, int accumulate,
+                                        uint64_t drop_seed, uint32_t row_base, float* loss_out, s2vt_stream st) {
+    TRY(check_ready(h));
+    if (!video || !captions || !mask || !mask_colsum_global || B <= 0 || N <= 0 || n_rows_global < N || !(norm > 0.f))
+        return h->fail(S2VT_EINVAL, "bad xe_backward_sharded arguments (the global sum(mask), its per-step sums and the global row count are required)");
+    cudaStream_t s = (cudaStream_t)st;
+    return DISPATCH(h, (train_impl<bf16>(h, s, 1, video, B, captions, mask, nullptr, nullptr, N, norm, grad_scale, accumulate, label_smoothing, decay, drop_seed, row_base, loss_out, nullptr, nullptr, mask_colsum_global, n_rows_global)),
+                    (train_impl<float>(h, s, 1, video, B, captions, mask, nullptr, nullptr, N, norm, grad_scale, accumulate, label_smoothing, decay, drop_seed, row_base, loss_out, nullptr, nullptr, mask_colsum_global, n_rows_global)));
 }
 
 // ---- attribute head (config 4) --------------------------------------------------------------------------------------

@@ -112,7 +112,7 @@ struct Mapped {
 const uint64_t kTableMagic = 0xdb4775248b80fb57ull;
 
 int read_block(const Mapped& f, uint64_t off, uint64_t size, Span* out) {
-    if (off + size + 5 > f.n) return fail(S2VT_EINVAL, "table block [%llu,+%llu) runs past the end of the file", (unsigned long long)off, (unsigned long long)size);
+    if (f.n < 5 || size > f.n - 5 || off > f.n - 5 - size) return fail(S2VT_EINVAL, "table block [%llu,+%llu) runs past the end of the file", (unsigned long long)off, (unsigned long long)size);
     const uint8_t* b = f.p + off;
     if (b[size] != 0) return fail(S2VT_EINVAL, "table block is compressed (type %d); TF Savers write raw blocks", (int)b[size]);
     if (crc_mask(crc32c(b, size + 1)) != rd32(b + size + 1)) return fail(S2VT_EINVAL, "table block at %llu fails its CRC32C", (unsigned long long)off);
@@ -364,6 +364,9 @@ int read_v1(const Tensor& t, float* out) {
                 }
             } else {                                                        // one unpacked element
                 if (got >= n) return fail(S2VT_ESHAPE, "%s holds more values than its shape", t.name.c_str());
+                // wire types: float = 5 (fixed32), double = 1 (fixed64), integers = 0 (varint); anything else is a malformed record
+                if ((want == 5 && f.wt != 5) || (want == 6 && f.wt != 1) || (want != 5 && want != 6 && f.wt != 0))
+                    return fail(S2VT_EINVAL, "%s: element with wire type %d does not match its dtype", t.name.c_str(), (int)f.wt);
                 if (want == 5) { float v; memcpy(&v, f.bytes.p, 4); out[got++] = v; }
                 else if (want == 6) { double v; memcpy(&v, f.bytes.p, 8); out[got++] = (float)v; }
                 else out[got++] = want == 7 ? (float)(int32_t)f.val : (float)(int64_t)f.val;

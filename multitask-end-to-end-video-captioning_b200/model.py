@@ -211,6 +211,17 @@ class Video_Caption_Generator(object):
                                               int(row_base), _ptr(self._loss), _stream()))
         return self._loss[:2]
 
+    def xe_backward_sharded(self, video, captions, mask, mask_colsum_global, n_rows_global, norm, decay=None, grad_scale=1.0, accumulate=False,
+                            drop_seed=0, row_base=0, label_smoothing=0.05):
+        """This rank's share of tf_loss and its gradients when the batch is split over ranks (Q3 couples the rows: the global per-step
+        mask sums [T_c], the global row count and the global sum(mask) are inputs).  Shares ADD up over the ranks."""
+        v = self._video(video); cap = self._i32(captions); m = self._f32(mask); cs = self._f32(mask_colsum_global)
+        d = self.decay_value if decay is None else decay
+        self._check(self.lib.s2vt_xe_backward_sharded(self.h, _ptr(v), v.shape[0], _ptr(cap), _ptr(m), cap.shape[0], float(label_smoothing), float(d),
+                                                      float(norm), _ptr(cs), int(n_rows_global), float(grad_scale), int(bool(accumulate)), int(drop_seed),
+                                                      int(row_base), _ptr(self._loss), _stream()))
+        return self._loss[:2]
+
     def attribute_backward(self, video, labels, grad_scale=1.0):
         v = self._video(video); y = self._f32(labels)
         out = torch.zeros(1, dtype=torch.float32, device=self.device)

@@ -117,3 +117,20 @@ def group_by_video(sents):
             order.append(vid)
         by[vid].append(s)
     return by, order
+
+
+def get_multilabel(vid_sentence, vocabulary):
+    """reinforce_multitask_e2e_attribute_loss.py:874-893: {vid: int64 [len(vocabulary)]} with label[k] = 1 iff attribute word k
+    occurs (as a whole `str.split()` token) in any sentence of the video."""
+    dup = {}                                                            # the reference marks EVERY position holding the word: duplicates share it
+    for k, w in enumerate(vocabulary):
+        dup.setdefault(w, []).append(k)
+    out = {}
+    for vid, sents in vid_sentence.items():
+        lab = np.zeros(len(vocabulary), dtype=np.int64)
+        for s in sents:
+            for w in set(s.split()):
+                if w in dup:
+                    lab[dup[w]] = 1
+        out[vid] = lab
+    return out

@@ -167,10 +167,20 @@ class XETrainer(object):
         it = self.global_step
         drop_seed = (self.seed * 7919 + it + 1) if self.dropout else 0
         n = captions.shape[0] if hasattr(captions, 'shape') else len(captions)
-        loss = m.xe_backward(video, captions, mask, drop_seed=drop_seed, row_base=rank * n).clone()
-        if world > 1:   # every rank holds an equal share of the batch: average the per-rank objectives
-            allreduce_gradients(m)
-            m.grads.mul_(1.0 / world)
+        if world == 1:
+            loss = m.xe_backward(video, captions, mask, drop_seed=drop_seed, row_base=0).clone()
+        else:
+            # Q3 couples the rows of a batch (step loss = mean_b(CE_b) * sum_b mask[b, i] / sum(mask)): exchange the per-step mask sums
+            # and the row count first, then every rank back-propagates its share with the GLOBAL statistics and the shares add up --
+            # the update equals the single-process one on the concatenated batch.  Weight decay is added once (rank 0).
+            msk = m._f32(mask)
+            stats = torch.cat([msk.sum(0), torch.tensor([float(n)], device=msk.device)])
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+            colsum, n_global = stats[:-1].contiguous(), int(round(float(stats[-1].item())))
+            loss = m.xe_backward_sharded(video, captions, msk, colsum, n_global, norm=float(colsum.sum().item()),
+                                         decay=(None if rank == 0 else 0.0), drop_seed=drop_seed, row_base=rank * n).clone()
+            allreduce_gradients(m, overlap=False)
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
         m.optimizer_step(exponential_decay(self.lr0, it, self.decay_steps), self.clip, wemb_slice_norm=False)
         self.global_step += 1
         return loss

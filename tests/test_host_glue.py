@@ -82,6 +82,13 @@ def test_batching_and_schedule():
     assert cli._batches(10, 3, 0, 1) == [0, 3, 6]               # zip(range(0, n-bs, bs), ...) drops the tail (Q6)
     assert cli._batches(9, 3, 0, 1) == [0, 3]
     assert cli._batches(20, 3, 1, 2) == [3, 9, 15]
+    # a batch count that does not divide by the world size: every rank gets the same number of batches (each one issues collectives)
+    # and together they are a prefix of the single-process batch list
+    for n, bs, world in ((10, 3, 2), (48774, 256, 8), (48774, 64, 8), (100, 7, 3)):
+        parts = [cli._batches(n, bs, r, world) for r in range(world)]
+        assert len({len(x) for x in parts}) == 1
+        merged = sorted(sum(parts, []))
+        assert merged == cli._batches(n, bs, 0, 1)[:len(merged)] and len(cli._batches(n, bs, 0, 1)) - len(merged) < world
     assert trainer.exponential_decay(1e-6, 999, 1000) == 1e-6 and trainer.exponential_decay(1e-6, 3000, 1000) == 1.25e-7
 
 
@@ -111,3 +118,72 @@ def test_gradient_allreduce_world_size_2_gloo(tmp_path):
     exp = torch.arange(1008, dtype=torch.float32) * 3
     exp[1002] = 30.0
     assert torch.equal(g, exp)
+
+
+def _uneven_worker(rank, world, port, out):
+    """The CLI's epoch loop shape: one all-reduce per batch, batch list from cli._batches with a count that does not divide evenly."""
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from s2vt_b200 import cli
+    total = torch.zeros(1)
+    for epoch in range(3):
+        for start in cli._batches(23, 3, rank, world):            # 7 batches for 2 ranks
+            t = torch.tensor([float(start)])
+            dist.all_reduce(t)
+            total += t
+    dist.barrier()
+    if rank == 0:
+        torch.save(total, out)
+    dist.destroy_process_group()
+
+
+def test_uneven_batch_count_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 't.pt')
+    mp.spawn(_uneven_worker, args=(2, 29613, out), nprocs=2, join=True)     # would dead-lock if the ranks ran 4 and 3 iterations
+    assert torch.load(out).item() == 3 * (0 + 3 + 6 + 9 + 12 + 15)
+
+
+class _FakeModel(object):
+    """Host stand-in with the attributes checkpoint.save / optimistic_restore touch."""
+
+    def __init__(self, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.variables = {'Wemb': (0, (6, 4)), 'encode_image_b': (24, (4,))}
+        self.params = torch.randn(28, generator=g)
+        self.adam_m = torch.randn(28, generator=g); self.adam_v = torch.rand(28, generator=g)
+        self.adam_step = 0
+
+    def state_dict(self):
+        return {k: self.params[o:o + int(np.prod(s))].view(*s).numpy().copy() for k, (o, s) in self.variables.items()}
+
+    def load_variables(self, named):
+        done = []
+        for k, (o, s) in self.variables.items():
+            if k in named and tuple(named[k].shape) == tuple(s):
+                self.params[o:o + int(np.prod(s))] = torch.from_numpy(np.asarray(named[k], np.float32).reshape(-1)); done.append(k)
+        return done
+
+
+def test_restore_brings_adam_state_and_matching_step_counter(tmp_path):
+    """optimistic_restore runs over tf.global_variables() (reinforcement_multisampling_tf_s2vt.py:47-61): Adam slots and beta powers
+    follow the variables; the step counter only when its name matches (Variable vs g_step)."""
+    from s2vt_b200 import checkpoint as ck
+    assert ck.adam_step_from_beta1_power(0.9) == 0                      # fresh optimiser: beta1_power initialised to beta1
+    assert ck.adam_step_from_beta1_power(0.9 ** 8) == 7                 # 7 applies -> beta1^(7+1)
+    a, b = _FakeModel(1), _FakeModel(2)
+    a.adam_step = 7
+    path = ck.save(a, str(tmp_path / 'xe-3'), global_step=1234, step_name='Variable')
+    restored, step = ck.optimistic_restore(b, path, with_optimizer=True, step_name='g_step')     # stage 2 restoring a stage-1 file
+    assert sorted(restored) == ['Wemb', 'encode_image_b'] and step == 0
+    assert b.adam_step == 7 and torch.equal(b.adam_m, a.adam_m) and torch.equal(b.adam_v, a.adam_v) and torch.equal(b.params, a.params)
+    c = _FakeModel(3)
+    _, step = ck.optimistic_restore(c, path, with_optimizer=True, step_name='Variable')          # stage 1 resuming itself
+    assert step == 1234
+    # a TF-written file carries no `adam_step`: it comes from beta1_power
+    d = dict(np.load(path)); del d['adam_step']
+    np.savez(str(tmp_path / 'tf_like.npz'), **d)
+    e = _FakeModel(4)
+    ck.optimistic_restore(e, str(tmp_path / 'tf_like.npz'), with_optimizer=True)
+    assert e.adam_step == 7
