@@ -19,6 +19,12 @@ import sys
 import threading
 import time
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # the CPU arm uses every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin NumPy's BLAS to one thread
+    # (the pools read the variable when the library loads, i.e. before `import numpy` below)
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -41,7 +47,8 @@ def parse():
     ap.add_argument('--samples', type=int, default=5, help='K sampled captions per video')
     ap.add_argument('--frames', type=int, default=80, help='T_v (BASELINE features [64, 80, 1536]; the reference literal is 5)')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
-    ap.add_argument('--ref-videos', type=int, default=8, help='videos per step of the CPU reference arm / cpu_baseline sample')
+    ap.add_argument('--ref-videos', type=int, default=0, help='videos per step of the CPU reference arm / cpu_baseline sample (0: --videos, the same configuration)')
+    ap.add_argument('--ref-seconds', type=float, default=150.0, help='CPU reference arm: stop timing further steps once this many seconds are spent (>= 2 steps are always timed)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-backend', default='auto')
     ap.add_argument('--overlap', type=int, default=-1, help='debug: side-stream overlap mask (s2vt_set_overlap)')
@@ -49,7 +56,10 @@ def parse():
                     help="train: the REINFORCE iteration (headline metric); beam: BASELINE config 5, the beam-5 captioning sweep over batch 1..1024")
     ap.add_argument('--beam-batches', default='1,2,4,8,16,32,64,128,256,512,1024')
     ap.add_argument('--quick', action='store_true', help='timed region only (for ncu launch lists): no e2e / roofline / CPU passes')
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.ref_videos <= 0:
+        a.ref_videos = a.videos
+    return a
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -127,43 +137,62 @@ class ClockSampler(threading.Thread):
 class OracleIteration(object):
     """reinforcement_multisampling_tf_s2vt.py:734-829 statement by statement on the host: K separate multinomial sampler
     runs + one greedy run (each re-encoding the frames), host CIDEr-D, build_loss forward at K*B rows with dropout,
-    BPTT, clip 5, Adam.  fp32, BLAS-threaded NumPy."""
+    BPTT, clip 5, Adam.  NumPy (fp32 for the timing arms, fp64 for the parity test), BLAS-threaded.
 
-    def __init__(self, args, vocab, by, order, bias):
+    Random streams are those of trainer.ReinforceTrainer (Philox sampler seed `seed + it` over rows k*B+j, dropout seed
+    `seed * 7919 + it + 1`), so one iteration here and one `ReinforceTrainer.step` see the same draws
+    (tests/test_gpu_bench_config_parity.py)."""
+
+    def __init__(self, samples, frames, videos, vocab, by, order, bias, seed=2024, lr0=1e-6, decay_steps=1000, clip=5.0, dtype=np.float32,
+                 video=None, video_index=None):
         from oracle import s2vt_numpy as M, ciderd, philox
         self.M, self.philox = M, philox
-        self.K, self.Tv, self.B = args.samples, args.frames, args.ref_videos
-        self.p = M.init_params(seed=4, dtype=np.float32, peaked_bias=bias, logit_scale=3.0, **DIMS)
+        self.K, self.Tv, self.B = samples, frames, videos
+        self.seed, self.lr0, self.decay_steps, self.clip, self.dtype = seed, lr0, decay_steps, clip, dtype
+        self.p = M.init_params(seed=4, dtype=dtype, peaked_bias=bias, logit_scale=3.0, **DIMS)
         self.opt = M.TFAdam(self.p)
         self.scorer = ciderd.CiderD([by[v] for v in order])
         self.i2w = {0: '<eos>', 1: '<bos>'}
         self.i2w.update((i + 2, w) for i, w in enumerate(vocab))
-        self.refs = [by[order[j % len(order)]] for j in range(self.B)]
-        self.video = features(self.B, self.Tv, 1234)
+        vidx = np.arange(self.B) % len(order) if video_index is None else np.asarray(video_index)
+        self.refs = [by[order[int(j)]] for j in vidx]
+        self.video = (features(self.B, self.Tv, 1234) if video is None else np.asarray(video)).astype(dtype)
         self.step_no = 0
+        self.last = {}
 
-    def step(self):
+    def step(self, use_samples=None, use_greedy=None):
+        """One iteration.  use_samples / use_greedy (parity test only): continue with these ids instead of the oracle's own draws -- they
+        are still drawn and kept in `last['own_samples']` / `last['own_greedy']` -- so that one categorical draw decided differently at
+        an fp32 near-tie does not void the comparison of everything downstream."""
         from oracle import text, ciderd
         M, K, B = self.M, self.K, self.B
         it = self.step_no
-        samples = [M.multinomial_sampler(self.p, self.video, 2024 + it, np.arange(k * B, (k + 1) * B)) for k in range(K)]
+        samples = [M.multinomial_sampler(self.p, self.video, self.seed + it, np.arange(k * B, (k + 1) * B)) for k in range(K)]   # :743-753
         greedy = M.greedy_sampler(self.p, self.video)
-        samples = np.vstack(samples)
+        samples = np.vstack(samples)                                                                  # :764-782 sample-major rows
+        own = dict(own_samples=samples, own_greedy=greedy)
+        if use_samples is not None:
+            samples = np.asarray(use_samples)
+        if use_greedy is not None:
+            greedy = np.asarray(use_greedy)
         vid_rows = np.concatenate([self.video] * K, 0)
-        mask, multi_decoded = text.decode_captions_masks(samples, self.i2w)
+        mask, multi_decoded = text.decode_captions_masks(samples, self.i2w)                           # :784
         _, greedy_decoded = text.decode_captions_masks(greedy, self.i2w)
         ref = {i: self.refs[i % B] for i in range(K * B)}
-        b = ciderd.evaluate_captions_cider(self.scorer, ref, greedy_decoded)
+        b = ciderd.evaluate_captions_cider(self.scorer, ref, greedy_decoded)                          # :790-795
         b = np.tile(b, K)
-        r = ciderd.evaluate_captions_cider(self.scorer, ref, multi_decoded)
+        r = ciderd.evaluate_captions_cider(self.scorer, ref, multi_decoded)                           # :806
         T = self.Tv + samples.shape[1]
         rows = np.arange(K * B)
-        d1 = np.stack([self.philox.dropout_mask(7 + it, self.philox.STREAM_DROP1, rows, t, DIMS['H'], 0.9) for t in range(T)])
-        d2 = np.stack([self.philox.dropout_mask(7 + it, self.philox.STREAM_DROP2, rows, t, DIMS['H'], 0.9) for t in range(T)])
+        ds = self.seed * 7919 + it + 1
+        d1 = np.stack([self.philox.dropout_mask(ds, self.philox.STREAM_DROP1, rows, t, DIMS['H'], 0.9) for t in range(T)]).astype(self.dtype)
+        d2 = np.stack([self.philox.dropout_mask(ds, self.philox.STREAM_DROP2, rows, t, DIMS['H'], 0.9) for t in range(T)]).astype(self.dtype)
+        # the rewards pass through float32 as in the feed (rewards / base_line are tf.float32 placeholders, :631-632)
         loss, grads, aux = M.rl_objective(self.p, vid_rows, samples, np.asarray(mask, np.float32), r.astype(np.float32), b.astype(np.float32), d1, d2)
-        clipped, gn = M.clip_by_global_norm(grads, 5.0, emb_slice_sqnorm=aux['emb_slice_sqnorm'])
-        self.p = self.opt.apply(self.p, clipped, M.exponential_decay(1e-6, it, 1000))
+        clipped, gn = M.clip_by_global_norm(grads, self.clip, emb_slice_sqnorm=aux['emb_slice_sqnorm'])     # :650
+        self.p = self.opt.apply(self.p, clipped, M.exponential_decay(self.lr0, it, self.decay_steps))        # :639-652
         self.step_no += 1
+        self.last = dict(samples=samples, greedy=greedy, rewards=r, baseline=b, mask=np.asarray(mask), loss=float(loss), grad_norm=float(gn), **own)
         return float(loss)
 
 
@@ -201,6 +230,7 @@ def run_reference_beam(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    use_all_host_threads()
     vocab, by, order = load_corpus()
     _, bias = peaked_bias(vocab, by)
     n = max(1, min(args.ref_videos, 8)) * max(args.steps, 1)
@@ -223,24 +253,44 @@ def shard_range(batch, rank, world):
     return min(batch, rank * per), min(batch, (rank + 1) * per)
 
 
+def use_all_host_threads():
+    """BLAS pools of this process -> every host core (also when the environment asked for one thread: see the top of the file)."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def run_reference(args):
+    """The reference's algorithm on the host cores, on the SAME configuration as the B200 arm (videos per step, K, T_v): W warm-up
+    iterations, then up to K timed ones -- timing stops early once --ref-seconds are spent (an iteration on 64 videos costs tens of
+    seconds), and `steps` reports what was timed."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    use_all_host_threads()
     vocab, by, order = load_corpus()
     w2i, bias = peaked_bias(vocab, by)
-    o = OracleIteration(args, vocab, by, order, bias)
-    for _ in range(args.warmup):
+    o = OracleIteration(args.samples, args.frames, args.ref_videos, vocab, by, order, bias)
+    for _ in range(min(args.warmup, 1)):          # one warm-up iteration pages in BLAS and the corpus; more would only burn minutes
         o.step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        o.step()
+    done, losses = 0, []
+    while done < max(args.steps, 1):
+        losses.append(o.step())
+        done += 1
+        if done >= 2 and time.perf_counter() - t0 > args.ref_seconds:
+            break
     dt = time.perf_counter() - t0
-    val = args.steps * args.ref_videos / dt
-    sample = '%d steps of the full iteration on %d videos x K=%d, T_v=%d, fp32 NumPy/OpenBLAS' % (args.steps, args.ref_videos, args.samples, args.frames)
-    out = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'videos/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-           'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': workload_config(args, args.ref_videos, 1),
+    val = done * args.ref_videos / dt
+    sample = ('%d timed iterations (of %d requested, %d warm-up) of the full iteration on %d videos x K=%d, T_v=%d, fp32 NumPy/OpenBLAS'
+              % (done, args.steps, min(args.warmup, 1), args.ref_videos, args.samples, args.frames))
+    out = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'videos/s', 'n_gpus': args.gpus, 'steps': done, 'warmup': min(args.warmup, 1),
+           'ms_per_step': 1e3 * dt / done, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': workload_config(args, args.ref_videos, 1), 'loss': losses[-1], 'losses': losses,
            'cpu_baseline': {'value': val, 'unit': 'videos/s', 'cores': cpu_threads(), 'kind': 'port', 'sample': sample},
            'e2e': {'value': val, 'unit': 'videos/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out), flush=True)
@@ -616,11 +666,12 @@ def run_b200(args):
                                      'peak_source': peak_src, 'launches_per_step': bn / args.steps, 'ms_per_step': bms / args.steps,
                                      'algorithmic_gflop_per_step': bfl / args.steps / 1e9}}
     if world == 1 and not args.no_cpu_baseline:
-        o = OracleIteration(args, vocab, by, order, bias)
-        o.step()
-        t0 = time.perf_counter(); o.step(); dt = time.perf_counter() - t0
-        out['cpu_baseline'] = {'value': args.ref_videos / dt, 'unit': 'videos/s', 'cores': cpu_threads(), 'kind': 'port',
-                               'sample': '1 full iteration (after 1 warm-up) on %d videos x K=%d, T_v=%d, fp32 NumPy/OpenBLAS oracle' % (args.ref_videos, K, Tv)}
+        use_all_host_threads()
+        OracleIteration(args.samples, 5, 2, vocab, by, order, bias).step()        # page in BLAS / the corpus on a tiny case
+        o = OracleIteration(args.samples, args.frames, args.ref_videos, vocab, by, order, bias)
+        t0 = time.perf_counter(); cpu_loss = o.step(); dt = time.perf_counter() - t0
+        out['cpu_baseline'] = {'value': args.ref_videos / dt, 'unit': 'videos/s', 'cores': cpu_threads(), 'kind': 'port', 'loss': cpu_loss,
+                               'sample': '1 full iteration on %d videos x K=%d, T_v=%d (the same configuration), fp32 NumPy/OpenBLAS oracle, %.1f s' % (args.ref_videos, K, Tv, dt)}
     print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
