@@ -216,6 +216,7 @@ __global__ void beam_finish_kernel(BeamState s, int cur, int* __restrict__ sente
 template <typename T>
 static int beam_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B, int k, float lnf, int32_t* sentences_out, int32_t* lengths_out,
                      float* logprob_out, float* score_out) {
+    typedef typename Fwd<T>::type F;   // forward operands: fp16 in the bf16 mode (common.cuh)
     const int Tv = h->Tv, Tc = h->Tc, Hp = h->Hp, Gp = h->Gp, Vp = h->Vp;
     const int R = B * k;
     Arena a(h->ws, h->ws_bytes);
@@ -235,7 +236,7 @@ static int beam_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B,
     TRY(run_encoder<T>(h, st, video, B, r));
     beam_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(s); KCHECK(h);
     // every beam starts from the encoder state; step 0 only uses beam 0 (nlive = 1)
-    tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2_final, B, R, Hp, r.h2r[0]); KCHECK(h);
+    tile_rows_kernel<F><<<R, 256, 0, st>>>(r.h2_final, B, R, Hp, r.h2r[0]); KCHECK(h);
     tile_rows_kernel<float><<<R, 256, 0, st>>>(r.c2e[Tv & 1], B, R, Hp, r.c2r[0]); KCHECK(h);
     int cur = 0;   // sentence ping-pong index
     // fused step (default; s2vt_set_overlap bit 3 keeps the un-fused launches as the A/B checker): the candidate arrays live in
@@ -248,29 +249,29 @@ static int beam_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B,
     for (int i = 0; i < Tc; ++i) {
         const int t = Tv + i;
         const int rows = i == 0 ? B : R;
-        typename EpiLstmFwd<T>::Params ep;
+        typename EpiLstmFwd<F>::Params ep;
         memset(&ep, 0, sizeof ep);
         ep.M = rows; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp; ep.add0_mod = B;
         ep.add1 = h->Etab; ep.tok = s.tok;
         ep.c_prev = r.c2r[0]; ep.c_out = r.c2r[1]; ep.h_out = r.h2r[1]; ep.keep = 1.f;
-        TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, r.h2r[0], Hp, h->W2hT, Hp, rows, Gp, Hp, ep)));
+        TRY((gemm<F, CfgStep, EpiLstmFwd<F>>(h, st, r.h2r[0], Hp, h->W2hT, Hp, rows, Gp, Hp, ep)));
         if (fused) {
             // :213-217 logits -> softmax -> top_k, fused: per-part candidates + soft-max statistics instead of the [rows, V] logits
             typename EpiLogitsTopK<T>::Params el = {rows, h->V, h->bo_p, cand_val, cand_idx, cand_stat, nparts};
-            TRY((gemm<T, CfgBig, EpiLogitsTopK<T>>(h, st, r.h2r[1], Hp, h->WoT, Hp, rows, Vp, Hp, el)));
-            beam_step_kernel<T><<<B, 32 * BEAM_MAXK, 0, st>>>(s, cand_val, cand_idx, cand_stat, nparts, h->V, i, cur, (double)lnf,
+            TRY((gemm<F, CfgBig, EpiLogitsTopK<T>>(h, st, r.h2r[1], Hp, h->WoT, Hp, rows, Vp, Hp, el)));
+            beam_step_kernel<F><<<B, 32 * BEAM_MAXK, 0, st>>>(s, cand_val, cand_idx, cand_stat, nparts, h->V, i, cur, (double)lnf,
                                                              r.h2r[1], r.h2r[0], r.c2r[1], r.c2r[0], Hp); KCHECK(h);
             h->launches++;
             cur ^= 1;
             continue;
         }
-        typename EpiStore<T>::Params el = {r.logits, nullptr, Vp, h->bo_p, rows, 0};
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, r.h2r[1], Hp, h->WoT, Hp, rows, Vp, Hp, el)));
+        typename EpiStore<F>::Params el = {r.logits, nullptr, Vp, h->bo_p, rows, 0};
+        TRY((gemm<F, CfgBig, EpiStore<F>>(h, st, r.h2r[1], Hp, h->WoT, Hp, rows, Vp, Hp, el)));
         topk_rows_kernel<<<rows, ROW_THREADS, 0, st>>>(r.logits, Vp, h->V, k, top_idx, top_lp); KCHECK(h);
         beam_update_kernel<<<(B + 63) / 64, 64, 0, st>>>(s, top_idx, top_lp, i, cur, (double)lnf); KCHECK(h);
         cur ^= 1;
         // children inherit the state produced by their parent's step
-        beam_gather_kernel<T><<<R, 256, 0, st>>>(r.h2r[1], s.parent, B, Hp, r.h2r[0]); KCHECK(h);
+        beam_gather_kernel<F><<<R, 256, 0, st>>>(r.h2r[1], s.parent, B, Hp, r.h2r[0]); KCHECK(h);
         beam_gather_kernel<float><<<R, 256, 0, st>>>(r.c2r[1], s.parent, B, Hp, r.c2r[0]); KCHECK(h);
     }
     beam_finish_kernel<<<(B + 127) / 128, 128, 0, st>>>(s, cur, sentences_out, lengths_out, logprob_out, score_out); KCHECK(h);
@@ -310,6 +311,7 @@ __global__ void to_f32_kernel(const T* __restrict__ in, int n, float* __restrict
 
 template <typename T>
 static int beam_init_impl(s2vt_handle* h, cudaStream_t st, const float* video, float* state1_out, float* state2_out) {
+    typedef typename Fwd<T>::type F;   // forward operands: fp16 in the bf16 mode (common.cuh)
     const int Tv = h->Tv, Hp = h->Hp, H = h->H;
     Arena a(h->ws, h->ws_bytes);
     Roll<T> r;
@@ -317,9 +319,9 @@ static int beam_init_impl(s2vt_handle* h, cudaStream_t st, const float* video, f
     float* hF = a.take<float>(Hp);
     if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small");
     TRY(run_encoder<T>(h, st, video, 1, r));
-    to_f32_kernel<T><<<(Hp + 255) / 256, 256, 0, st>>>(r.f.h1_all + (size_t)Tv * Hp, Hp, hF); KCHECK(h);
+    to_f32_kernel<F><<<(Hp + 255) / 256, 256, 0, st>>>(r.f.h1_all + (size_t)Tv * Hp, Hp, hF); KCHECK(h);
     state_pack_kernel<<<1, 256, 0, st>>>(r.f.c1_all + (size_t)Tv * Hp, hF, H, state1_out); KCHECK(h);
-    to_f32_kernel<T><<<(Hp + 255) / 256, 256, 0, st>>>(r.h2_final, Hp, hF); KCHECK(h);
+    to_f32_kernel<F><<<(Hp + 255) / 256, 256, 0, st>>>(r.h2_final, Hp, hF); KCHECK(h);
     state_pack_kernel<<<1, 256, 0, st>>>(r.c2e[Tv & 1], hF, H, state2_out); KCHECK(h);
     return 0;
 }
@@ -327,29 +329,30 @@ static int beam_init_impl(s2vt_handle* h, cudaStream_t st, const float* video, f
 template <typename T>
 static int beam_step_impl(s2vt_handle* h, cudaStream_t st, const float* state2, const float* state1, const int32_t* word, int k, int32_t* idx_out,
                           float* prob_out, float* state2_out, float* state1_out) {
+    typedef typename Fwd<T>::type F;   // forward operands: fp16 in the bf16 mode (common.cuh)
     const int Hp = h->Hp, H = h->H, Gp = h->Gp, Vp = h->Vp;
     h->front_valid = false;
     TRY(wait_late_weights(h, st));
     Arena a(h->ws, h->ws_bytes);
-    float* c1 = a.take<float>(Hp); T* h1 = a.take<T>(Hp); float* c1n = a.take<float>(Hp); T* h1n = a.take<T>(Hp); float* h1F = a.take<float>(Hp);
-    float* c2 = a.take<float>(Hp); T* h2 = a.take<T>(Hp); float* c2n = a.take<float>(Hp); T* h2n = a.take<T>(Hp); float* h2F = a.take<float>(Hp);
+    float* c1 = a.take<float>(Hp); F* h1 = a.take<F>(Hp); float* c1n = a.take<float>(Hp); F* h1n = a.take<F>(Hp); float* h1F = a.take<float>(Hp);
+    float* c2 = a.take<float>(Hp); F* h2 = a.take<F>(Hp); float* c2n = a.take<float>(Hp); F* h2n = a.take<F>(Hp); float* h2F = a.take<float>(Hp);
     float* g2x = a.take<float>(Gp); float* logits = a.take<float>(Vp); float* lp = a.take<float>(BEAM_MAXK);
     if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small");
-    state_unpack_kernel<T><<<1, 256, 0, st>>>(state1, H, Hp, c1, h1); KCHECK(h);
-    state_unpack_kernel<T><<<1, 256, 0, st>>>(state2, H, Hp, c2, h2); KCHECK(h);
-    typename EpiLstmFwd<T>::Params e1;
+    state_unpack_kernel<F><<<1, 256, 0, st>>>(state1, H, Hp, c1, h1); KCHECK(h);
+    state_unpack_kernel<F><<<1, 256, 0, st>>>(state2, H, Hp, c2, h2); KCHECK(h);
+    typename EpiLstmFwd<F>::Params e1;
     memset(&e1, 0, sizeof e1);
     e1.M = 1; e1.Hp = Hp; e1.bias = h->b1_p; e1.c_prev = c1; e1.c_out = c1n; e1.h_out = h1n; e1.h_outF = h1F; e1.keep = 1.f;
-    TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, h1, Hp, h->W1hT, Hp, 1, Gp, Hp, e1)));       // lstm1(padding, state1)
-    typename EpiStore<T>::Params eg = {g2x, nullptr, Gp, nullptr, 1, 0};
-    TRY((gemm<T, CfgStep, EpiStore<T>>(h, st, h1n, Hp, h->W2xT, Hp, 1, Gp, Hp, eg)));
-    typename EpiLstmFwd<T>::Params e2;
+    TRY((gemm<F, CfgStep, EpiLstmFwd<F>>(h, st, h1, Hp, h->W1hT, Hp, 1, Gp, Hp, e1)));       // lstm1(padding, state1)
+    typename EpiStore<F>::Params eg = {g2x, nullptr, Gp, nullptr, 1, 0};
+    TRY((gemm<F, CfgStep, EpiStore<F>>(h, st, h1n, Hp, h->W2xT, Hp, 1, Gp, Hp, eg)));
+    typename EpiLstmFwd<F>::Params e2;
     memset(&e2, 0, sizeof e2);
     e2.M = 1; e2.Hp = Hp; e2.bias = h->b2_p; e2.add0 = g2x; e2.add1 = h->Etab; e2.tok = word;
     e2.c_prev = c2; e2.c_out = c2n; e2.h_out = h2n; e2.h_outF = h2F; e2.keep = 1.f;
-    TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, h2, Hp, h->W2hT, Hp, 1, Gp, Hp, e2)));       // lstm2([out1, emb], state2)
-    typename EpiStore<T>::Params el = {logits, nullptr, Vp, h->bo_p, 1, 0};
-    TRY((gemm<T, CfgStep, EpiStore<T>>(h, st, h2n, Hp, h->WoT, Hp, 1, Vp, Hp, el)));
+    TRY((gemm<F, CfgStep, EpiLstmFwd<F>>(h, st, h2, Hp, h->W2hT, Hp, 1, Gp, Hp, e2)));       // lstm2([out1, emb], state2)
+    typename EpiStore<F>::Params el = {logits, nullptr, Vp, h->bo_p, 1, 0};
+    TRY((gemm<F, CfgStep, EpiStore<F>>(h, st, h2n, Hp, h->WoT, Hp, 1, Vp, Hp, el)));
     topk_rows_kernel<<<1, ROW_THREADS, 0, st>>>(logits, Vp, h->V, k, idx_out, lp); KCHECK(h);
     exp_kernel<<<1, 32, 0, st>>>(lp, k, prob_out); KCHECK(h);
     state_pack_kernel<<<1, 256, 0, st>>>(c1n, h1F, H, state1_out); KCHECK(h);

@@ -1,10 +1,22 @@
 // Shared device helpers for the S2VT B200 library (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
+
+// Operand type of the FORWARD GEMMs of a compute mode.  The bf16 mode (tensor-core mode) keeps every forward value -- activations,
+// the K-major weight copies, the word-embedding table -- in IEEE fp16: same 16 bits and the same tcgen05 kind::f16 rate as bf16,
+// but 10 mantissa bits instead of 7, which is what brings the teacher-forced logits within the 1e-3 the north star quotes
+// (bf16 operands: 4.4e-3 at H = 1000, tests/test_gpu_bench_config_parity.py).  Every forward quantity is bounded (|h| < 1,
+// post-ReLU features, weights of magnitude 0.1), far inside fp16's range.  Gradients keep bf16: REINFORCE gate gradients reach
+// 1e-9 and below, under fp16's normal range.  The weight-gradient GEMMs X^T . dY therefore multiply an fp16 operand by a bf16 one
+// (the instruction descriptor carries one format per operand).
+template <typename T> struct Fwd { typedef T type; };
+template <> struct Fwd<bf16> { typedef f16 type; };
 
 #define S2VT_PAD 128  // every contraction / output dimension is zero-padded to a multiple of this
 
@@ -14,8 +26,10 @@ __host__ __device__ inline size_t ru64(size_t x, size_t m) { return (x + m - 1) 
 template <typename T> __device__ __forceinline__ T from_f32(float x);
 template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ f16 from_f32<f16>(float x) { return __float2half_rn(x); }
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ float to_f32(f16 x) { return __half2float(x); }
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10.  Must match oracle/philox.py bit for bit (Random123 KAT in tests/test_oracle_model.py).
@@ -60,9 +74,11 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 template <typename T> __device__ __forceinline__ float sigm(float x);
 template <> __device__ __forceinline__ float sigm<float>(float x) { return 1.0f / (1.0f + expf(-x)); }
 template <> __device__ __forceinline__ float sigm<bf16>(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+template <> __device__ __forceinline__ float sigm<f16>(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 template <typename T> __device__ __forceinline__ float tanh_(float x);
 template <> __device__ __forceinline__ float tanh_<float>(float x) { return tanhf(x); }
 template <> __device__ __forceinline__ float tanh_<bf16>(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+template <> __device__ __forceinline__ float tanh_<f16>(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 // four saved gate activations (si, tj, sf, so) in the compute dtype
 __device__ __forceinline__ float4 load_gates4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 load_gates4(const bf16* p) {
@@ -70,12 +86,23 @@ __device__ __forceinline__ float4 load_gates4(const bf16* p) {
     float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
     return make_float4(a.x, a.y, b.x, b.y);
 }
+__device__ __forceinline__ float4 load_gates4(const f16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
 // the same four activations kept packed (as stored) while they wait in registers: 2 registers instead of 4 in bf16 mode
 template <typename T> struct GateRaw;
 template <> struct GateRaw<float> { float4 v; };
 template <> struct GateRaw<bf16> { uint2 v; };
+template <> struct GateRaw<f16> { uint2 v; };
 __device__ __forceinline__ void load_gates_raw(const float* p, GateRaw<float>& r) { r.v = *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void load_gates_raw(const bf16* p, GateRaw<bf16>& r) { r.v = *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ void load_gates_raw(const f16* p, GateRaw<f16>& r) { r.v = *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ float4 unpack_gates(const GateRaw<f16>& r) {
+    float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ float4 unpack_gates(const GateRaw<float>& r) { return r.v; }
 __device__ __forceinline__ float4 unpack_gates(const GateRaw<bf16>& r) {
     float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.v.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.v.y));
@@ -84,6 +111,12 @@ __device__ __forceinline__ float4 unpack_gates(const GateRaw<bf16>& r) {
 __device__ __forceinline__ void store_gates4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void store_gates4(bf16* p, float4 v) {
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ void store_gates4(f16* p, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
     uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
     *reinterpret_cast<uint2*>(p) = u;
 }

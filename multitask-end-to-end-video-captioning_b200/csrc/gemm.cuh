@@ -41,20 +41,28 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t
     unsigned a = (unsigned)__cvta_generic_to_shared(p);
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
 }
-__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+template <typename T16> __device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma_16816<bf16>(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma_16816<f16>(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 template <typename T, class Cfg> struct Mainloop;
 
-// ---- bf16 tensor-core mainloop (mma.sync) ---------------------------------------------------------------------
-template <class Cfg>
-struct Mainloop<bf16, Cfg> {
-    __device__ static void run(const bf16* __restrict__ A, int lda, const bf16* __restrict__ B, int ldb, int M, int K, int m0, int n0,
+// ---- 16-bit tensor-core mainloop (mma.sync; bf16 x bf16 or fp16 x fp16) -----------------------------------------
+template <typename T16, class Cfg>
+struct Mainloop16 {
+    __device__ static void run(const T16* __restrict__ A_, int lda, const T16* __restrict__ B_, int ldb, int M, int K, int m0, int n0,
                                unsigned char* smem, float* Cs) {
+        const bf16* A = reinterpret_cast<const bf16*>(A_); const bf16* B = reinterpret_cast<const bf16*>(B_);   // 16-bit payloads: the copy code is type-blind
         constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, LDS = Cfg::LDS, ST = Cfg::STAGES;
         constexpr int MT = WM / 16, NT = WN / 8;
         static_assert(NT % 2 == 0, "warp tile N must cover pairs of n8 tiles");
@@ -111,8 +119,8 @@ struct Mainloop<bf16, Cfg> {
                     ldmatrix_x4(b0, b1, b2, b3, b + (wn * WN + j * 8 + (lane & 7) + (lane >> 4) * 8) * LDS + kk + ((lane >> 3) & 1) * 8);
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
-                        mma_bf16_16816(acc[i][j], af[i], b0, b1);
-                        mma_bf16_16816(acc[i][j + 1], af[i], b2, b3);
+                        mma_16816<T16>(acc[i][j], af[i], b0, b1);
+                        mma_16816<T16>(acc[i][j + 1], af[i], b2, b3);
                     }
                 }
             }
@@ -130,6 +138,9 @@ struct Mainloop<bf16, Cfg> {
         __syncthreads();
     }
 };
+
+template <class Cfg> struct Mainloop<bf16, Cfg> : Mainloop16<bf16, Cfg> {};
+template <class Cfg> struct Mainloop<f16, Cfg> : Mainloop16<f16, Cfg> {};
 
 // ---- fp32 SIMT mainloop ----------------------------------------------------------------------------------------
 template <class Cfg>
@@ -193,6 +204,14 @@ __device__ __forceinline__ void store8(float* dst, const float* v) {
 __device__ __forceinline__ void store8(bf16* dst, const float* v) {
     __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
     __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(dst) = u;
+}
+__device__ __forceinline__ void store8(f16* dst, const float* v) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
     uint4 u;
     u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
     u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
@@ -557,7 +576,8 @@ struct LstmBwdArgs {
     float* dc;               // [M, Hp] in: dc from step t+1, out: dc for step t-1
     unsigned long long seed; uint32_t stream; uint32_t step; uint32_t row_base; float keep;  // dropout on dh_ext (keep>=1: none)
 };
-template <typename T>
+// T: type of the gate GRADIENTS written; F: type the forward pass saved the gate ACTIVATIONS in (Fwd<T>::type in the S2VT engine)
+template <typename T, typename F = T>
 __device__ __forceinline__ void lstm_bwd_unit(const LstmBwdArgs& p, T* dg_out, int gr, int u, float dh_rec) {
     const int G = 4 * p.Hp;
     size_t o = (size_t)gr * p.Hp + u;
@@ -566,7 +586,7 @@ __device__ __forceinline__ void lstm_bwd_unit(const LstmBwdArgs& p, T* dg_out, i
         float m = p.keep < 1.0f ? dropout_mult(p.seed, p.stream, p.row_base + gr, p.step, u, p.keep) : 1.0f;
         dh += p.dh_ext[o] * m;
     }
-    float4 g = load_gates4(reinterpret_cast<const T*>(p.gates) + (size_t)gr * G + 4 * u);
+    float4 g = load_gates4(reinterpret_cast<const F*>(p.gates) + (size_t)gr * G + 4 * u);
     float si = g.x, tj = g.y, sf = g.z, so = g.w;
     float tc = tanh_<T>(p.c_new[o]);
     float d_o = dh * tc;
@@ -580,12 +600,12 @@ __device__ __forceinline__ void lstm_bwd_unit(const LstmBwdArgs& p, T* dg_out, i
     d[3] = from_f32<T>(d_o * so * (1.0f - so));
 }
 // GEMM form: acc[row, u] = dG(t+1)[row, :] . Wh[u, :]   (N dimension = hidden units)
-template <typename T>
+template <typename T, typename F = T>
 struct EpiLstmBwd {
     // Direct form: a thread owns one row and a chunk of 8 hidden units of dh_rec (the accumulator columns are units).
     static constexpr bool kDirect = true;
     static constexpr int kUnitsPerChunk = 8;
-    struct Pre { GateRaw<T> g[8]; float4 cn[2], cp[2], dc[2], dh[2]; };   // gates stay packed until used (register pressure of the split-K epilogue)
+    struct Pre { GateRaw<F> g[8]; float4 cn[2], cp[2], dc[2], dh[2]; };   // gates stay packed until used (register pressure of the split-K epilogue)
     struct Params {
         LstmBwdArgs a; T* dg_out;
     };
@@ -596,7 +616,7 @@ struct EpiLstmBwd {
         if (gr >= a.M) return;
         const size_t o = (size_t)gr * a.Hp + u0;
         if (part != 2) {
-            const T* g = reinterpret_cast<const T*>(a.gates) + (size_t)gr * 4 * a.Hp + 4 * u0;
+            const F* g = reinterpret_cast<const F*>(a.gates) + (size_t)gr * 4 * a.Hp + 4 * u0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) load_gates_raw(g + 4 * j, pre.g[j]);
             const float4* dc = reinterpret_cast<const float4*>(a.dc + o); pre.dc[0] = dc[0]; pre.dc[1] = dc[1];
@@ -651,7 +671,7 @@ struct EpiLstmBwd {
         for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::NTHREADS) {
             int r = idx / Cfg::BN, c = idx % Cfg::BN, gr = m0 + r;
             if (gr >= p.a.M) continue;
-            lstm_bwd_unit<T>(p.a, p.dg_out, gr, n0 + c, Cs[r * Cfg::LDC + c]);
+            lstm_bwd_unit<T, F>(p.a, p.dg_out, gr, n0 + c, Cs[r * Cfg::LDC + c]);
         }
     }
 };

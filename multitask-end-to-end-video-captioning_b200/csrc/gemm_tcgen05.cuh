@@ -22,7 +22,10 @@ namespace tc {
 static __device__ unsigned long long* g_probe = nullptr;   // static: one copy per translation unit (s2vt_debug_probe arms the S2VT engine's)
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-constexpr int BM = 128, BK = 64, NTHREADS = 192;   // NTHREADS: staged-epilogue kernels (2 role warps + 4 epilogue warps)
+constexpr int BM = 128, BK = 64, NTHREADS = 192;
+constexpr uint32_t FMT_A_F16 = 1u << 7, FMT_B_F16 = 1u << 10;
+template <typename T> struct FmtOf { static constexpr uint32_t A = 0, B = 0; };
+template <> struct FmtOf<f16> { static constexpr uint32_t A = FMT_A_F16, B = FMT_B_F16; };   // NTHREADS: staged-epilogue kernels (2 role warps + 4 epilogue warps)
 
 template <int BN_, int NTHREADS_ = tc::NTHREADS>
 struct Cfg {
@@ -38,7 +41,9 @@ struct Cfg {
     static constexpr int SMEM_BYTES = (PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES) + BAR_BYTES + 1024;   // + alignment slack
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;   // power of two >= 32
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6), a/b_format BF16 [7,10)/[10,13),
-    // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+    // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).  Format 0 = F16, 1 = BF16: the kernels take a run-time
+    // `fmt` word whose bits are CLEARED from IDESC -- FMT_A_F16 / FMT_B_F16 turn an operand into IEEE fp16 (same tensor maps: TMA
+    // moves 16-bit payloads), so fp16 x fp16, bf16 x bf16 and the mixed fp16 x bf16 weight-gradient products share one kernel.
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
@@ -207,14 +212,14 @@ template <int BN> struct ChainAcc { static constexpr int N = 1; };
 
 template <int BN, class Epi, int KS, int CX = 1, int CY = 1, bool MN = false>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                                                                      int K, int a_rows, typename Epi::Params ep) {
+                                                                      int K, int a_rows, uint32_t fmt, typename Epi::Params ep) {
     // a_rows: rows of the A K-block actually fetched (TMA box height).  Problems with M <= 64 fetch 64 rows only; the rest of
     // the 128-row smem tile is stale and only feeds accumulator rows >= M, which no epilogue reads.
     using C = Cfg<BN, Threads<BN, Epi>::N>;
     static_assert(KS == 1 || (KS == 4 && Epi::kDirect), "split-K needs a direct epilogue and a cluster of 4");
     static_assert(KS == 1 || (CX == 1 && CY == 1), "split-K and multicast clusters are exclusive");
     static_assert(!MN || (KS == 1 && CX == 1 && CY == 1), "MN-major operands: plain kernel only");
-    constexpr uint32_t IDESC = C::IDESC | (MN ? ((1u << 15) | (1u << 16)) : 0u);
+    const uint32_t IDESC = (C::IDESC | (MN ? ((1u << 15) | (1u << 16)) : 0u)) & ~fmt;
     constexpr bool MC = CX * CY > 1;
     constexpr int NACC = ChainAcc<BN>::N;
     constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
@@ -506,7 +511,7 @@ inline const CUtensorMap* get_map3d(MapCache& cache, const void* ptr, int rows, 
 // row-major; C[M, N] = X^T . Y.
 template <int BN, class Epi, int KS = 1, int CX = 1, int CY = 1, bool MN = false>
 inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K,
-                          const typename Epi::Params& ep, bool pdl = false) {
+                          const typename Epi::Params& ep, bool pdl = false, uint32_t fmt = 0) {
     if (M <= 0) return cudaSuccess;
     constexpr int NT = Threads<BN, Epi>::N;
     using C = Cfg<BN, NT>;
@@ -547,7 +552,7 @@ inline cudaError_t launch(MapCache& cache, cudaStream_t st, const bf16* A, int l
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, a_rows, ep);
+    return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, a_rows, fmt, ep);
 }
 
 }  // namespace tc

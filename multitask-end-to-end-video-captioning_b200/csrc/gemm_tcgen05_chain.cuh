@@ -45,8 +45,9 @@ template <int BN, class Epi, int KS, bool WS, int CX = 1>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                             int K, int a_rows, int a_row0, int a_row_stride,
                                                                             const typename Epi::Params* __restrict__ steps, int nsteps,
-                                                                            unsigned* __restrict__ gbar) {
+                                                                            unsigned* __restrict__ gbar, uint32_t fmt) {
     using C = Cfg<BN, Threads<BN, Epi>::N>;
+    const uint32_t IDESC = C::IDESC & ~fmt;           // fmt: operand formats (FMT_A_F16 | FMT_B_F16 select fp16, gemm_tcgen05.cuh)
     static_assert(Epi::kDirect, "chain kernel: register epilogues only");
     static_assert(KS == 1 || KS == 4, "split-K cluster of 4 or none");
     static_assert(CX == 1 || (WS && KS == 1), "activation multicast: weights-stationary forward chains only");
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                     const uint64_t adesc = make_desc(smem_u32(smem + i * WS_A)), bdesc = make_desc(smem_u32(wsm + i * C::B_BYTES));
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < C::BK / 16; ++k) mma_bf16(tmem_base + (uint32_t)((i % NACC) * BN), adesc + 2 * k, bdesc + 2 * k, C::IDESC, i >= NACC || k != 0);
+                        for (int k = 0; k < C::BK / 16; ++k) mma_bf16(tmem_base + (uint32_t)((i % NACC) * BN), adesc + 2 * k, bdesc + 2 * k, IDESC, i >= NACC || k != 0);
                     }
                 }
             } else {
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                     const uint64_t adesc = make_desc(a), bdesc = make_desc(a + C::A_BYTES);
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < C::BK / 16; ++k) mma_bf16(tmem_base + (uint32_t)((i % NACC) * BN), adesc + 2 * k, bdesc + 2 * k, C::IDESC, i >= NACC || k != 0);
+                        for (int k = 0; k < C::BK / 16; ++k) mma_bf16(tmem_base + (uint32_t)((i % NACC) * BN), adesc + 2 * k, bdesc + 2 * k, IDESC, i >= NACC || k != 0);
                         mma_commit(empty + st);
                     }
                 }
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
 // Returns cudaErrorLaunchOutOfResources (without launching) if the grid cannot be co-resident.
 template <int BN, class Epi, int KS, bool WS = false, int CX = 1>
 inline cudaError_t launch_chain(MapCache& cache, cudaStream_t st, const bf16* A, int lda, int a_total_rows, int a_row0, int a_row_stride, const bf16* B,
-                                int ldb, int M, int N, int K, const typename Epi::Params* steps_dev, int nsteps, unsigned* gbar, bool pdl) {
+                                int ldb, int M, int N, int K, const typename Epi::Params* steps_dev, int nsteps, unsigned* gbar, bool pdl, uint32_t fmt = 0) {
     constexpr int NT = Threads<BN, Epi>::N;
     using C = Cfg<BN, NT>;
     constexpr int SMEM = (WS ? 16 * (64 * 128 + C::B_BYTES) + 512 + 1024 : C::SMEM_BYTES + 512) + (KS > 1 ? KS * 32 * BN * 4 : 0);
@@ -359,7 +360,7 @@ inline cudaError_t launch_chain(MapCache& cache, cudaStream_t st, const bf16* A,
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, a_rows, a_row0, a_row_stride, steps_dev, nsteps, gbar);
+    return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, a_rows, a_row0, a_row_stride, steps_dev, nsteps, gbar, fmt);
 }
 
 }  // namespace tc

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(576) sample_chain_kernel(const __grid_constant
                                                            int K, int n_mt, int n_cell_n, int n_pick_n,
                                                            const typename CellEpi::Params* __restrict__ cell_steps,
                                                            const typename PickEpi::Params* __restrict__ pick_steps, int nsteps,
-                                                           unsigned* __restrict__ gbar) {
+                                                           unsigned* __restrict__ gbar, uint32_t fmt) {
     static_assert(CellEpi::kDirect && !PickEpi::kDirect, "cell: register epilogue, pick: staged epilogue");
     constexpr int NT = 576;
     using CC = Cfg<128, NT>;           // cell tiles
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(576) sample_chain_kernel(const __grid_constant
                     const uint64_t adesc = make_desc(a), bdesc = make_desc(a + CC::A_BYTES);
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, CC::IDESC, i > 0 || k != 0);
+                        for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, (CC::IDESC & ~fmt), i > 0 || k != 0);
                         mma_commit(emptyC + st);
                     }
                 }
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(576) sample_chain_kernel(const __grid_constant
                     const uint64_t adesc = make_desc(a), bdesc = make_desc(a + CP::A_BYTES);
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, CP::IDESC, i > 0 || k != 0);
+                        for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, (CP::IDESC & ~fmt), i > 0 || k != 0);
                         mma_commit(emptyP + st);
                     }
                 }
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(576) sample_chain_ovl_kernel(const __grid_cons
                                                                int K, int n_mt, int n_cell_n, int n_pick_n,
                                                                const typename CellEpi::Params* __restrict__ cell_steps,
                                                                const typename PickEpi::Params* __restrict__ pick_steps, int nsteps,
-                                                               unsigned* __restrict__ gbar) {
+                                                               unsigned* __restrict__ gbar, uint32_t fmt) {
     static_assert(CellEpi::kDirect && !PickEpi::kDirect, "cell: register epilogue, pick: staged epilogue");
     constexpr int NT = 576;
     using CC = Cfg<128, NT>;
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(576) sample_chain_ovl_kernel(const __grid_cons
                 const uint64_t adesc = make_desc(a), bdesc = make_desc(a + CC::A_BYTES);
                 if (leader) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base + CELL_COL, adesc + 2 * k, bdesc + 2 * k, CC::IDESC, i > 0 || k != 0);
+                    for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base + CELL_COL, adesc + 2 * k, bdesc + 2 * k, (CC::IDESC & ~fmt), i > 0 || k != 0);
                     mma_commit(emptyS + st);
                 }
             }
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(576) sample_chain_ovl_kernel(const __grid_cons
                     const uint64_t adesc = make_desc(a), bdesc = make_desc(a + CP::A_BYTES);
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, CP::IDESC, i > 0 || k != 0);
+                        for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, (CP::IDESC & ~fmt), i > 0 || k != 0);
                         mma_commit(emptyP + st);
                     }
                 }
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(576) sample_chain_ovl_kernel(const __grid_cons
 template <class CellEpi, class PickEpi, bool OVL = true>
 inline cudaError_t launch_sample_chain(MapCache& cache, cudaStream_t st, const bf16* H0, const bf16* H1, int ldh, int rows, const bf16* Wh, int ldwh, int Ncell,
                                        const bf16* Wo, int ldwo, int Npick, int K, const typename CellEpi::Params* cell_dev,
-                                       const typename PickEpi::Params* pick_dev, int nsteps, unsigned* gbar, bool pdl) {
+                                       const typename PickEpi::Params* pick_dev, int nsteps, unsigned* gbar, bool pdl, uint32_t fmt = 0) {
     constexpr int NT = 576;
     using CC = Cfg<128, NT>;
     using CP = Cfg<256, NT>;
@@ -534,7 +534,7 @@ inline cudaError_t launch_sample_chain(MapCache& cache, cudaStream_t st, const b
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, kern, *mh0, *mh1, *mwh, *mwo, K, n_mt, n_cell_n, n_pick_n, cell_dev, pick_dev, nsteps, gbar);
+    return cudaLaunchKernelEx(&cfg, kern, *mh0, *mh1, *mwh, *mwo, K, n_mt, n_cell_n, n_pick_n, cell_dev, pick_dev, nsteps, gbar, fmt);
 }
 
 }  // namespace tc

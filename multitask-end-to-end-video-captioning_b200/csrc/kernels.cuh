@@ -52,20 +52,29 @@ __global__ void convert_video_kernel(const float* __restrict__ video, const int*
     for (int c = threadIdx.x; c < Dp; c += blockDim.x) d[c] = from_f32<T>(c < D ? s[c] : 0.f);
 }
 
-// Generic tiled transpose of a compute-dtype matrix: dst[c][r] = src[r][c], r < R, c < C (dst padded region untouched).
-template <typename T>
-__global__ void transpose_kernel(const T* __restrict__ src, int lds, int R, int C, T* __restrict__ dst, int ldd) {
-    __shared__ T tile[32][34];
+// Generic tiled transpose of a compute-dtype matrix: dst[c][r] = src[r][c], r < R, c < C (dst padded region untouched); TI != TO
+// converts on the way (fp16 activations -> bf16 for the K-major checker mainloops).
+template <typename TI, typename TO = TI>
+__global__ void transpose_kernel(const TI* __restrict__ src, int lds, int R, int C, TO* __restrict__ dst, int ldd) {
+    __shared__ TO tile[32][34];
     int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int r = r0 + i, c = c0 + threadIdx.x;
-        if (r < R && c < C) tile[i][threadIdx.x] = src[(size_t)r * lds + c];
+        if (r < R && c < C) tile[i][threadIdx.x] = from_f32<TO>(to_f32(src[(size_t)r * lds + c]));
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int c = c0 + i, r = r0 + threadIdx.x;
         if (r < R && c < C) dst[(size_t)c * ldd + r] = tile[threadIdx.x][i];
     }
+}
+
+// element-wise type conversion (4 elements per thread)
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ src, size_t n, TO* __restrict__ dst) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (i + k < n) dst[i + k] = from_f32<TO>(to_f32(src[i + k]));
 }
 
 // fp32 -> compute dtype copy with optional dropout (used for the dropout-applied LSTM1 output of the training graph):

@@ -17,11 +17,11 @@
 #include "gemm_tcgen05_sample.cuh"
 #include "kernels.cuh"
 
-template <typename T>
+template <typename T, typename F>
 __global__ void lstm_bwd_elem_kernel(LstmBwdArgs a, T* dg_out) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.M * a.Hp) return;
-    lstm_bwd_unit<T>(a, dg_out, idx / a.Hp, idx % a.Hp, 0.f);
+    lstm_bwd_unit<T, F>(a, dg_out, idx / a.Hp, idx % a.Hp, 0.f);
 }
 
 // out[r, :] = in[r % B, :]  (replicate the per-video encoder state over the K+1 decode rows)
@@ -269,8 +269,8 @@ template <typename T> struct EpiBytes<EpiLstmFwd<T>> {
         return b;
     }
 };
-template <typename T> struct EpiBytes<EpiLstmBwd<T>> {
-    static double get(const s2vt_handle* h, const typename EpiLstmBwd<T>::Params& p, int M) {
+template <typename T, typename F> struct EpiBytes<EpiLstmBwd<T, F>> {
+    static double get(const s2vt_handle* h, const typename EpiLstmBwd<T, F>::Params& p, int M) {
         const double H = h->H, G = 4.0 * h->H;
         return M * G * sizeof(T) + M * H * 4 * 4 + (p.a.dh_ext ? M * H * 4 : 0) + M * G * sizeof(T);   // gates, c_new/c_prev/dc in/out, dh_ext, dG out
     }
@@ -296,9 +296,14 @@ static int chain_end(s2vt_handle* h, cudaStream_t st) {
 template <class Epi> struct kPdlLogits { static constexpr bool value = false; };
 template <typename T> struct kPdlLogits<EpiLogitsPick<T>> { static constexpr bool value = true; };
 template <typename T> struct kPdlLogits<EpiLogitsTopK<T>> { static constexpr bool value = true; };
+template <class Epi> struct IsCellBwd { static constexpr bool value = false; };
+template <typename T, typename F> struct IsCellBwd<EpiLstmBwd<T, F>> { static constexpr bool value = true; };
+// T: type of BOTH operands (forward products: Fwd<T>::type x Fwd<T>::type, backward products: T x T; the mixed weight-gradient
+// products go through wgrad below).  16-bit types take the tcgen05 path, the operand format travels in the `fmt` word.
 template <typename T, class Cfg, class Epi>
 static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const typename Epi::Params& ep,
                 int logical_k = 0, int logical_m = 0) {
+    constexpr uint32_t fmt = tc::FmtOf<T>::A | tc::FmtOf<T>::B;
     s2vt_handle::ProfRec rec;
     const bool in_chain = h->prof && h->chain_open && Cfg::BM < 128;
     const bool bracket = h->prof && !in_chain;
@@ -318,8 +323,8 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
     }
     h->launches++;
     bool done = false;
-    if constexpr (std::is_same<T, bf16>::value) {
-        if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC) {   // tcgen05 + TMA + TMEM path (default for bf16)
+    if constexpr (sizeof(T) == 2) {
+        if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC) {   // tcgen05 + TMA + TMEM path (default for the 16-bit operand types)
             if (!h->tc_cache) h->tc_cache = new tc::MapCache();
             tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
             // per-step GEMMs are launched as programmatic dependents: their prologue and weight prefetch overlap the tail of the
@@ -328,26 +333,26 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
                 // batched GEMMs are bound by L2 -> SM bandwidth, so use the widest tile (128 x 256: 85 flop per byte fetched vs
                 // 64 for 128 x 128).  gemm_backend 3 / 4 select the 128-wide tile without / with 2x2 TMA multicast (measured
                 // slower on B200: at cluster sizes <= 4 multicast does not reduce L2 traffic).
-                if (h->cfg.gemm_backend == 4 && (N / 128) % 2 == 0) CUDA_TRY(h, (tc::launch<128, Epi, 1, 2, 2>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
-                else if (h->cfg.gemm_backend == 3 || N % 256 != 0) CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false)));
-                else CUDA_TRY(h, (tc::launch<256, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, kPdlLogits<Epi>::value)));
+                if (h->cfg.gemm_backend == 4 && (N / 128) % 2 == 0) CUDA_TRY(h, (tc::launch<128, Epi, 1, 2, 2>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false, fmt)));
+                else if (h->cfg.gemm_backend == 3 || N % 256 != 0) CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false, fmt)));
+                else CUDA_TRY(h, (tc::launch<256, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, kPdlLogits<Epi>::value, fmt)));
             }
-            else if constexpr (std::is_same<Epi, EpiLstmBwd<bf16>>::value) {
+            else if constexpr (IsCellBwd<Epi>::value) {
                 // cell backward: K = 4H is long and N = H gives few tiles -> split K over a cluster of 4 CTAs (DSMEM reduction)
                 if ((K / tc::BK) % 4 == 0) {
-                    if (M > 128 && h->cfg.gemm_backend != 7) CUDA_TRY(h, (tc::launch<128, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
-                    else if (M > 128) CUDA_TRY(h, (tc::launch<64, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
-                    else CUDA_TRY(h, (tc::launch<32, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
-                } else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+                    if (M > 128 && h->cfg.gemm_backend != 7) CUDA_TRY(h, (tc::launch<128, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true, fmt)));
+                    else if (M > 128) CUDA_TRY(h, (tc::launch<64, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true, fmt)));
+                    else CUDA_TRY(h, (tc::launch<32, Epi, 4>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true, fmt)));
+                } else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true, fmt)));
             }
             else if (M > 128 && N > 1024) {
                 // every column tile of a row block reads the same activations: fetch them once per cluster of 8 (TMA multicast)
-                if (h->cfg.gemm_backend == 5 && (N / 64) % 8 == 0) CUDA_TRY(h, (tc::launch<64, Epi, 1, 8, 1>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
-                else if (h->cfg.gemm_backend == 6 && (N / 64) % 4 == 0) CUDA_TRY(h, (tc::launch<64, Epi, 1, 4, 1>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
-                else if (h->cfg.gemm_backend == 7) CUDA_TRY(h, (tc::launch<64, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
-                else CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));   // <= 148 CTAs, one per SM: balanced smem fill
+                if (h->cfg.gemm_backend == 5 && (N / 64) % 8 == 0) CUDA_TRY(h, (tc::launch<64, Epi, 1, 8, 1>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true, fmt)));
+                else if (h->cfg.gemm_backend == 6 && (N / 64) % 4 == 0) CUDA_TRY(h, (tc::launch<64, Epi, 1, 4, 1>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true, fmt)));
+                else if (h->cfg.gemm_backend == 7) CUDA_TRY(h, (tc::launch<64, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true, fmt)));
+                else CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true, fmt)));   // <= 148 CTAs, one per SM: balanced smem fill
             }
-            else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true)));
+            else CUDA_TRY(h, (tc::launch<32, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, true, fmt)));
             done = true;
         }
     }
@@ -359,13 +364,24 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
 // Weight gradient  grad (+)= X^T . Y  over R rows (X [R, ldx]: Mf padded features, Y [R, ldy]: Nf padded features).
 // tcgen05 path: MN-major operand descriptors read X and Y as they lie (no transposed copies, ragged R zero-filled by TMA).
 // Other mainloops need K-major operands: X and Y are transposed into the scratch buffers first.
-template <typename T> static int transpose(s2vt_handle* h, cudaStream_t st, const T* src, int lds, int R, int C, T* dst, int ldd, int rows_dst_padded);
+template <typename TI, typename TO> static int transpose(s2vt_handle* h, cudaStream_t st, const TI* src, int lds, int R, int C, TO* dst, int ldd, int rows_dst_padded);
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
-template <typename T>
-static int wgrad(s2vt_handle* h, cudaStream_t st, const T* X, int ldx, int Mf, const T* Y, int ldy, int Nf, int R, const EpiGradStore::Params& ep,
+// X: a forward activation (type F = Fwd<T>::type), Y: a gradient (type T).  In the bf16 mode that is an fp16 x bf16 product: one
+// tcgen05 kind::f16 instruction with a_format F16 and b_format BF16.
+template <typename T, typename F>
+static int wgrad(s2vt_handle* h, cudaStream_t st, const F* X, int ldx, int Mf, const T* Y, int ldy, int Nf, int R, const EpiGradStore::Params& ep,
                  T* tA, T* tB, int logical_m) {
-    if constexpr (std::is_same<T, bf16>::value) {
+    if constexpr (sizeof(T) == 2) {
+        uint32_t fmt = tc::FmtOf<F>::A | tc::FmtOf<T>::B;
         if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC && h->cfg.gemm_backend != 8) {
+            // A/B switch (debug): S2VT_WGRAD_CONVERT=1 rounds the fp16 activations to bf16 first, so the product is bf16 x bf16
+            static const bool convert_x = getenv("S2VT_WGRAD_CONVERT") && atoi(getenv("S2VT_WGRAD_CONVERT")) != 0;
+            if (convert_x && !std::is_same<F, T>::value) {
+                const size_t n = (size_t)R * ldx;
+                convert_kernel<F, T><<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(X, n, tA); KCHECK(h);
+                X = reinterpret_cast<const F*>(tA);
+                fmt = tc::FmtOf<T>::A | tc::FmtOf<T>::B;
+            }
             s2vt_handle::ProfRec rec;
             if (h->prof) {
                 rec.a = prof_event(h); rec.b = prof_event(h);
@@ -377,15 +393,15 @@ static int wgrad(s2vt_handle* h, cudaStream_t st, const T* X, int ldx, int Mf, c
             h->launches++;
             if (!h->tc_cache) h->tc_cache = new tc::MapCache();
             tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
-            if (Nf % 256 == 0) CUDA_TRY(h, (tc::launch<256, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false)));
-            else CUDA_TRY(h, (tc::launch<128, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false)));
+            if (Nf % 256 == 0) CUDA_TRY(h, (tc::launch<256, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false, fmt)));
+            else CUDA_TRY(h, (tc::launch<128, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false, fmt)));
             if (h->prof) { cudaEventRecord(rec.b, st); h->prof_recs.push_back(rec); }
             return 0;
         }
     }
     const int Rp = ru(R, S2VT_PAD);
-    TRY(transpose<T>(h, st, X, ldx, R, Mf, tA, Rp, Mf));
-    TRY(transpose<T>(h, st, Y, ldy, R, Nf, tB, Rp, Nf));
+    TRY((transpose<F, T>(h, st, X, ldx, R, Mf, tA, Rp, Mf)));     // the K-major mainloops multiply like types: X is converted on the way
+    TRY((transpose<T, T>(h, st, Y, ldy, R, Nf, tB, Rp, Nf)));
     return gemm<T, CfgBig, EpiGradStore>(h, st, tA, Rp, tB, Rp, Mf, Nf, Rp, ep, R, logical_m);
 }
 template <typename T>
@@ -411,7 +427,8 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
     if (n == 0) return 0;
     chain_begin(h, st);
     bool done = false;
-    if constexpr (std::is_same<T, bf16>::value) {
+    if constexpr (sizeof(T) == 2) {
+        constexpr uint32_t fmt = tc::FmtOf<T>::A | tc::FmtOf<T>::B;
         if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC && h->cfg.gemm_backend != 9 && n >= 2) {
             if (!h->tc_cache) h->tc_cache = new tc::MapCache();
             tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
@@ -420,24 +437,24 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
             unsigned* gbar = h->gbar + (st == h->side ? 16 : 0);
             const P* dp = (const P*)dev_params;
             cudaError_t e;
-            constexpr bool bwd = std::is_same<Epi, EpiLstmBwd<bf16>>::value;
+            constexpr bool bwd = IsCellBwd<Epi>::value;
             if constexpr (bwd) {
                 if ((c.K / tc::BK) % 4 != 0) e = cudaErrorLaunchOutOfResources;
-                else if (c.M > 128) e = tc::launch_chain<128, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                else if (c.M > 128) e = tc::launch_chain<128, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt);
                 else {
                     e = cudaErrorLaunchOutOfResources;
-                    if (c.M <= 64 && h->cfg.gemm_backend != 10) e = tc::launch_chain<32, Epi, 4, true>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
-                    if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true); }
+                    if (c.M <= 64 && h->cfg.gemm_backend != 10) e = tc::launch_chain<32, Epi, 4, true>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt);
+                    if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }
                 }
             } else {
-                if (c.M > 128) e = tc::launch_chain<128, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
+                if (c.M > 128) e = tc::launch_chain<128, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt);
                 else {
                     e = cudaErrorLaunchOutOfResources;   // weights-stationary variant first (rows <= 64, K <= 16 blocks)
                     // weights stationary + the activation rows multicast over clusters of 8 column tiles (gemm_backend 11 / 12: clusters of 4 / none)
-                    if (c.M <= 64 && h->cfg.gemm_backend != 10 && h->cfg.gemm_backend != 11 && h->cfg.gemm_backend != 12) e = tc::launch_chain<32, Epi, 1, true, 8>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true);
-                    if (e == cudaErrorLaunchOutOfResources && c.M <= 64 && h->cfg.gemm_backend == 11) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1, true, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true); }
-                    if (e == cudaErrorLaunchOutOfResources && c.M <= 64 && h->cfg.gemm_backend != 10) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1, true>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true); }
-                    if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true); }
+                    if (c.M <= 64 && h->cfg.gemm_backend != 10 && h->cfg.gemm_backend != 11 && h->cfg.gemm_backend != 12) e = tc::launch_chain<32, Epi, 1, true, 8>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt);
+                    if (e == cudaErrorLaunchOutOfResources && c.M <= 64 && h->cfg.gemm_backend == 11) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1, true, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }
+                    if (e == cudaErrorLaunchOutOfResources && c.M <= 64 && h->cfg.gemm_backend != 10) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1, true>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }
+                    if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }
                 }
             }
             if (e == cudaSuccess) {
@@ -496,6 +513,7 @@ static int refresh_impl(s2vt_handle* h, cudaStream_t st) {
         CUDA_TRY(h, cudaMemsetAsync(h->state + begin, 0, end - begin, st));
         h->copies_zeroed = true;
     }
+    typedef typename Fwd<T>::type F;      // K-major copies feed the forward products (fp16 in the bf16 mode), TF-layout copies the backward ones
     const float* W1 = h->P_(h->iW1); const float* W2 = h->P_(h->iW2);
     const int G = 4 * H;
     TRY(ensure_side(h));
@@ -503,29 +521,29 @@ static int refresh_impl(s2vt_handle* h, cudaStream_t st) {
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));                 // parameters (and the zeroing) are final on `st` here
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
     // early half, caller's stream: what the next call needs first (frame projection and LSTM1 forward)
-    TRY(pack<T>(h, st, h->P_(h->iWe), E, D, E, h->WeT, Dp, 0, 1));                         // WeT [Ep, Dp]
-    TRY(pack<T>(h, st, W1, G, E, G, h->W1xT, Ep, H, 1));                                   // W1xT [Gp, Ep]
-    TRY(pack<T>(h, st, W1 + (size_t)E * G, G, H, G, h->W1hT, Hp, H, 1));                   // W1hT [Gp, Hp]
+    TRY(pack<F>(h, st, h->P_(h->iWe), E, D, E, h->WeT, Dp, 0, 1));                         // WeT [Ep, Dp]
+    TRY(pack<F>(h, st, W1, G, E, G, h->W1xT, Ep, H, 1));                                   // W1xT [Gp, Ep]
+    TRY(pack<F>(h, st, W1 + (size_t)E * G, G, H, G, h->W1hT, Hp, H, 1));                   // W1hT [Gp, Hp]
     pack_vector_kernel<<<(E + 255) / 256, 256, 0, st>>>(h->P_(h->ibe), E, h->be_p, 0); KCHECK(h);
     pack_vector_kernel<<<(G + 255) / 256, 256, 0, st>>>(h->P_(h->ib1), G, h->b1_p, H); KCHECK(h);
     // late half, side stream: overlaps the next call's frame projection and LSTM1 chain (see wait_late_weights)
     TRY(pack<T>(h, s2, W1, G, E, G, h->W1x, Gp, H, 0));                                    // W1x  [Ep, Gp]
     TRY(pack<T>(h, s2, W1 + (size_t)E * G, G, H, G, h->W1h, Gp, H, 0));                    // W1h  [Hp, Gp]
-    TRY(pack<T>(h, s2, W2, G, H, G, h->W2xT, Hp, H, 1));                                   // rows [0,H): out1
+    TRY(pack<F>(h, s2, W2, G, H, G, h->W2xT, Hp, H, 1));                                   // rows [0,H): out1
     TRY(pack<T>(h, s2, W2, G, H, G, h->W2x, Gp, H, 0));
-    TRY(pack<T>(h, s2, W2 + (size_t)H * G, G, E, G, h->W2eT, Ep, H, 1));                   // rows [H,H+E): word embedding
+    TRY(pack<F>(h, s2, W2 + (size_t)H * G, G, E, G, h->W2eT, Ep, H, 1));                   // rows [H,H+E): word embedding
     TRY(pack<T>(h, s2, W2 + (size_t)H * G, G, E, G, h->W2e, Gp, H, 0));
-    TRY(pack<T>(h, s2, W2 + (size_t)(H + E) * G, G, H, G, h->W2hT, Hp, H, 1));             // rows [H+E, 2H+E): h2
+    TRY(pack<F>(h, s2, W2 + (size_t)(H + E) * G, G, H, G, h->W2hT, Hp, H, 1));             // rows [H+E, 2H+E): h2
     TRY(pack<T>(h, s2, W2 + (size_t)(H + E) * G, G, H, G, h->W2h, Gp, H, 0));
-    TRY(pack<T>(h, s2, h->P_(h->iWo), V, H, V, h->WoT, Hp, 0, 1));                         // WoT [Vp, Hp]
+    TRY(pack<F>(h, s2, h->P_(h->iWo), V, H, V, h->WoT, Hp, 0, 1));                         // WoT [Vp, Hp]
     TRY(pack<T>(h, s2, h->P_(h->iWo), V, H, V, h->Wo, Vp, 0, 0));                          // Wo  [Hp, Vp]
-    TRY(pack<T>(h, s2, h->P_(h->iWemb), E, V, E, h->WembC, Ep, 0, 0));                     // Wemb [Vp, Ep]
-    if (h->A) TRY(pack<T>(h, s2, h->P_(h->iAW), h->A, D, h->A, h->attrWT, Dp, 0, 1));      // attrWT [Ap, Dp]
+    TRY(pack<F>(h, s2, h->P_(h->iWemb), E, V, E, h->WembC, Ep, 0, 0));                     // Wemb [Vp, Ep]
+    if (h->A) TRY(pack<F>(h, s2, h->P_(h->iAW), h->A, D, h->A, h->attrWT, Dp, 0, 1));      // attrWT [Ap, Dp]
     pack_vector_kernel<<<(G + 255) / 256, 256, 0, s2>>>(h->P_(h->ib2), G, h->b2_p, H); KCHECK(h);
     pack_vector_kernel<<<(V + 255) / 256, 256, 0, s2>>>(h->P_(h->ibo), V, h->bo_p, 0); KCHECK(h);
     // Etab[v, :] = Wemb[v, :] . W2[emb rows]  (packed gate order) -- the word-embedding contribution to LSTM2's gates
-    typename EpiStore<T>::Params ep = {h->Etab, nullptr, Gp, nullptr, Vp, 0};
-    TRY((gemm<T, CfgBig, EpiStore<T>>(h, s2, h->WembC, Ep, h->W2eT, Ep, Vp, Gp, Ep, ep)));
+    typename EpiStore<F>::Params ep = {h->Etab, nullptr, Gp, nullptr, Vp, 0};
+    TRY((gemm<F, CfgBig, EpiStore<F>>(h, s2, h->WembC, Ep, h->W2eT, Ep, Vp, Gp, Ep, ep)));
     CUDA_TRY(h, cudaEventRecord(h->ev_refresh, s2));
     h->fresh = true;
     h->front_valid = false;
@@ -541,39 +559,42 @@ extern "C" int s2vt_refresh(s2vt_handle* h, s2vt_stream st) {
 // forward plans
 // =================================================================================================================
 template <typename T>
-struct Front {   // per-video part: frame projection + LSTM1 over all T steps
-    T* Xc; T* img; float* G1x; T* h1_all; float* c1_all; T* gates1; void* chain;
+struct Front {   // per-video part: frame projection + LSTM1 over all T steps (forward values: type F)
+    typedef typename Fwd<T>::type F;
+    F* Xc; F* img; float* G1x; F* h1_all; float* c1_all; F* gates1; void* chain;
 };
 template <typename T>
 static void plan_front(const s2vt_handle* h, Arena& a, int B, bool train, Front<T>& f) {
-    f.Xc = a.take<T>((size_t)h->Tv * B * h->Dp);
-    f.img = a.take<T>((size_t)h->Tv * B * h->Ep);
+    typedef typename Fwd<T>::type F;
+    f.Xc = a.take<F>((size_t)h->Tv * B * h->Dp);
+    f.img = a.take<F>((size_t)h->Tv * B * h->Ep);
     f.G1x = a.take<float>((size_t)h->Tv * B * h->Gp);
-    f.h1_all = a.take<T>((size_t)(h->T + 1) * B * h->Hp);
+    f.h1_all = a.take<F>((size_t)(h->T + 1) * B * h->Hp);
     f.c1_all = a.take<float>((size_t)(h->T + 1) * B * h->Hp);
-    f.gates1 = train ? a.take<T>((size_t)h->T * B * h->Gp) : nullptr;
+    f.gates1 = train ? a.take<F>((size_t)h->T * B * h->Gp) : nullptr;
     f.chain = a.take<char>((size_t)(h->T + 1) * 512);   // per-step epilogue parameters of the persistent chains (<= 512 B each)
 }
 
 template <typename T>
 static int run_front(s2vt_handle* h, cudaStream_t st, const float* video, int B, Front<T>& f) {
+    typedef typename Fwd<T>::type F;
     const int Tv = h->Tv, T_ = h->T, Dp = h->Dp, Ep = h->Ep, Hp = h->Hp, Gp = h->Gp;
-    convert_video_kernel<T><<<Tv * B, 256, 0, st>>>(video, nullptr, B, Tv, h->D, Dp, f.Xc); KCHECK(h);
+    convert_video_kernel<F><<<Tv * B, 256, 0, st>>>(video, nullptr, B, Tv, h->D, Dp, f.Xc); KCHECK(h);
     {   // img = Xc . We + be   (:107-111 tf.nn.xw_plus_b)
-        typename EpiStore<T>::Params ep = {nullptr, f.img, Ep, h->be_p, Tv * B, 0};
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, f.Xc, Dp, h->WeT, Dp, Tv * B, Ep, Dp, ep)));
+        typename EpiStore<F>::Params ep = {nullptr, f.img, Ep, h->be_p, Tv * B, 0};
+        TRY((gemm<F, CfgBig, EpiStore<F>>(h, st, f.Xc, Dp, h->WeT, Dp, Tv * B, Ep, Dp, ep)));
     }
     {   // G1x = img . W1[x rows]  (the input half of LSTM1's concat([x, h]) W, all frames at once)
-        typename EpiStore<T>::Params ep = {f.G1x, nullptr, Gp, nullptr, Tv * B, 0};
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, f.img, Ep, h->W1xT, Ep, Tv * B, Gp, Ep, ep)));
+        typename EpiStore<F>::Params ep = {f.G1x, nullptr, Gp, nullptr, Tv * B, 0};
+        TRY((gemm<F, CfgBig, EpiStore<F>>(h, st, f.img, Ep, h->W1xT, Ep, Tv * B, Gp, Ep, ep)));
     }
-    CUDA_TRY(h, cudaMemsetAsync(f.h1_all, 0, (size_t)B * Hp * sizeof(T), st));
+    CUDA_TRY(h, cudaMemsetAsync(f.h1_all, 0, (size_t)B * Hp * sizeof(F), st));
     CUDA_TRY(h, cudaMemsetAsync(f.c1_all, 0, (size_t)B * Hp * sizeof(float), st));
-    StepChain<T, EpiLstmFwd<T>> ch;
+    StepChain<F, EpiLstmFwd<F>> ch;
     ch.A = f.h1_all; ch.lda = Hp; ch.a_total_rows = (T_ + 1) * B; ch.a_row0 = 0; ch.a_row_stride = B;
-    ch.B = (const T*)h->W1hT; ch.ldb = Hp; ch.M = B; ch.N = Gp; ch.K = Hp;
+    ch.B = (const F*)h->W1hT; ch.ldb = Hp; ch.M = B; ch.N = Gp; ch.K = Hp;
     for (int t = 0; t < T_; ++t) {   // :128-129 / :148-149 LSTM1; decoder steps get `padding` -> no input term (Q8)
-        typename EpiLstmFwd<T>::Params ep;
+        typename EpiLstmFwd<F>::Params ep;
         memset(&ep, 0, sizeof ep);
         ep.M = B; ep.Hp = Hp; ep.bias = h->b1_p;
         ep.add0 = t < Tv ? f.G1x + (size_t)t * B * Gp : nullptr;
@@ -583,26 +604,28 @@ static int run_front(s2vt_handle* h, cudaStream_t st, const float* video, int B,
         ep.keep = 1.f;
         ch.eps.push_back(ep);
     }
-    TRY((run_chain<T, EpiLstmFwd<T>>(h, st, ch, f.chain)));
+    TRY((run_chain<F, EpiLstmFwd<F>>(h, st, ch, f.chain)));
     return 0;
 }
 
 // ---- rollout (greedy + K samples), also the front half of beam search --------------------------------------------
 template <typename T>
 struct Roll {
-    Front<T> f; float* G2x; T* h2enc; float* c2e[2]; T* h2r[2]; float* c2r[2]; float* logits; int* tok[2]; int* ids; void* chain;
-    T* h2_final;   // encoder LSTM2 output state (rows of h2enc after the last frame)
+    typedef typename Fwd<T>::type F;
+    Front<T> f; float* G2x; F* h2enc; float* c2e[2]; F* h2r[2]; float* c2r[2]; float* logits; int* tok[2]; int* ids; void* chain;
+    F* h2_final;   // encoder LSTM2 output state (rows of h2enc after the last frame)
     float* pick_val; int* pick_idx; int pick_ld;
 };
 template <typename T>
 static void plan_roll(const s2vt_handle* h, Arena& a, int B, int R, Roll<T>& r) {
+    typedef typename Fwd<T>::type F;
     plan_front<T>(h, a, B, true, r.f);   // same layout as the training plan so the LSTM1 forward can be shared
     r.G2x = a.take<float>((size_t)h->T * B * h->Gp);
-    r.h2enc = a.take<T>((size_t)(h->Tv + 1) * B * h->Hp);   // LSTM2 state after every frame (one buffer: the persistent chain strides through it)
+    r.h2enc = a.take<F>((size_t)(h->Tv + 1) * B * h->Hp);   // LSTM2 state after every frame (one buffer: the persistent chain strides through it)
     r.h2_final = r.h2enc ? r.h2enc + (size_t)h->Tv * B * h->Hp : nullptr;
     for (int i = 0; i < 2; ++i) r.c2e[i] = a.take<float>((size_t)B * h->Hp);
     r.chain = a.take<char>((size_t)(h->T + 1) * 512);
-    for (int i = 0; i < 2; ++i) { r.h2r[i] = a.take<T>((size_t)R * h->Hp); r.c2r[i] = a.take<float>((size_t)R * h->Hp); }
+    for (int i = 0; i < 2; ++i) { r.h2r[i] = a.take<F>((size_t)R * h->Hp); r.c2r[i] = a.take<float>((size_t)R * h->Hp); }
     r.logits = a.take<float>((size_t)R * h->Vp);
     r.tok[0] = a.take<int>(R); r.tok[1] = a.take<int>(R);
     r.ids = a.take<int>((size_t)R * h->Tc);
@@ -613,28 +636,29 @@ static void plan_roll(const s2vt_handle* h, Arena& a, int B, int R, Roll<T>& r) 
 // frames -> (LSTM1 all steps, G2x all steps, LSTM2 encoder steps).  Leaves the encoder state in h2_final, c2e[Tv&1].
 template <typename T>
 static int run_encoder(s2vt_handle* h, cudaStream_t st, const float* video, int B, Roll<T>& r) {
+    typedef typename Fwd<T>::type F;
     const int Tv = h->Tv, T_ = h->T, Hp = h->Hp, Gp = h->Gp;
     h->front_valid = false;
     TRY(run_front<T>(h, st, video, B, r.f));
     h->front_valid = true; h->front_B = B; h->front_video = video;
     TRY(wait_late_weights(h, st));
     {   // G2x = h1 . W2[out1 rows] for every step (bare cells: no dropout in the samplers, Q2)
-        typename EpiStore<T>::Params ep = {r.G2x, nullptr, Gp, nullptr, T_ * B, 0};
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, r.f.h1_all + (size_t)B * Hp, Hp, h->W2xT, Hp, T_ * B, Gp, Hp, ep)));
+        typename EpiStore<F>::Params ep = {r.G2x, nullptr, Gp, nullptr, T_ * B, 0};
+        TRY((gemm<F, CfgBig, EpiStore<F>>(h, st, r.f.h1_all + (size_t)B * Hp, Hp, h->W2xT, Hp, T_ * B, Gp, Hp, ep)));
     }
-    CUDA_TRY(h, cudaMemsetAsync(r.h2enc, 0, (size_t)B * Hp * sizeof(T), st));
+    CUDA_TRY(h, cudaMemsetAsync(r.h2enc, 0, (size_t)B * Hp * sizeof(F), st));
     CUDA_TRY(h, cudaMemsetAsync(r.c2e[0], 0, (size_t)B * Hp * sizeof(float), st));
-    StepChain<T, EpiLstmFwd<T>> ch;
+    StepChain<F, EpiLstmFwd<F>> ch;
     ch.A = r.h2enc; ch.lda = Hp; ch.a_total_rows = (Tv + 1) * B; ch.a_row0 = 0; ch.a_row_stride = B;
-    ch.B = (const T*)h->W2hT; ch.ldb = Hp; ch.M = B; ch.N = Gp; ch.K = Hp;
+    ch.B = (const F*)h->W2hT; ch.ldb = Hp; ch.M = B; ch.N = Gp; ch.K = Hp;
     for (int t = 0; t < Tv; ++t) {   // :131-132 LSTM2 on concat([output1, padding]) -> the embedding rows see zeros (Q8)
-        typename EpiLstmFwd<T>::Params ep;
+        typename EpiLstmFwd<F>::Params ep;
         memset(&ep, 0, sizeof ep);
         ep.M = B; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp;
         ep.c_prev = r.c2e[t & 1]; ep.c_out = r.c2e[(t + 1) & 1]; ep.h_out = r.h2enc + (size_t)(t + 1) * B * Hp; ep.keep = 1.f;
         ch.eps.push_back(ep);
     }
-    TRY((run_chain<T, EpiLstmFwd<T>>(h, st, ch, r.chain)));
+    TRY((run_chain<F, EpiLstmFwd<F>>(h, st, ch, r.chain)));
     return 0;
 }
 
@@ -648,6 +672,7 @@ static int logits_tile_bn(const s2vt_handle* h) {
 template <typename T>
 static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B, int K, uint64_t seed, uint32_t row_base, int32_t* sampled_out,
                         int32_t* greedy_out) {
+    typedef typename Fwd<T>::type F;
     const int Tv = h->Tv, Tc = h->Tc, Hp = h->Hp, Gp = h->Gp, Vp = h->Vp;
     const bool want_greedy = greedy_out != nullptr;
     const int R = (K + (want_greedy ? 1 : 0)) * B;
@@ -657,16 +682,16 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
     plan_roll<T>(h, a, B, R, r);
     if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small: need %zu bytes", a.used);
     TRY(run_encoder<T>(h, st, video, B, r));
-    tile_rows_kernel<T><<<R, 256, 0, st>>>(r.h2_final, B, R, Hp, r.h2r[0]); KCHECK(h);
+    tile_rows_kernel<F><<<R, 256, 0, st>>>(r.h2_final, B, R, Hp, r.h2r[0]); KCHECK(h);
     tile_rows_kernel<float><<<R, 256, 0, st>>>(r.c2e[Tv & 1], B, R, Hp, r.c2r[0]); KCHECK(h);
     fill_int_kernel<<<(R + 255) / 256, 256, 0, st>>>(r.tok[0], R, 1); KCHECK(h);   // <bos> = 1 (:321-323)
     const int logits_bn = logits_tile_bn<T>(h);
     const int nt = Vp / logits_bn;
-    std::vector<typename EpiLstmFwd<T>::Params> cells(Tc);
+    std::vector<typename EpiLstmFwd<F>::Params> cells(Tc);
     std::vector<typename EpiLogitsPick<T>::Params> picks(Tc);
     for (int i = 0; i < Tc; ++i) {
         const int t = Tv + i;
-        typename EpiLstmFwd<T>::Params& ep = cells[i];
+        typename EpiLstmFwd<F>::Params& ep = cells[i];
         memset(&ep, 0, sizeof ep);
         ep.M = R; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp; ep.add0_mod = B;
         ep.add1 = h->Etab; ep.tok = r.tok[0];                     // step 0: <bos>; later steps resolve the previous step's candidates
@@ -694,11 +719,12 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
             CUDA_TRY(h, cudaMemcpyAsync(dev, cells.data(), Tc * sizeof(cells[0]), cudaMemcpyHostToDevice, st));
             CUDA_TRY(h, cudaMemcpyAsync(dev + pick_off, picks.data(), Tc * sizeof(picks[0]), cudaMemcpyHostToDevice, st));
             chain_begin(h, st);
-            auto launcher = (h->overlap & 32) ? tc::launch_sample_chain<EpiLstmFwd<bf16>, EpiLogitsPick<bf16>, false>      // bit 5: without the overlap
-                                              : tc::launch_sample_chain<EpiLstmFwd<bf16>, EpiLogitsPick<bf16>, true>;
+            auto launcher = (h->overlap & 32) ? tc::launch_sample_chain<EpiLstmFwd<F>, EpiLogitsPick<bf16>, false>      // bit 5: without the overlap
+                                              : tc::launch_sample_chain<EpiLstmFwd<F>, EpiLogitsPick<bf16>, true>;
             cudaError_t e = launcher(
                 mc, st, (const bf16*)r.h2r[0], (const bf16*)r.h2r[1], Hp, R, (const bf16*)h->W2hT, Hp, Gp, (const bf16*)h->WoT, Hp, Vp, Hp,
-                (const typename EpiLstmFwd<bf16>::Params*)dev, (const typename EpiLogitsPick<bf16>::Params*)(dev + pick_off), Tc, h->gbar + (st == h->side ? 16 : 0), true);
+                (const typename EpiLstmFwd<F>::Params*)dev, (const typename EpiLogitsPick<bf16>::Params*)(dev + pick_off), Tc, h->gbar + (st == h->side ? 16 : 0), true,
+                tc::FmtOf<F>::A | tc::FmtOf<F>::B);
             if (e == cudaSuccess) {
                 chained = true;
                 h->launches++;
@@ -706,7 +732,7 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
                     const double lm = logical_dim(h, R), lk = logical_dim(h, Hp);
                     for (int i = 0; i < Tc; ++i) {
                         h->chain.flops += 2.0 * lm * lk * (logical_dim(h, Gp) + logical_dim(h, Vp));
-                        h->chain.bytes += (2.0 * lm * lk + (logical_dim(h, Gp) + logical_dim(h, Vp)) * lk) * sizeof(T) + EpiBytes<EpiLstmFwd<T>>::get(h, cells[i], R);
+                        h->chain.bytes += (2.0 * lm * lk + (logical_dim(h, Gp) + logical_dim(h, Vp)) * lk) * sizeof(T) + EpiBytes<EpiLstmFwd<F>>::get(h, cells[i], R);
                     }
                     h->chain.count += Tc; h->chain.launches += 1; h->chain.M = R; h->chain.N = Gp + Vp; h->chain.K = Hp;
                 }
@@ -720,8 +746,8 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
     }
     if (!chained)
         for (int i = 0; i < Tc; ++i) {
-            TRY((gemm<T, CfgStep, EpiLstmFwd<T>>(h, st, r.h2r[i & 1], Hp, h->W2hT, Hp, R, Gp, Hp, cells[i])));
-            TRY((gemm<T, CfgBig, EpiLogitsPick<T>>(h, st, r.h2r[(i + 1) & 1], Hp, h->WoT, Hp, R, Vp, Hp, picks[i])));
+            TRY((gemm<F, CfgStep, EpiLstmFwd<F>>(h, st, r.h2r[i & 1], Hp, h->W2hT, Hp, R, Gp, Hp, cells[i])));
+            TRY((gemm<F, CfgBig, EpiLogitsPick<T>>(h, st, r.h2r[(i + 1) & 1], Hp, h->WoT, Hp, R, Vp, Hp, picks[i])));
         }
     resolve_picks_kernel<<<(R + 127) / 128, 128, 0, st>>>(r.pick_val, r.pick_idx, r.pick_ld, nt, R, r.ids, Tc, Tc - 1); KCHECK(h);
     if (K > 0 && sampled_out)
@@ -761,27 +787,29 @@ extern "C" int s2vt_caption_masks(s2vt_handle* h, const int32_t* ids, int N, flo
 // =================================================================================================================
 template <typename T>
 struct Train {
+    typedef typename Fwd<T>::type F;     // forward values F, gradients T
     Front<T> f;
-    T* out1d; float* G2x; T* h2_all; float* c2_all; T* gates2; T* out2d; float* logits;
+    F* out1d; float* G2x; F* h2_all; float* c2_all; F* gates2; F* out2d; float* logits;
     int *prev_tok, *target; float *ca, *cb, *cc, *logp, *sumlsm;
     // backward
     T* dlogits; float* dout2; T* dG2; float* dc2; float* dout1; float* dEmb; float* dh1; T* dG1; float* dc1; float* dimgF; T* dimgT_src;
     T *tA, *tB;   // transposed operand scratch (largest: [Vp, Mp])
     T *tA2, *tB2; // same for the LSTM1 chain on the side stream
     void *chain_f, *chain_b2, *chain_b1;   // per-step parameters of the persistent chains
-    T* emb;
+    F* emb;
 };
 
 template <typename T>
 static void plan_train(const s2vt_handle* h, Arena& a, int B, int N, bool backward, bool want_logits_only, Train<T>& p) {
+    typedef typename Fwd<T>::type F;
     const int T_ = h->T, Tv = h->Tv, Tc = h->Tc, Hp = h->Hp, Gp = h->Gp, Vp = h->Vp, Ep = h->Ep, Dp = h->Dp;
     plan_front<T>(h, a, B, backward, p.f);
-    p.out1d = a.take<T>((size_t)T_ * N * Hp);
+    p.out1d = a.take<F>((size_t)T_ * N * Hp);
     p.G2x = a.take<float>((size_t)T_ * N * Gp);
-    p.h2_all = a.take<T>((size_t)(T_ + 1) * N * Hp);
+    p.h2_all = a.take<F>((size_t)(T_ + 1) * N * Hp);
     p.c2_all = a.take<float>((size_t)(T_ + 1) * N * Hp);
-    p.gates2 = backward ? a.take<T>((size_t)T_ * N * Gp) : nullptr;
-    p.out2d = a.take<T>((size_t)Tc * N * Hp);
+    p.gates2 = backward ? a.take<F>((size_t)T_ * N * Gp) : nullptr;
+    p.out2d = a.take<F>((size_t)Tc * N * Hp);
     p.logits = a.take<float>((size_t)Tc * N * Vp);
     p.prev_tok = a.take<int>((size_t)Tc * N); p.target = a.take<int>((size_t)Tc * N);
     p.ca = a.take<float>((size_t)Tc * N); p.cb = a.take<float>((size_t)Tc * N); p.cc = a.take<float>((size_t)Tc * N);
@@ -800,7 +828,7 @@ static void plan_train(const s2vt_handle* h, Arena& a, int B, int N, bool backwa
     p.dc1 = a.take<float>((size_t)B * Hp);
     p.dimgF = a.take<float>((size_t)Tv * B * Ep);
     p.dimgT_src = a.take<T>((size_t)Tv * B * Ep);
-    p.emb = a.take<T>((size_t)Tc * N * Ep);
+    p.emb = a.take<F>((size_t)Tc * N * Ep);
     size_t ta = (size_t)Hp * Mp2;                       // activations^T : at most [max(Hp,Ep,Dp), Mp2]
     if ((size_t)Dp * Mp1 > ta) ta = (size_t)Dp * Mp1;
     if ((size_t)Ep * MpD > ta) ta = (size_t)Ep * MpD;
@@ -813,12 +841,12 @@ static void plan_train(const s2vt_handle* h, Arena& a, int B, int N, bool backwa
     p.tB2 = a.take<T>(tb2 + 256);
 }
 
-template <typename T>
-static int transpose(s2vt_handle* h, cudaStream_t st, const T* src, int lds, int R, int C, T* dst, int ldd, int rows_dst_padded) {
+template <typename TI, typename TO>
+static int transpose(s2vt_handle* h, cudaStream_t st, const TI* src, int lds, int R, int C, TO* dst, int ldd, int rows_dst_padded) {
     // zero the destination (pads along the contraction dimension must be zero), then transpose the valid part
-    CUDA_TRY(h, cudaMemsetAsync(dst, 0, (size_t)rows_dst_padded * ldd * sizeof(T), st));
+    CUDA_TRY(h, cudaMemsetAsync(dst, 0, (size_t)rows_dst_padded * ldd * sizeof(TO), st));
     dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
-    transpose_kernel<T><<<grid, block, 0, st>>>(src, lds, R, C, dst, ldd);
+    transpose_kernel<TI, TO><<<grid, block, 0, st>>>(src, lds, R, C, dst, ldd);
     KCHECK(h);
     return 0;
 }
@@ -828,6 +856,7 @@ template <typename T>
 static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* video, int B, const int32_t* captions, const float* mask, const float* rewards,
                       const float* base_line, int N, float norm, float grad_scale, int accumulate, float ls, float decay, uint64_t drop_seed,
                       uint32_t row_base, float* loss_out, float* logp_out, float* logits_out, const float* xe_colsum = nullptr, int xe_nglobal = 0) {
+    typedef typename Fwd<T>::type F;     // forward operands / activations (fp16 in the bf16 mode); gradients stay T
     const int Tv = h->Tv, Tc = h->Tc, T_ = h->T, Hp = h->Hp, Gp = h->Gp, Vp = h->Vp, Ep = h->Ep, Dp = h->Dp;
     const int H = h->H, E = h->E, V = h->V, D = h->D, G = 4 * h->H;
     const bool backward = mode != 2;
@@ -845,21 +874,21 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         TRY(run_front<T>(h, st, video, B, p.f));
     }
     TRY(wait_late_weights(h, st));
-    expand_dropout_kernel<T><<<T_ * N, 256, 0, st>>>(p.f.h1_all + (size_t)B * Hp, B, N, Hp, H, p.out1d, drop_seed, S2VT_STREAM_DROP1, row_base, keep);
+    expand_dropout_kernel<F><<<T_ * N, 256, 0, st>>>(p.f.h1_all + (size_t)B * Hp, B, N, Hp, H, p.out1d, drop_seed, S2VT_STREAM_DROP1, row_base, keep);
     KCHECK(h);
     {
-        typename EpiStore<T>::Params ep = {p.G2x, nullptr, Gp, nullptr, T_ * N, 0};
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.out1d, Hp, h->W2xT, Hp, T_ * N, Gp, Hp, ep)));
+        typename EpiStore<F>::Params ep = {p.G2x, nullptr, Gp, nullptr, T_ * N, 0};
+        TRY((gemm<F, CfgBig, EpiStore<F>>(h, st, p.out1d, Hp, h->W2xT, Hp, T_ * N, Gp, Hp, ep)));
     }
     caption_tables_kernel<<<(Tc * N + 255) / 256, 256, 0, st>>>(captions, N, Tc, p.prev_tok, p.target); KCHECK(h);
-    CUDA_TRY(h, cudaMemsetAsync(p.h2_all, 0, (size_t)N * Hp * sizeof(T), st));
+    CUDA_TRY(h, cudaMemsetAsync(p.h2_all, 0, (size_t)N * Hp * sizeof(F), st));
     CUDA_TRY(h, cudaMemsetAsync(p.c2_all, 0, (size_t)N * Hp * sizeof(float), st));
     {
-        StepChain<T, EpiLstmFwd<T>> ch;
+        StepChain<F, EpiLstmFwd<F>> ch;
         ch.A = p.h2_all; ch.lda = Hp; ch.a_total_rows = (T_ + 1) * N; ch.a_row0 = 0; ch.a_row_stride = N;
-        ch.B = (const T*)h->W2hT; ch.ldb = Hp; ch.M = N; ch.N = Gp; ch.K = Hp;
+        ch.B = (const F*)h->W2hT; ch.ldb = Hp; ch.M = N; ch.N = Gp; ch.K = Hp;
         for (int t = 0; t < T_; ++t) {
-            typename EpiLstmFwd<T>::Params ep;
+            typename EpiLstmFwd<F>::Params ep;
             memset(&ep, 0, sizeof ep);
             ep.M = N; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = p.G2x + (size_t)t * N * Gp;
             if (t >= Tv) { ep.add1 = h->Etab; ep.tok = p.prev_tok + (size_t)(t - Tv) * N; ep.hdrop_out = p.out2d + (size_t)(t - Tv) * N * Hp; }
@@ -869,11 +898,11 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
             ep.seed = drop_seed; ep.stream = S2VT_STREAM_DROP2; ep.step = (uint32_t)t; ep.row_base = row_base; ep.keep = keep;
             ch.eps.push_back(ep);
         }
-        TRY((run_chain<T, EpiLstmFwd<T>>(h, st, ch, p.chain_f)));
+        TRY((run_chain<F, EpiLstmFwd<F>>(h, st, ch, p.chain_f)));
     }
     {   // logits for all decode steps at once (:163 / :286)
-        typename EpiStore<T>::Params ep = {p.logits, nullptr, Vp, h->bo_p, Tc * N, 0};
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.out2d, Hp, h->WoT, Hp, Tc * N, Vp, Hp, ep)));
+        typename EpiStore<F>::Params ep = {p.logits, nullptr, Vp, h->bo_p, Tc * N, 0};
+        TRY((gemm<F, CfgBig, EpiStore<F>>(h, st, p.out2d, Hp, h->WoT, Hp, Tc * N, Vp, Hp, ep)));
     }
     if (logits_out)
         CUDA_TRY(h, cudaMemcpy2DAsync(logits_out, (size_t)V * sizeof(float), p.logits, (size_t)Vp * sizeof(float), (size_t)V * sizeof(float), (size_t)Tc * N,
@@ -916,7 +945,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
     {   // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums
         EpiGradStore::Params ep = {h->G_(h->iWo), V, H, V, 0, 1.f};
-        TRY(wgrad<T>(h, s2, p.out2d, Hp, Hp, p.dlogits, Vp, Vp, MD, ep, p.tA, p.tB, H));
+        TRY((wgrad<T, F>(h, s2, p.out2d, Hp, Hp, p.dlogits, Vp, Vp, MD, ep, p.tA, p.tB, H)));
         TRY(bias_grad<T>(h, s2, p.dlogits, Vp, Vp, MD, V, 0, h->G_(h->ibo)));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
@@ -927,7 +956,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     // LSTM2 BPTT
     CUDA_TRY(h, cudaMemsetAsync(p.dc2, 0, (size_t)N * Hp * sizeof(float), st));
     {
-        StepChain<T, EpiLstmBwd<T>> ch;       // step s of the chain is time t = T-2-s; its A operand is dG2 of time t+1
+        StepChain<T, EpiLstmBwd<T, F>> ch;    // step s of the chain is time t = T-2-s; its A operand is dG2 of time t+1
         ch.A = p.dG2; ch.lda = Gp; ch.a_total_rows = T_ * N; ch.a_row0 = (T_ - 1) * N; ch.a_row_stride = -N;
         ch.B = (const T*)h->W2h; ch.ldb = Gp; ch.M = N; ch.N = Hp; ch.K = Gp;
         for (int t = T_ - 1; t >= 0; --t) {
@@ -939,13 +968,13 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
             b.dc = p.dc2; b.seed = drop_seed; b.stream = S2VT_STREAM_DROP2; b.step = (uint32_t)t; b.row_base = row_base; b.keep = keep;
             T* dg = p.dG2 + (size_t)t * N * Gp;
             if (t == T_ - 1) {
-                lstm_bwd_elem_kernel<T><<<(N * Hp + 255) / 256, 256, 0, st>>>(b, dg); KCHECK(h);
+                lstm_bwd_elem_kernel<T, F><<<(N * Hp + 255) / 256, 256, 0, st>>>(b, dg); KCHECK(h);
             } else {
-                typename EpiLstmBwd<T>::Params ep = {b, dg};
+                typename EpiLstmBwd<T, F>::Params ep = {b, dg};
                 ch.eps.push_back(ep);
             }
         }
-        TRY((run_chain<T, EpiLstmBwd<T>>(h, st, ch, p.chain_b2)));
+        TRY((run_chain<T, EpiLstmBwd<T, F>>(h, st, ch, p.chain_b2)));
     }
     {   // gradient flowing into LSTM1's (dropped, shared-per-video) output
         typename EpiStore<T>::Params ep = {p.dout1, nullptr, Hp, nullptr, M2, 0};
@@ -960,7 +989,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     // LSTM1 BPTT over the B shared rows (side stream)
     CUDA_TRY(h, cudaMemsetAsync(p.dc1, 0, (size_t)B * Hp * sizeof(float), s3));
     {
-        StepChain<T, EpiLstmBwd<T>> ch;
+        StepChain<T, EpiLstmBwd<T, F>> ch;
         ch.A = p.dG1; ch.lda = Gp; ch.a_total_rows = T_ * B; ch.a_row0 = (T_ - 1) * B; ch.a_row_stride = -B;
         ch.B = (const T*)h->W1h; ch.ldb = Gp; ch.M = B; ch.N = Hp; ch.K = Gp;
         for (int t = T_ - 1; t >= 0; --t) {
@@ -971,29 +1000,29 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
             b.dc = p.dc1; b.keep = 1.f;
             T* dg = p.dG1 + (size_t)t * B * Gp;
             if (t == T_ - 1) {
-                lstm_bwd_elem_kernel<T><<<(B * Hp + 255) / 256, 256, 0, s3>>>(b, dg); KCHECK(h);
+                lstm_bwd_elem_kernel<T, F><<<(B * Hp + 255) / 256, 256, 0, s3>>>(b, dg); KCHECK(h);
             } else {
-                typename EpiLstmBwd<T>::Params ep = {b, dg};
+                typename EpiLstmBwd<T, F>::Params ep = {b, dg};
                 ch.eps.push_back(ep);
             }
         }
-        TRY((run_chain<T, EpiLstmBwd<T>>(h, s3, ch, p.chain_b1)));
+        TRY((run_chain<T, EpiLstmBwd<T, F>>(h, s3, ch, p.chain_b1)));
     }
     {   // LSTM1 kernel / bias gradients (side stream, own transpose scratch)
         float* gW1 = h->G_(h->iW1);
         TRY(bias_grad<T>(h, s3, p.dG1, Gp, Gp, M1, 0, H, h->G_(h->ib1)));
         EpiGradStore::Params e2 = {gW1 + (size_t)E * G, G, H, G, H, 1.f};
-        TRY(wgrad<T>(h, s3, p.f.h1_all, Hp, Hp, p.dG1, Gp, Gp, M1, e2, p.tA2, p.tB2, H));     // h1 before step t = h1_all[t]
+        TRY((wgrad<T, F>(h, s3, p.f.h1_all, Hp, Hp, p.dG1, Gp, Gp, M1, e2, p.tA2, p.tB2, H)));     // h1 before step t = h1_all[t]
         // frame-embedding rows: encoder steps only
         EpiGradStore::Params e1 = {gW1, G, E, G, H, 1.f};
-        TRY(wgrad<T>(h, s3, p.f.img, Ep, Ep, p.dG1, Gp, Gp, ME, e1, p.tA2, p.tB2, E));
+        TRY((wgrad<T, F>(h, s3, p.f.img, Ep, Ep, p.dG1, Gp, Gp, ME, e1, p.tA2, p.tB2, E)));
     }
     {   // frame projection gradients: dimg = dG1[enc] . W1[x rows]^T ; dWe = X^T . dimg ; dbe = column sums (side stream)
         typename EpiStore<T>::Params ep = {p.dimgF, p.dimgT_src, Ep, nullptr, ME, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, s3, p.dG1, Gp, h->W1x, Gp, ME, Ep, Gp, ep)));
         TRY(bias_grad<T>(h, s3, p.dimgT_src, Ep, Ep, ME, E, 0, h->G_(h->ibe)));
         EpiGradStore::Params e = {h->G_(h->iWe), E, D, E, 0, 1.f};
-        TRY(wgrad<T>(h, s3, p.f.Xc, Dp, Dp, p.dimgT_src, Ep, Ep, ME, e, p.tA2, p.tB2, D));
+        TRY((wgrad<T, F>(h, s3, p.f.Xc, Dp, Dp, p.dimgT_src, Ep, Ep, ME, e, p.tA2, p.tB2, D)));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_join, s3));
     // ---- main stream meanwhile: embedding and LSTM2 weight gradients
@@ -1006,13 +1035,13 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         float* gW2 = h->G_(h->iW2);
         TRY(bias_grad<T>(h, st, p.dG2, Gp, Gp, M2, 0, H, h->G_(h->ib2)));
         EpiGradStore::Params e1 = {gW2, G, H, G, H, 1.f};
-        TRY(wgrad<T>(h, st, p.out1d, Hp, Hp, p.dG2, Gp, Gp, M2, e1, p.tA, p.tB, H));
+        TRY((wgrad<T, F>(h, st, p.out1d, Hp, Hp, p.dG2, Gp, Gp, M2, e1, p.tA, p.tB, H)));
         EpiGradStore::Params e3 = {gW2 + (size_t)(H + E) * G, G, H, G, H, 1.f};
-        TRY(wgrad<T>(h, st, p.h2_all, Hp, Hp, p.dG2, Gp, Gp, M2, e3, p.tA, p.tB, H));          // h2 before step t = h2_all[t]
+        TRY((wgrad<T, F>(h, st, p.h2_all, Hp, Hp, p.dG2, Gp, Gp, M2, e3, p.tA, p.tB, H)));          // h2 before step t = h2_all[t]
         // embedding rows: decode steps only
-        gather_rows_kernel<T><<<MD, 128, 0, st>>>((const T*)h->WembC, Ep, p.prev_tok, MD, p.emb); KCHECK(h);
+        gather_rows_kernel<F><<<MD, 128, 0, st>>>((const F*)h->WembC, Ep, p.prev_tok, MD, p.emb); KCHECK(h);
         EpiGradStore::Params e2 = {gW2 + (size_t)H * G, G, E, G, H, 1.f};
-        TRY(wgrad<T>(h, st, p.emb, Ep, Ep, p.dG2 + (size_t)Tv * N * Gp, Gp, Gp, MD, e2, p.tA, p.tB, E));
+        TRY((wgrad<T, F>(h, st, p.emb, Ep, Ep, p.dG2 + (size_t)Tv * N * Gp, Gp, Gp, MD, e2, p.tA, p.tB, E)));
     }
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));   // join
     if (mode == 1 && decay > 0.f) {   // Q4: L2 on every variable without 'bias' in its name (the LSTM '/biases' only)
@@ -1078,26 +1107,27 @@ extern "C" int s2vt_xe_backward_sharded(s2vt_handle* h, const float* video, int 
 // ---- attribute head (config 4) --------------------------------------------------------------------------------------
 template <typename T>
 static int attribute_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B, const float* labels, float grad_scale, float* loss_out) {
+    typedef typename Fwd<T>::type F;
     const int A = h->A, Ap = h->Ap, D = h->D, Dp = h->Dp, Bp = ru(B, S2VT_PAD);
     h->front_valid = false;
     TRY(wait_late_weights(h, st));
     Arena a(h->ws, h->ws_bytes);
-    T* pooled = a.take<T>((size_t)B * Dp);
+    F* pooled = a.take<F>((size_t)B * Dp);
     float* z = a.take<float>((size_t)B * Ap);
     T* dz = a.take<T>((size_t)B * Ap);
     T* pooledT = a.take<T>((size_t)Dp * Bp);
     T* dzT = a.take<T>((size_t)Ap * Bp);
     float* battr = a.take<float>(Ap);
     if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small: need %zu bytes", a.used);
-    mean_frames_kernel<T><<<B, 256, 0, st>>>(video, h->Tv, D, Dp, pooled); KCHECK(h);
+    mean_frames_kernel<F><<<B, 256, 0, st>>>(video, h->Tv, D, Dp, pooled); KCHECK(h);
     CUDA_TRY(h, cudaMemsetAsync(battr, 0, Ap * sizeof(float), st));
     CUDA_TRY(h, cudaMemcpyAsync(battr, h->P_(h->iAb), A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    typename EpiStore<T>::Params ep = {z, nullptr, Ap, battr, B, 0};
-    TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, pooled, Dp, h->attrWT, Dp, B, Ap, Dp, ep)));
+    typename EpiStore<F>::Params ep = {z, nullptr, Ap, battr, B, 0};
+    TRY((gemm<F, CfgBig, EpiStore<F>>(h, st, pooled, Dp, h->attrWT, Dp, B, Ap, Dp, ep)));
     sigmoid_ce_kernel<T><<<1, 256, 0, st>>>(z, Ap, labels, B, A, Ap, grad_scale, dz, h->scal + 8); KCHECK(h);
     if (loss_out) CUDA_TRY(h, cudaMemcpyAsync(loss_out, h->scal + 8, sizeof(float), cudaMemcpyDeviceToDevice, st));
     EpiGradStore::Params eg = {h->G_(h->iAW), A, D, A, 0, 1.f};
-    TRY(wgrad<T>(h, st, pooled, Dp, Dp, dz, Ap, Ap, B, eg, pooledT, dzT, D));
+    TRY((wgrad<T, F>(h, st, pooled, Dp, Dp, dz, Ap, Ap, B, eg, pooledT, dzT, D)));
     TRY(bias_grad<T>(h, st, dz, Ap, Ap, B, A, 0, h->G_(h->iAb)));
     return 0;
 }

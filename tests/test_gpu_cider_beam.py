@@ -170,7 +170,8 @@ def test_beam_search_bf16_runs_and_mostly_agrees():
     gold = json.loads(bytes(g['beam_k5_lnf0']).decode())
     same = sum(sent[v, :lens[v]].tolist() == gold[v]['sentence'] for v in range(2))
     print('\n[beam bf16] %d / 2 sentences identical to the fp64 oracle; logprob diff %s' % (same, [float(lp[v] - gold[v]['logprob']) for v in range(2)]))
-    assert all(abs(lp[v] - gold[v]['logprob']) < 0.2 for v in range(2))
+    # identical sentences -> the log-probability is a sum of <= 35 log-softmax values, each within the bf16-mode tolerance
+    assert all(abs(lp[v] - gold[v]['logprob']) < (2e-2 if sent[v, :lens[v]].tolist() == gold[v]['sentence'] else 0.2) for v in range(2))
 
 
 @pytest.mark.parametrize('precision,Tv,B', [('fp32', 5, 8), ('bf16', 5, 8), ('bf16', 5, 1), ('bf16', 5, 3), ('bf16', 80, 64)])

@@ -73,18 +73,18 @@ def test_teacher_forced_logits_and_logprobs(precision, tol, dims, Tv):
     e1 = rel_err(logits.cpu().numpy(), ref_logits)
     e2 = rel_err(logp.cpu().numpy(), ref_logp)
     print('\n[teacher_forced %s H=%d] logits rel err %.3e, logp rel err %.3e (tol %.0e)' % (precision, dims['H'], e1, e2, tol))
-    # log-probs meet the north-star tolerance in both modes.  Raw bf16 logits cannot: rounding both operands of a
-    # K~1000 random-sign dot product to 8 mantissa bits gives ~1.6e-3 relative rms error per GEMM layer (measured
-    # 1.9e-3 .. 3.8e-3 through the 3-layer path), so the bf16 logit bound is 5e-3; DESIGN.md "Numerics" has the analysis.
+    # north-star tolerance, verbatim: 1e-5 (fp32 mode) / 1e-3 (bf16 mode) on logits AND log-probs.  The bf16 mode multiplies its
+    # forward GEMMs on fp16 operands (10 mantissa bits, same tensor rate; bf16 operands gave 3.8e-3 .. 4.4e-3 on the logits).
     assert e2 < tol
-    assert e1 < (tol if precision == 'fp32' else 5e-3)
+    assert e1 < tol
 
 
-def test_bf16_kernels_match_bf16_rounded_oracle():
-    """Isolates kernel correctness from bf16 quantisation: oracle run on bf16-rounded weights."""
+def test_bf16_mode_kernels_match_fp16_rounded_oracle():
+    """Isolates kernel correctness from operand quantisation: oracle run on weights / features rounded to fp16, the forward operand type of
+    the bf16 mode (activations are rounded too inside the kernels, hence the remaining 1e-3)."""
     dims, Tv, Tc, N = SMALL, 3, 7, 6
     p = rand_params(dims)
-    rnd = lambda a: torch.tensor(a).to(torch.bfloat16).to(torch.float32).numpy()
+    rnd = lambda a: torch.tensor(a).to(torch.float16).to(torch.float32).numpy()
     pq = {k: (rnd(v) if v.ndim == 2 else v) for k, v in p.items()}
     m = make(dims, Tv, Tc, 'bf16', params=p)
     video = M.synthetic_features(N, Tv, dims['D'])
@@ -92,8 +92,8 @@ def test_bf16_kernels_match_bf16_rounded_oracle():
     _, logits = m.teacher_forward(video, cap, want_logits=True)
     ref, _ = M.teacher_forward({k: v.astype(np.float64) for k, v in pq.items()}, rnd(video).astype(np.float64), cap, keep_cache=False)
     e = rel_err(logits.cpu().numpy(), ref)
-    print('\n[bf16 vs bf16-rounded-weight oracle] rel err %.3e' % e)
-    assert e < 1e-2
+    print('\n[bf16 mode vs fp16-rounded-weight oracle] rel err %.3e' % e)
+    assert e < 1e-3
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
@@ -112,7 +112,7 @@ def test_dropout_masks_match_philox_oracle(precision):
     ref, _ = M.teacher_forward(p, vid_rows, cap, d1, d2, keep_cache=False)
     e = rel_err(logits.cpu().numpy(), ref)
     print('\n[dropout %s] logits rel err %.3e' % (precision, e))
-    assert e < (1e-5 if precision == 'fp32' else 1e-2)
+    assert e < (1e-5 if precision == 'fp32' else 1e-3)
     logp0, _ = m.teacher_forward(video, cap, drop_seed=0)
     assert rel_err(logp0.cpu().numpy(), logp.cpu().numpy()) > 1e-3           # dropout really changes the result
 
@@ -133,7 +133,9 @@ def test_greedy_and_sampled_ids(precision):
     # oracle greedy (fp64 golden) + margins from the oracle's own logits
     ref_ids, ref_logits = M.greedy_sampler({k: v.astype(np.float64) for k, v in pB.items()}, video.astype(np.float64), Tc, return_logits=True)
     assert (ref_ids == g['greedy_ids']).all()
-    tol = 1e-4 * np.abs(ref_logits).max() if precision == 'fp32' else 2e-2 * np.abs(ref_logits).max()
+    # ids exact wherever the oracle's top-2 margin exceeds the logit tolerance (north star): 1e-5 / 1e-3 relative, x2 because a
+    # margin is a difference of two logits
+    tol = (2e-5 if precision == 'fp32' else 2e-3) * np.abs(ref_logits).max()
     # compare position by position until the first divergence of each row (after that the inputs differ)
     n_checked = n_match = 0
     for b in range(B):
@@ -192,7 +194,7 @@ def _grad_report(m, grads, tol, tag):
     return worst
 
 
-@pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('bf16', 5e-2)])
+@pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('bf16', 2e-2)])
 @pytest.mark.parametrize('keep', [1.0, 0.9])
 def test_rl_backward_gradients(precision, tol, keep):
     dims, Tv, Tc, B, K = SMALL, 3, 7, 4, 2
@@ -222,7 +224,7 @@ def test_rl_backward_gradients(precision, tol, keep):
     assert rel_err(m.grads[:m.n_params].cpu().numpy(), g_dedup.cpu().numpy()) < (1e-5 if precision == 'fp32' else 2e-2)
 
 
-@pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('bf16', 5e-2)])
+@pytest.mark.parametrize('precision,tol', [('fp32', 2e-4), ('bf16', 2e-2)])
 def test_xe_backward_gradients(precision, tol):
     dims, Tv, Tc, N = SMALL, 3, 7, 6
     p = rand_params(dims, dtype=np.float64)
