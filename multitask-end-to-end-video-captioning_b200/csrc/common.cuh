@@ -13,8 +13,8 @@ typedef __half f16;
 // but 10 mantissa bits instead of 7, which is what brings the teacher-forced logits within the 1e-3 the north star quotes
 // (bf16 operands: 4.4e-3 at H = 1000, tests/test_gpu_bench_config_parity.py).  Every forward quantity is bounded (|h| < 1,
 // post-ReLU features, weights of magnitude 0.1), far inside fp16's range.  Gradients keep bf16: REINFORCE gate gradients reach
-// 1e-9 and below, under fp16's normal range.  The weight-gradient GEMMs X^T . dY therefore multiply an fp16 operand by a bf16 one
-// (the instruction descriptor carries one format per operand).
+// 1e-9 and below, under fp16's normal range.  The weight-gradient GEMMs X^T . dY round their activation operand to bf16 first
+// (kind::f16 takes one format for both operands; the mixed descriptor faults on B200).
 template <typename T> struct Fwd { typedef T type; };
 template <> struct Fwd<bf16> { typedef f16 type; };
 

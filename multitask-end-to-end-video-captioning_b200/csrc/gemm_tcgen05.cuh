@@ -43,7 +43,8 @@ struct Cfg {
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6), a/b_format BF16 [7,10)/[10,13),
     // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).  Format 0 = F16, 1 = BF16: the kernels take a run-time
     // `fmt` word whose bits are CLEARED from IDESC -- FMT_A_F16 / FMT_B_F16 turn an operand into IEEE fp16 (same tensor maps: TMA
-    // moves 16-bit payloads), so fp16 x fp16, bf16 x bf16 and the mixed fp16 x bf16 weight-gradient products share one kernel.
+    // moves 16-bit payloads), so the fp16 x fp16 forward products and the bf16 x bf16 backward products share one kernel.  Both
+    // operands must have the SAME format: a mixed descriptor raises an illegal-instruction fault on B200 (measured).
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 

@@ -366,21 +366,19 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
 // Other mainloops need K-major operands: X and Y are transposed into the scratch buffers first.
 template <typename TI, typename TO> static int transpose(s2vt_handle* h, cudaStream_t st, const TI* src, int lds, int R, int C, TO* dst, int ldd, int rows_dst_padded);
 #define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
-// X: a forward activation (type F = Fwd<T>::type), Y: a gradient (type T).  In the bf16 mode that is an fp16 x bf16 product: one
-// tcgen05 kind::f16 instruction with a_format F16 and b_format BF16.
+// X: a forward activation (type F = Fwd<T>::type), Y: a gradient (type T).  tcgen05.mma kind::f16 wants ONE format for both operands
+// (an instruction descriptor with a_format F16 and b_format BF16 raises an illegal-instruction fault on B200 -- measured), so in
+// the bf16 mode the fp16 activations are rounded to bf16 on their way into the product (one streaming pass, ~0.4 GB per iteration).
 template <typename T, typename F>
 static int wgrad(s2vt_handle* h, cudaStream_t st, const F* X, int ldx, int Mf, const T* Y, int ldy, int Nf, int R, const EpiGradStore::Params& ep,
                  T* tA, T* tB, int logical_m) {
     if constexpr (sizeof(T) == 2) {
-        uint32_t fmt = tc::FmtOf<F>::A | tc::FmtOf<T>::B;
+        constexpr uint32_t fmt = tc::FmtOf<T>::A | tc::FmtOf<T>::B;
         if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC && h->cfg.gemm_backend != 8) {
-            // A/B switch (debug): S2VT_WGRAD_CONVERT=1 rounds the fp16 activations to bf16 first, so the product is bf16 x bf16
-            static const bool convert_x = getenv("S2VT_WGRAD_CONVERT") && atoi(getenv("S2VT_WGRAD_CONVERT")) != 0;
-            if (convert_x && !std::is_same<F, T>::value) {
+            if constexpr (!std::is_same<F, T>::value) {
                 const size_t n = (size_t)R * ldx;
                 convert_kernel<F, T><<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(X, n, tA); KCHECK(h);
                 X = reinterpret_cast<const F*>(tA);
-                fmt = tc::FmtOf<T>::A | tc::FmtOf<T>::B;
             }
             s2vt_handle::ProfRec rec;
             if (h->prof) {
