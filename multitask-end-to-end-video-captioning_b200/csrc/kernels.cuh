@@ -69,12 +69,20 @@ __global__ void transpose_kernel(const TI* __restrict__ src, int lds, int R, int
     }
 }
 
-// element-wise type conversion (4 elements per thread)
+// element-wise conversion between the two 16-bit types, 8 elements (one 128-bit access) per thread and iteration; n % 8 == 0 and both
+// pointers 16-byte aligned (padded activation matrices)
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ src, size_t n, TO* __restrict__ dst) {
-    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const size_t n8 = n / 8, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const uint4 u = reinterpret_cast<const uint4*>(src)[i];
+        const TI* x = reinterpret_cast<const TI*>(&u);
+        uint4 o;
+        TO* y = reinterpret_cast<TO*>(&o);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if (i + k < n) dst[i + k] = from_f32<TO>(to_f32(src[i + k]));
+        for (int k = 0; k < 8; ++k) y[k] = from_f32<TO>(to_f32(x[k]));
+        reinterpret_cast<uint4*>(dst)[i] = o;
+    }
 }
 
 // fp32 -> compute dtype copy with optional dropout (used for the dropout-applied LSTM1 output of the training graph):

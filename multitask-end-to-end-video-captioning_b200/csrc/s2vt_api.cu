@@ -14,6 +14,7 @@
 #include "gemm.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_chain.cuh"
+#include "gemm_tcgen05_ws2.cuh"
 #include "gemm_tcgen05_sample.cuh"
 #include "kernels.cuh"
 
@@ -377,7 +378,7 @@ static int wgrad(s2vt_handle* h, cudaStream_t st, const F* X, int ldx, int Mf, c
         if (h->cfg.gemm_backend != S2VT_GEMM_MMA_SYNC && h->cfg.gemm_backend != 8) {
             if constexpr (!std::is_same<F, T>::value) {
                 const size_t n = (size_t)R * ldx;
-                convert_kernel<F, T><<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(X, n, tA); KCHECK(h);
+                convert_kernel<F, T><<<148 * 8, 256, 0, st>>>(X, n, tA); KCHECK(h);      // ldx is a multiple of 128: n % 8 == 0
                 X = reinterpret_cast<const F*>(tA);
             }
             s2vt_handle::ProfRec rec;
@@ -445,7 +446,15 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
                     if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<32, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }
                 }
             } else {
-                if (c.M > 128) e = tc::launch_chain<128, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt);
+                if (c.M > 128) {
+                    // > 128 rows: weights-stationary slabs + two software-pipelined halves per row group (gemm_tcgen05_ws2.cuh);
+                    // the plain ring chain is the fallback (shape does not fit / gemm_backend 13)
+                    e = cudaErrorLaunchOutOfResources;
+                    if (h->cfg.gemm_backend != 13 && h->cfg.gemm_backend != 10)
+                        e = tc::launch_ws2_chain<Epi>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n,
+                                                      gbar + 32, true, fmt);
+                    if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<128, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }
+                }
                 else {
                     e = cudaErrorLaunchOutOfResources;   // weights-stationary variant first (rows <= 64, K <= 16 blocks)
                     // weights stationary + the activation rows multicast over clusters of 8 column tiles (gemm_backend 11 / 12: clusters of 4 / none)

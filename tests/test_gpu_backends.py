@@ -93,3 +93,19 @@ def test_sampling_chain_equals_per_step_launches(b, k, tv):
     for name in ('steps', 'chain2', 'plain_chain'):
         assert torch.equal(out['chain'][0], out[name][0]) and torch.equal(out['chain'][1], out[name][1]), name
     assert len(np.unique(out['chain'][0].numpy())) > 50      # not a degenerate rollout
+
+
+@pytest.mark.parametrize('b,k,tv', [(64, 5, 5), (64, 3, 5), (40, 4, 3), (64, 6, 2)])
+def test_pipelined_weights_stationary_chain_equals_plain_chain(b, k, tv):
+    """> 128 caption rows, H=1000: the teacher-forced LSTM2 chain on the pipelined weights-stationary kernel (gemm_tcgen05_ws2.cuh: 43 x 3
+    CTAs, resident weight slabs, two M=64 halves per row group, per-half flags) against the plain ring chain (gemm_backend
+    chain_plain).  One accumulator, K ascending in both -> bit-identical logits; row counts 320 / 192 / 160 / 384 exercise full,
+    short and ragged row groups."""
+    dims = dict(D=1536, E=500, H=1000, V=9972)
+    a = _run('auto', dims, tv, 35, b, k)
+    p = _run('chain_plain', dims, tv, 35, b, k)
+    assert torch.equal(a['greedy'], p['greedy']) and torch.equal(a['samp'], p['samp'])
+    assert torch.equal(a['logits'], p['logits'])
+    rel = float((a['grads'] - p['grads']).abs().max() / p['grads'].abs().max())
+    assert rel < 1e-5, rel
+    assert abs(a['loss'] - p['loss']) < 1e-6 * max(1.0, abs(p['loss']))
