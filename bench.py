@@ -556,6 +556,35 @@ def run_b200(args):
             print(json.dumps({'metric': METRIC, 'value': value, 'unit': 'videos/s', 'ms_per_step': ms / args.steps, 'gpu_launches': int(launches),
                               'quick': True}), file=out_stream, flush=True)
         return
+    # ---- data-parallel extras (N > 1): strong scaling on BASELINE config 2's global batch, and the gradient all-reduce alone
+    strong, collective = None, None
+    if world > 1:
+        nbytes = int(model.grads.numel() * 4)
+        s2vt_b200.trainer.allreduce_gradients(model, overlap=False)
+        ar_ms = timed(10, lambda: s2vt_b200.trainer.allreduce_gradients(model, overlap=False)) / 10
+        collective = {'op': 'NCCL all-reduce(sum) of the flat fp32 gradient block, one call, nothing overlapped', 'bytes': nbytes, 'ms': ar_ms,
+                      'algbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9, 'busbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
+                      'nvlink5_per_direction_GBps': 900.0,
+                      'in_step': 'embed_word_W/b, Wemb and the LSTM2 gradients (~80 % of the bytes) are reduced under the backward kernels '
+                                 '(s2vt_grad_segment_ready); the rest follows the backward call'}
+        if args.videos % world == 0:
+            Bs = args.videos // world
+            m2 = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=Bs,
+                                                   n_video_lstm_step=Tv, n_caption_lstm_step=35, bias_init_vector=bias, dropout_rate=0.9,
+                                                   precision=args.precision, max_videos=Bs, max_rows=K * Bs, seed=4, gemm_backend=args.gemm_backend)
+            m2.variable('embed_word_W').mul_(3.0)
+            m2.refresh()
+            t2 = s2vt_b200.trainer.ReinforceTrainer(m2, scorer, n_samples=K, start_learning_rate=1e-6, decay_steps=1000, clip_norm=5.0, seed=2024)
+            f2, v2 = feats_dev[:Bs].contiguous(), vidx_dev[:Bs].contiguous()
+            for _ in range(3):
+                t2.step(f2, v2)
+            ms_s = timed(args.steps, lambda: t2.step(f2, v2))
+            strong = {'scaling': 'strong', 'global_videos': args.videos, 'videos_per_gpu': Bs, 'rows_per_gpu': K * Bs, 'ms_per_step': ms_s / args.steps,
+                      'value': args.videos * args.steps / (ms_s / 1e3), 'unit': 'videos/s',
+                      'note': 'BASELINE config 2 literally: global batch %d split over %d GPUs; the per-GPU work shrinks to %d rows, the %d sequential '
+                              'recurrent steps and the all-reduce do not' % (args.videos, world, K * Bs, 3 * (Tv + 35) + 2 * 35)}
+            del t2, m2
+            torch.cuda.empty_cache()
     run_e2e(2)
     ms_e2e = timed(1, lambda: run_e2e(args.steps))
     e2e = world * B * args.steps / (ms_e2e / 1e3)
@@ -599,6 +628,42 @@ def run_b200(args):
             sc.score_ids(ids, rows)
             rw[name + '_us_per_%d_hyps' % ids.shape[0]] = 1e3 * timed(20, lambda: sc.score_ids(ids, rows)) / 20
         beam['reward_kernels'] = rw
+        # BASELINE config 3 (frame count of the attention file, 32): S2VT greedy and beam-5 decode on [B, 32, 1536]
+        m32 = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=B,
+                                                n_video_lstm_step=32, n_caption_lstm_step=35, bias_init_vector=bias, dropout_rate=1.0, beam_size=5,
+                                                precision=args.precision, max_videos=B, max_rows=B, seed=4)
+        m32.variable('embed_word_W').mul_(3.0); m32.refresh()
+        for _ in range(2):
+            m32.beam_search(feats32, 5, 1.0); m32.greedy(feats32)
+        b32 = timed(3, lambda: m32.beam_search(feats32, 5, 1.0)); g32 = timed(3, lambda: m32.greedy(feats32))
+        beam['config3_s2vt_32_frames'] = {'beam5_captions_per_s': 3 * B / (b32 / 1e3), 'greedy_captions_per_s': 3 * B / (g32 / 1e3), 'batch': B, 'T_v': 32}
+        del m32
+        # BASELINE config 4: multitask REINFORCE step with the 400-way attribute head (reinforce_multitask_e2e_attribute_loss.py:957), batch 128,
+        # single sample, T_v = 5: rollout(1) + CIDEr-D + -(1-alpha) RL backward + alpha attribute-head backward + clip 10 + Adam
+        B4, alpha = 128, 0.05
+        m4 = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=B4,
+                                               n_video_lstm_step=5, n_caption_lstm_step=35, bias_init_vector=bias, dropout_rate=0.9, n_attributes=400,
+                                               precision=args.precision, max_videos=B4, max_rows=B4, seed=4)
+        m4.variable('embed_word_W').mul_(3.0); m4.refresh()
+        f4 = torch.from_numpy(features(B4, 5, 777)).cuda()
+        v4 = torch.from_numpy((np.arange(B4) % len(order)).astype(np.int32)).cuda()
+        y4 = (torch.rand(B4, 400, device='cuda') < 0.05).float()
+        it4 = [0]
+
+        def step4():
+            it4[0] += 1
+            samp, greedy = m4.rollout(f4, 1, seed=100 + it4[0])
+            mask, _ = m4.caption_masks(samp)
+            sc = scorer.score_ids(torch.cat([samp, greedy]), v4.repeat(2)).to(torch.float32)
+            m4.rl_backward(f4, samp, mask, sc[:B4], sc[B4:], grad_scale=1.0 - alpha, drop_seed=it4[0])
+            m4.attribute_backward(f4, y4, grad_scale=alpha)
+            m4.optimizer_step(1e-6, 10.0)
+
+        for _ in range(3):
+            step4()
+        c4 = timed(5, step4)
+        beam['config4_multitask_attribute'] = {'videos_per_s': 5 * B4 / (c4 / 1e3), 'ms_per_step': c4 / 5, 'batch': B4, 'K': 1, 'T_v': 5, 'n_attributes': 400, 'alpha': alpha}
+        del m4, f4
         del feats32
         torch.cuda.empty_cache()
         # BASELINE config 1: tf_s2vt.py cross-entropy train step (teacher-forced forward with dropout, label-smoothed CE + L2, BPTT,
@@ -632,11 +697,26 @@ def run_b200(args):
     _, dM, dN, dK, dms, dcnt, dby, dln = dom
     dname = 'EpiLstmBwd' if dK > dN else 'EpiLstmFwd'
     d_ach = dby / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
-    roof = {'kernel': 'tc::gemm_tc_chain_kernel<BN, %s<bf16>> rows=%d N=%d K=%d (persistent chain: per time step h.W_h on tcgen05 + fused '
-                      'BasicLSTMCell %s, grid barrier between steps)' % (dname, dM, dN, dK, 'backward' if dK > dN else 'forward'),
+    def chain_kernel_name(M_, N_, K_):
+        if K_ > N_:
+            return 'tc::gemm_tc_chain_kernel<%d, EpiLstmBwd<bf16, f16>, 4> (persistent BPTT chain, split-K cluster of 4)' % (128 if M_ > 128 else 32)
+        if M_ > 128:
+            return 'tc::gemm_tc_ws2_chain_kernel<EpiLstmFwd<f16>> (weights-stationary slabs, two pipelined M=64 halves per row group)'
+        return 'tc::gemm_tc_chain_kernel<32, EpiLstmFwd<f16>, 1, weights-stationary> (persistent forward chain)'
+
+    chains = []
+    for c_, M_, N_, K_, ms_, n_, b_, l_ in sorted(shapes, key=lambda x: -x[4]):
+        if c_ == 1 and l_ and n_ > l_:       # persistent chains only (one launch walks many steps)
+            ach = b_ / (ms_ * 1e-3) / 1e9
+            chains.append({'kernel': chain_kernel_name(M_, N_, K_), 'rows': M_, 'N': N_, 'K': K_, 'direction': 'backward' if K_ > N_ else 'forward',
+                           'launches_per_step': l_ / args.steps, 'recurrent_steps_per_launch': n_ / l_, 'us_per_recurrent_step': 1e3 * ms_ / n_,
+                           'ms_per_step': ms_ / args.steps, 'achieved': ach, 'unit': 'GB/s', 'frac': ach / hbm if hbm else None,
+                           'traffic': STEP_KERNEL_DRAM_BYTES_PER_LAUNCH.get((M_, N_, K_))})
+    roof = {'kernel': '%s rows=%d N=%d K=%d: per time step h.W_h on tcgen05 + fused BasicLSTMCell %s'
+                      % (chain_kernel_name(dM, dN, dK), dM, dN, dK, 'backward' if dK > dN else 'forward'),
             'bound': 'hbm', 'achieved': d_ach, 'peak': hbm, 'unit': 'GB/s', 'frac': d_ach / hbm if hbm else None,
             'traffic': STEP_KERNEL_DRAM_BYTES_PER_LAUNCH.get((dM, dN, dK)),
-            'traffic_source': 'ncu --set full dram__bytes_read+write per launch, cold caches (profiles/r1_chain_ncu_full_f.md)',
+            'traffic_source': 'ncu --set full dram__bytes_read+write per launch, cold caches (profiles/)',
             'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)',
             'launches_per_step': dln / args.steps, 'recurrent_steps_per_launch': dcnt / dln if dln else None,
             'us_per_launch': 1e3 * dms / dln if dln else None, 'ms_per_step': dms / args.steps,
@@ -656,7 +736,7 @@ def run_b200(args):
            'gemm_shapes': [{'class': 'batched' if c == 0 else 'step', 'M': M_, 'N': N_, 'K': K_, 'gemms_per_step': n_ / args.steps,
                             'launches_per_step': l_ / args.steps, 'us_per_gemm': 1e3 * ms_ / n_, 'ms_per_step': ms_ / args.steps}
                            for c, M_, N_, K_, ms_, n_, b_, l_ in sorted(shapes, key=lambda x: -x[4])],
-           'roofline': roof,
+           'roofline': roof, 'roofline_chains': chains, 'strong_scaling': strong, 'collective': collective,
            'roofline_recurrent_family': {'kernels': 'all recurrent-step kernels (persistent chains + the per-step launches of the sampling loops)',
                                          'bound': 'hbm', 'achieved': ach_gb, 'peak': hbm, 'unit': 'GB/s', 'frac': ach_gb / hbm if hbm else None,
                                          'recurrent_steps_per_iteration': sn / args.steps, 'ms_per_step': sms / args.steps,

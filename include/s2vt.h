@@ -168,11 +168,13 @@ int s2vt_profile_read(s2vt_handle* h, double* ms_out, double* flops_out, long lo
  * chain runs many steps per launch), bytes = algorithmic bytes; bytes / launches may be NULL */
 int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* K, double* ms, long long* count, double* bytes,
                         long long* launches);
-/* Data-parallel overlap hook.  After s2vt_rl_backward (plain REINFORCE objective: grad_scale 1, no accumulation) the gradients of
- * embed_word_W and embed_word_b -- one contiguous range of the flat block, a third of its bytes -- are final long before the call's
- * last kernel: they only need d logits, and the BPTT chains follow.  This makes `stream` wait for exactly that point and returns the
- * range (in floats), so the host can launch its all-reduce under the chains and reduce the rest afterwards.  S2VT_ESTATE if the
- * last backward call gives no such guarantee (XE / mixed objectives add weight decay or a second pass). */
+/* Data-parallel overlap hook.  After s2vt_rl_backward (plain REINFORCE objective: grad_scale 1, no accumulation) three contiguous
+ * ranges of the flat gradient block are final long before the call's last kernel:
+ *   segment 0: embed_word_W, embed_word_b (a third of the bytes) -- they only need d logits, the BPTT chains follow;
+ *   segment 1: Wemb;   segment 2: the LSTM2 weights and biases -- final while the LSTM1 BPTT chain still runs on the side stream.
+ * The call makes `stream` wait for exactly that point and returns the range (in floats), so the host can launch its all-reduce under
+ * the remaining kernels and reduce the rest afterwards.  S2VT_ESTATE if the last backward call gives no such guarantee (XE / mixed
+ * objectives add weight decay or a second pass) or the segment was already handed out. */
 int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int64_t* offset, int64_t* count);
 /* tuning: which independent pieces use the library's internal side stream (bit 0: late half of s2vt_refresh, bit 1: the
  * vocabulary weight gradient, bit 2: the LSTM1 backward chain); default 7.  Bit 3 (debug) makes s2vt_beam_search use its un-fused

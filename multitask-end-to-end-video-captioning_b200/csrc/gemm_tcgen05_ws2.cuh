@@ -114,10 +114,10 @@ __global__ void __launch_bounds__(WS2_THREADS) gemm_tc_ws2_chain_kernel(const __
                                 __trap();
                             }
                         }
-                        WS2_PROBE(if (probe && hf == 0) probe[8 * s + 1] = gtimer());
                     }
                     __syncwarp();
                 }
+                WS2_PROBE(if (probe && lane == 0) probe[8 * s + 4 * hf + 0] = gtimer());      // dependency satisfied, loads start
                 if (leader) asm volatile("fence.proxy.async;" ::: "memory");   // rows written through the generic proxy by other SMs are read by TMA
                 const int arow = a_row0 + s * a_row_stride + row_lo[hf];
                 for (int i = 0; i < KBL; ++i, ++g) {
@@ -146,7 +146,6 @@ __global__ void __launch_bounds__(WS2_THREADS) gemm_tc_ws2_chain_kernel(const __
                     const int st = g % WS2_STAGES;
                     mbar_wait(full + st, (g / WS2_STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    WS2_PROBE(if (probe && hf == 0 && i == 0 && leader) probe[8 * s + 2] = gtimer());
                     const uint64_t adesc = make_desc(smem_u32(ring + st * WS2_A_STAGE)), bdesc = make_desc(smem_u32(wsm + i * WS2_W_TILE));
                     if (leader) {
 #pragma unroll
@@ -156,7 +155,7 @@ __global__ void __launch_bounds__(WS2_THREADS) gemm_tc_ws2_chain_kernel(const __
                 }
                 if (leader) {
                     mma_commit(acc_full + hf);
-                    WS2_PROBE(if (probe && hf == 0) probe[8 * s + 3] = gtimer());
+                    WS2_PROBE(if (probe) probe[8 * s + 4 * hf + 1] = gtimer());                  // all MMAs of the half issued
                 }
             }
         }
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(WS2_THREADS) gemm_tc_ws2_chain_kernel(const __
                 typename Epi::Pre pre;
                 Epi::prefetch(ep, gr, gc, pre);
                 mbar_wait(acc_full + hf, s & 1);
-                WS2_PROBE(if (probe && hf == 0 && threadIdx.x == 64) probe[8 * s + 4] = gtimer());
+                WS2_PROBE(if (probe && threadIdx.x == 64) probe[8 * s + 4 * hf + 2] = gtimer());        // accumulator ready, epilogue starts
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * 128 + 32 * chunk), v);
@@ -188,8 +187,7 @@ __global__ void __launch_bounds__(WS2_THREADS) gemm_tc_ws2_chain_kernel(const __
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * WS2_EPI_WARPS) : "memory");
                 if (threadIdx.x == 64) {
                     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(flags + (rg * 2 + hf)), "r"(1u) : "memory");
-                    WS2_PROBE(if (probe && hf == 0) { probe[8 * s + 5] = gtimer(); probe[8 * s + 6] = ((unsigned long long)(WS2_BN + 200000) << 32) | (unsigned)K; });
-                    WS2_PROBE(if (probe && hf == 1) probe[8 * s + 0] = gtimer());
+                    WS2_PROBE(if (probe) probe[8 * s + 4 * hf + 3] = gtimer());                      // half published
                 }
             }
         }

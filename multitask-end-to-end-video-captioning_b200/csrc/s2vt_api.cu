@@ -176,7 +176,7 @@ extern "C" int s2vt_set_reuse_frontend(s2vt_handle* h, int enable) {
     return 0;
 }
 extern "C" void s2vt_destroy(s2vt_handle* h) {
-    if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_refresh); cudaEventDestroy(h->ev_wo); }
+    if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_refresh); cudaEventDestroy(h->ev_wo); cudaEventDestroy(h->ev_seg[0]); cudaEventDestroy(h->ev_seg[1]); }
     if (h && h->tc_cache) delete static_cast<tc::MapCache*>(h->tc_cache);
     delete h;
 }
@@ -497,6 +497,8 @@ static int ensure_side(s2vt_handle* h) {
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_refresh, cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_wo, cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_seg[0], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_seg[1], cudaEventDisableTiming));
     return 0;
 }
 // The "late" half of a refresh (everything but the frame projection / LSTM1 forward weights) runs on the side stream;
@@ -960,6 +962,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     // pass), so a caller may start their all-reduce now, under the BPTT chains (s2vt_grad_segment_ready).
     h->wo_grad_early = mode == 0 && !accumulate && grad_scale == 1.f;
     if (h->wo_grad_early) CUDA_TRY(h, cudaEventRecord(h->ev_wo, s2));
+    h->seg_ready = h->wo_grad_early ? 1u : 0u;
     // LSTM2 BPTT
     CUDA_TRY(h, cudaMemsetAsync(p.dc2, 0, (size_t)N * Hp * sizeof(float), st));
     {
@@ -1037,6 +1040,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         typename EpiStore<T>::Params ee = {p.dEmb, nullptr, Ep, nullptr, MD, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2 + (size_t)Tv * N * Gp, Gp, h->W2e, Gp, MD, Ep, Gp, ee)));
         scatter_emb_grad_kernel<<<MD, 128, 0, st>>>(p.dEmb, Ep, p.prev_tok, MD, E, h->G_(h->iWemb), h->grads + h->P); KCHECK(h);   // aux[0] = slice square norm (R6)
+        if (h->wo_grad_early) { CUDA_TRY(h, cudaEventRecord(h->ev_seg[0], st)); h->seg_ready |= 2u; }      // d Wemb is final (the aux slot travels with the remainder)
     }
     {   // LSTM2 kernel / bias gradients: [out1 ; emb ; h2]^T . dG2
         float* gW2 = h->G_(h->iW2);
@@ -1049,6 +1053,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         gather_rows_kernel<F><<<MD, 128, 0, st>>>((const F*)h->WembC, Ep, p.prev_tok, MD, p.emb); KCHECK(h);
         EpiGradStore::Params e2 = {gW2 + (size_t)H * G, G, E, G, H, 1.f};
         TRY((wgrad<T, F>(h, st, p.emb, Ep, Ep, p.dG2 + (size_t)Tv * N * Gp, Gp, Gp, MD, e2, p.tA, p.tB, E)));
+        if (h->wo_grad_early) { CUDA_TRY(h, cudaEventRecord(h->ev_seg[1], st)); h->seg_ready |= 4u; }      // d LSTM2 weights / biases are final
     }
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));   // join
     if (mode == 1 && decay > 0.f) {   // Q4: L2 on every variable without 'bias' in its name (the LSTM '/biases' only)
@@ -1150,12 +1155,15 @@ extern "C" int s2vt_attribute_backward(s2vt_handle* h, const float* video, int B
 // ---- optimiser ----------------------------------------------------------------------------------------------------
 extern "C" int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int64_t* offset, int64_t* count) {
     if (!h || !h->bound) return S2VT_ESTATE;
-    if (segment != 0 || !offset || !count) return h->fail(S2VT_EINVAL, "segment 0 (embed_word_W, embed_word_b) is the only early segment");
-    if (!h->wo_grad_early || !h->ev_wo) return h->fail(S2VT_ESTATE, "the last backward call did not finish this segment early");
-    CUDA_TRY(h, cudaStreamWaitEvent((cudaStream_t)stream, h->ev_wo, 0));
-    *offset = (int64_t)h->vars[h->iWo].off;
-    *count = (int64_t)(h->vars[h->iWo].count() + h->vars[h->ibo].count());
-    h->wo_grad_early = false;      // one hand-out per backward call
+    if (segment < 0 || segment > 2 || !offset || !count) return h->fail(S2VT_EINVAL, "segments: 0 (embed_word_W, embed_word_b), 1 (Wemb), 2 (LSTM2 weights, biases)");
+    if (!(h->seg_ready & (1u << segment))) return h->fail(S2VT_ESTATE, "the last backward call did not finish this segment early");
+    cudaEvent_t ev = segment == 0 ? h->ev_wo : h->ev_seg[segment - 1];
+    CUDA_TRY(h, cudaStreamWaitEvent((cudaStream_t)stream, ev, 0));
+    const int first = segment == 0 ? h->iWo : (segment == 1 ? h->iWemb : h->iW2), last = segment == 0 ? h->ibo : (segment == 1 ? h->iWemb : h->ib2);
+    *offset = (int64_t)h->vars[first].off;
+    *count = (int64_t)(h->vars[last].off + h->vars[last].count() - h->vars[first].off);
+    h->seg_ready &= ~(1u << segment);      // one hand-out per backward call
+    if (segment == 0) h->wo_grad_early = false;
     return S2VT_OK;
 }
 

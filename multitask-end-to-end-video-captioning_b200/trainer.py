@@ -28,35 +28,51 @@ def exponential_decay(lr0, global_step, decay_steps, rate=0.5):
 _AR_STREAMS = {}
 
 
-def allreduce_gradients(model, bucket_bytes=32 << 20, overlap=True):
+def allreduce_gradients(model, bucket_bytes=0, overlap=True):
     """Sum the flat fp32 gradient block (+ aux slots: slice norm, loss, sum(mask)) over the ranks.
 
-    overlap: the gradients of embed_word_W / embed_word_b (a third of the bytes) are final before the BPTT chains start; their
-    all-reduce is enqueued on a stream that waits for exactly that point (`s2vt_grad_segment_ready`), so it runs under the chains.
-    The remaining ranges follow in buckets launched back to back once the backward call has finished."""
+    overlap: three ranges are final before the backward call's last kernel -- embed_word_W / embed_word_b before the BPTT chains
+    start, Wemb and the LSTM2 weights while the LSTM1 chain still runs -- and their all-reduces are enqueued on a stream that waits
+    for exactly those points (`s2vt_grad_segment_ready`), so they run under the remaining kernels.  What is left (frame projection,
+    LSTM1, aux slots) follows once the backward call has finished, one collective per contiguous range (bucket_bytes > 0 splits
+    ranges into buckets; NVSwitch bandwidth does not ask for it)."""
     rank, world = _world()
     if world == 1:
         return
     g = model.grads
     n = g.numel()
-    step = max(1, bucket_bytes // 4)
-    works, ranges = [], [(0, n)]
+    works, done = [], []
     if overlap and g.is_cuda and hasattr(model, 'grad_segment_ready'):
         dev = g.device
         st = _AR_STREAMS.get(dev)
         if st is None:
             st = _AR_STREAMS[dev] = torch.cuda.Stream(device=dev)
-        seg = model.grad_segment_ready(st)
-        if seg is not None:
+        for segment in (0, 1, 2):
+            seg = model.grad_segment_ready(st, segment)
+            if seg is None:
+                continue
             off, cnt = seg
             with torch.cuda.stream(st):
                 works.append(dist.all_reduce(g[off:off + cnt], op=dist.ReduceOp.SUM, async_op=True))
-            ranges = [(0, off), (off + cnt, n)]
-    for lo, hi in ranges:
+            done.append((off, off + cnt))
+    for lo, hi in complement_ranges(done, n):
+        step = max(1, bucket_bytes // 4) if bucket_bytes > 0 else hi - lo
         for i in range(lo, hi, step):
             works.append(dist.all_reduce(g[i:min(hi, i + step)], op=dist.ReduceOp.SUM, async_op=True))
     for w in works:
         w.wait()
+
+
+def complement_ranges(done, n):
+    """[0, n) minus the (disjoint) half-open ranges in `done`, as a sorted list of half-open ranges."""
+    out, pos = [], 0
+    for lo, hi in sorted(done):
+        if lo > pos:
+            out.append((pos, lo))
+        pos = max(pos, hi)
+    if pos < n:
+        out.append((pos, n))
+    return out
 
 
 class FeaturePipe(object):

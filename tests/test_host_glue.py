@@ -90,6 +90,10 @@ def test_batching_and_schedule():
         merged = sorted(sum(parts, []))
         assert merged == cli._batches(n, bs, 0, 1)[:len(merged)] and len(cli._batches(n, bs, 0, 1)) - len(merged) < world
     assert trainer.exponential_decay(1e-6, 999, 1000) == 1e-6 and trainer.exponential_decay(1e-6, 3000, 1000) == 1.25e-7
+    # gradient ranges left for the final all-reduce once the early-final segments (s2vt_grad_segment_ready) have been handed out
+    assert trainer.complement_ranges([], 10) == [(0, 10)]
+    assert trainer.complement_ranges([(7, 10), (0, 2), (4, 5)], 12) == [(2, 4), (5, 7), (10, 12)]
+    assert trainer.complement_ranges([(0, 12)], 12) == []
 
 
 def _dp_worker(rank, world, port, out):
