@@ -15,6 +15,7 @@
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_chain.cuh"
 #include "gemm_tcgen05_ws2.cuh"
+#include "gemm_tcgen05_pair.cuh"
 #include "gemm_tcgen05_sample.cuh"
 #include "kernels.cuh"
 
@@ -334,7 +335,16 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
                 // batched GEMMs are bound by L2 -> SM bandwidth, so use the widest tile (128 x 256: 85 flop per byte fetched vs
                 // 64 for 128 x 128).  gemm_backend 3 / 4 select the 128-wide tile without / with 2x2 TMA multicast (measured
                 // slower on B200: at cluster sizes <= 4 multicast does not reduce L2 traffic).
-                if (h->cfg.gemm_backend == 4 && (N / 128) % 2 == 0) CUDA_TRY(h, (tc::launch<128, Epi, 1, 2, 2>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false, fmt)));
+                // large products: 256 x 256 tiles on CTA pairs (cta_group::2, 131 flop per fetched byte); gemm_backend 14 keeps them on single CTAs
+                bool paired = false;
+                if constexpr (!Epi::kDirect && !kPdlLogits<Epi>::value) {
+                    if ((h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05) && N % 256 == 0 && M >= 1024) {
+                        CUDA_TRY(h, (tc::launch_pair<Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false, fmt)));
+                        paired = true;
+                    }
+                }
+                if (paired) {}
+                else if (h->cfg.gemm_backend == 4 && (N / 128) % 2 == 0) CUDA_TRY(h, (tc::launch<128, Epi, 1, 2, 2>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false, fmt)));
                 else if (h->cfg.gemm_backend == 3 || N % 256 != 0) CUDA_TRY(h, (tc::launch<128, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false, fmt)));
                 else CUDA_TRY(h, (tc::launch<256, Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, kPdlLogits<Epi>::value, fmt)));
             }
@@ -392,7 +402,9 @@ static int wgrad(s2vt_handle* h, cudaStream_t st, const F* X, int ldx, int Mf, c
             h->launches++;
             if (!h->tc_cache) h->tc_cache = new tc::MapCache();
             tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
-            if (Nf % 256 == 0) CUDA_TRY(h, (tc::launch<256, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false, fmt)));
+            if (Nf % 256 == 0 && Mf >= 256 && (h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05))
+                CUDA_TRY(h, (tc::launch_pair<EpiGradStore, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false, fmt)));
+            else if (Nf % 256 == 0) CUDA_TRY(h, (tc::launch<256, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false, fmt)));
             else CUDA_TRY(h, (tc::launch<128, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false, fmt)));
             if (h->prof) { cudaEventRecord(rec.b, st); h->prof_recs.push_back(rec); }
             return 0;
