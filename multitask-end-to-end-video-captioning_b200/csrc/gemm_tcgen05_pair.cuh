@@ -1,7 +1,7 @@
 // CTA-pair (cta_group::2) tcgen05 GEMM for the large batched products:  C[M,N] = A[M,K] . B[N,K]^T  (or C = X^T . Y, MN-major).
 //
 // The single-CTA kernel of gemm_tcgen05.cuh is bound by the L2 -> SM fill (~42 B/clk/SM): a 128 x 256 tile needs 48 KB per K-block
-// for 4.2 MFLOP (85 flop per fetched byte).  Here two CTAs on the two SMs of a TPC (cluster dims (1,2,1)) compute one 256 x 256 tile
+// for 4.2 MFLOP (85 flop per fetched byte).  Here two CTAs on the two SMs of a TPC (cluster dims (2,1,1)) compute one 256 x 256 tile
 // with ONE tcgen05.mma.cta_group::2 (M = 256, N = 256) per K step: CTA r of the pair holds rows [128 r, 128 r + 128) of A and rows
 // [128 r, 128 r + 128) of the B tile, the tensor cores read both halves of B, each CTA's TMEM receives its own 128 x 256 part of the
 // accumulator.  Per CTA and K-block that is 32 KB for the same 4.2 MFLOP -- 131 flop per fetched byte.
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(Threads<PAIR_BN, Epi>::N) gemm_tc_pair_kernel(
     float* Cs = reinterpret_cast<float*>(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * PAIR_BN;          // blockIdx.y = 2 * pair + rank
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * PAIR_BN;          // blockIdx.x = 2 * pair + rank: cluster dims (2, 1, 1)
     const int nb = n0 + 128 * (int)rank;                                  // this CTA's half of the B tile
     const int KBL = MN ? (K + BK - 1) / BK : K / BK;
 
@@ -164,7 +164,7 @@ inline cudaError_t launch_pair(MapCache& cache, cudaStream_t st, const bf16* A, 
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(N / PAIR_BN, ((M + 255) / 256) * 2, 1);
+    cfg.gridDim = dim3(((M + 255) / 256) * 2, N / PAIR_BN, 1);
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
@@ -176,10 +176,18 @@ inline cudaError_t launch_pair(MapCache& cache, cudaStream_t st, const bf16* A, 
         ++na;
     }
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 2; attr[na].val.clusterDim.z = 1;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
     ++na;
     cfg.attrs = attr;
     cfg.numAttrs = na;
+    static const bool debug = getenv("S2VT_DEBUG_CHAIN") != nullptr;
+    if (debug) {
+        int ncl = -1;
+        cudaError_t qe = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+        fprintf(stderr, "s2vt pair gemm: M=%d N=%d K=%d grid=(%u,%u) threads=%d smem=%d max active clusters=%d (%s)\n", M, N, K, cfg.gridDim.x, cfg.gridDim.y, NT, SMEM, ncl,
+                cudaGetErrorString(qe));
+        (void)cudaGetLastError();
+    }
     return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, fmt, ep);
 }
 
