@@ -183,6 +183,10 @@ int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int
  * makes s2vt_rollout run its decode loop (> 128 rows) as one persistent sampling chain instead of two launches per step (measured
  * slower on B200, kept for A/B runs; bit 5 selects its variant without the MMA / epilogue overlap) */
 int s2vt_set_overlap(s2vt_handle* h, int mask);
+/* debug / measurement: one GEMM of the given (padded) shape on scratch operands inside the bound workspace, through the engine's own
+ * dispatch (tile shape, CTA pairs, gemm_backend) -- scripts/gemm_shapes.py times every shape of an iteration in isolation with it.
+ * mn_major != 0: C[M,N] = X^T . Y over K rows (weight-gradient form); fp32_out: fp32 or fp16 result store. */
+int s2vt_debug_gemm(s2vt_handle* h, int M, int N, int K, int mn_major, int fp32_out, s2vt_stream st);
 /* debug: per-launch phase timestamps (%globaltimer) of CTA (0,0) of every tcgen05 GEMM; NULL disables */
 int s2vt_debug_probe(void* device_buffer);
 

@@ -54,6 +54,7 @@ SIGNATURES = {
     's2vt_rl_backward': (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _u64, _u32, _vp, _vp]),
     's2vt_xe_backward': (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _i32, _u64, _u32, _vp, _vp]),
     's2vt_xe_backward_sharded': (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _f32, _f32, _f32, _vp, _i32, _f32, _i32, _u64, _u32, _vp, _vp]),
+    's2vt_debug_gemm': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     's2vt_attribute_backward': (_i32, [_vp, _vp, _i32, _vp, _f32, _vp, _vp]),
     's2vt_optimizer_step': (_i32, [_vp, _f32, _f32, _i64, _i32, _vp, _vp]),
     's2vt_grad_segment_ready': (_i32, [_vp, _i32, _vp, C.POINTER(_i64), C.POINTER(_i64)]),

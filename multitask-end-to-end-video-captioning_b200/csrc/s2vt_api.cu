@@ -1223,6 +1223,38 @@ extern "C" size_t s2vt_workspace_bytes(const s2vt_handle* h, int n_videos, int n
 
 #include "beam.cuh"
 
+// ---- isolated GEMM timing (scripts/gemm_shapes.py): one product of a given shape on scratch operands, through the same dispatch
+// (and gemm_backend) as the engine's own products.  mn_major: C[M,N] = X^T . Y over K rows (the weight-gradient form).
+extern "C" int s2vt_debug_gemm(s2vt_handle* h, int M, int N, int K, int mn_major, int fp32_out, s2vt_stream st_) {
+    if (!h || !h->bound) return S2VT_ESTATE;
+    if (h->cfg.precision != S2VT_PREC_BF16) return h->fail(S2VT_EINVAL, "debug_gemm: bf16 mode only");
+    if (M <= 0 || N % 128 != 0 || (!mn_major && K % 128 != 0) || (mn_major && M % 128 != 0)) return h->fail(S2VT_EINVAL, "debug_gemm: N (and K, or M for mn_major) must be multiples of 128");
+    cudaStream_t st = (cudaStream_t)st_;
+    Arena a(h->ws, h->ws_bytes);
+    bf16* A = a.take<bf16>((size_t)(mn_major ? K : M) * (mn_major ? M : K));
+    bf16* B = a.take<bf16>((size_t)(mn_major ? K : N) * (mn_major ? N : K));
+    float* outF = a.take<float>((size_t)M * N);
+    f16* outT = a.take<f16>((size_t)M * N);
+    if (a.overflow) return h->fail(S2VT_ENOSPACE, "workspace too small: need %zu bytes", a.used);
+    static size_t zeroed_a = 0, zeroed_b = 0;
+    if (zeroed_a != (size_t)M * K || zeroed_b != (size_t)N * K) {      // operands: zeros (timing only), once per shape
+        CUDA_TRY(h, cudaMemsetAsync(A, 0, (size_t)M * K * 2, st));
+        CUDA_TRY(h, cudaMemsetAsync(B, 0, (size_t)N * K * 2, st));
+        zeroed_a = (size_t)M * K; zeroed_b = (size_t)N * K;
+    }
+    if (mn_major) {
+        EpiGradStore::Params ep = {outF, N, M, N, 0, 1.f};
+        bf16* none = nullptr;
+        return wgrad<bf16, bf16>(h, st, A, M, M, B, N, N, K, ep, none, none, M);
+    }
+    if (fp32_out) {
+        typename EpiStore<f16>::Params ep = {outF, nullptr, N, nullptr, M, 0};
+        return gemm<f16, CfgBig, EpiStore<f16>>(h, st, A, K, B, K, M, N, K, ep);
+    }
+    typename EpiStore<f16>::Params ep = {nullptr, outT, N, nullptr, M, 0};
+    return gemm<f16, CfgBig, EpiStore<f16>>(h, st, A, K, B, K, M, N, K, ep);
+}
+
 // ---- instrumentation ------------------------------------------------------------------------------------------------
 extern "C" long long s2vt_launch_count(const s2vt_handle* h) { return h ? h->launches : 0; }
 extern "C" int s2vt_profile(s2vt_handle* h, int enable) {
