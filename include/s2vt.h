@@ -52,7 +52,8 @@ enum { S2VT_GEMM_AUTO = 0, S2VT_GEMM_MMA_SYNC = 1, S2VT_GEMM_TCGEN05 = 2,
        S2VT_GEMM_CHAIN_MC4 = 11,     /* weights-stationary chains: activation multicast over clusters of 4 instead of 8 */
        S2VT_GEMM_CHAIN_NOMC = 12,    /* weights-stationary chains without activation multicast */
        S2VT_GEMM_CHAIN_PLAIN = 13,   /* > 128-row forward chains on the plain ring kernel instead of the pipelined weights-stationary one */
-       S2VT_GEMM_SINGLE_CTA = 14 };  /* large batched GEMMs on single-CTA 128 x 256 tiles instead of cta_group::2 pairs (256 x 256) */
+       S2VT_GEMM_SINGLE_CTA = 14,    /* large batched GEMMs on single-CTA 128 x 256 tiles instead of cta_group::2 pairs (256 x 256) */
+       S2VT_GEMM_PAIR_ALL = 15 };    /* every large batched GEMM on pairs (default: only where the isolated timings say the pair wins) */
 
 /* Model dimensions: the "Train Parameters" constants of reinforcement_multisampling_tf_s2vt.py:505-511
  * (dim_image, word_dim, lstm_dim, n_video_lstm_step, n_caption_lstm_step) and n_words = len(wordtoix) (:617). */

@@ -252,7 +252,7 @@ static int beam_impl(s2vt_handle* h, cudaStream_t st, const float* video, int B,
         typename EpiLstmFwd<F>::Params ep;
         memset(&ep, 0, sizeof ep);
         ep.M = rows; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp; ep.add0_mod = B;
-        ep.add1 = h->Etab; ep.tok = s.tok;
+        ep.add1 = reinterpret_cast<const F*>(h->Etab); ep.tok = s.tok;
         ep.c_prev = r.c2r[0]; ep.c_out = r.c2r[1]; ep.h_out = r.h2r[1]; ep.keep = 1.f;
         TRY((gemm<F, CfgStep, EpiLstmFwd<F>>(h, st, r.h2r[0], Hp, h->W2hT, Hp, rows, Gp, Hp, ep)));
         if (fused) {
@@ -348,7 +348,7 @@ static int beam_step_impl(s2vt_handle* h, cudaStream_t st, const float* state2, 
     TRY((gemm<F, CfgStep, EpiStore<F>>(h, st, h1n, Hp, h->W2xT, Hp, 1, Gp, Hp, eg)));
     typename EpiLstmFwd<F>::Params e2;
     memset(&e2, 0, sizeof e2);
-    e2.M = 1; e2.Hp = Hp; e2.bias = h->b2_p; e2.add0 = g2x; e2.add1 = h->Etab; e2.tok = word;
+    e2.M = 1; e2.Hp = Hp; e2.bias = h->b2_p; e2.add0 = g2x; e2.add1 = reinterpret_cast<const F*>(h->Etab); e2.tok = word;
     e2.c_prev = c2; e2.c_out = c2n; e2.h_out = h2n; e2.h_outF = h2F; e2.keep = 1.f;
     TRY((gemm<F, CfgStep, EpiLstmFwd<F>>(h, st, h2, Hp, h->W2hT, Hp, 1, Gp, Hp, e2)));       // lstm2([out1, emb], state2)
     typename EpiStore<F>::Params el = {logits, nullptr, Vp, h->bo_p, 1, 0};

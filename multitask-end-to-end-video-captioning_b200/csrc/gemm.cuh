@@ -237,7 +237,7 @@ struct EpiStore {
                 if (p.accumulate) { float4 w = *reinterpret_cast<const float4*>(p.outF + o); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
                 *reinterpret_cast<float4*>(p.outF + o) = v;
             }
-            if (p.outT) { p.outT[o] = from_f32<T>(v.x); p.outT[o + 1] = from_f32<T>(v.y); p.outT[o + 2] = from_f32<T>(v.z); p.outT[o + 3] = from_f32<T>(v.w); }
+            if (p.outT) store_gates4(p.outT + o, v);      // 4 consecutive values: one 8-byte (16-bit types) / 16-byte (fp32) store
         }
     }
 };
@@ -404,6 +404,7 @@ struct EpiGradStore {
     static constexpr bool kDirect = false;
     struct Params {
         float* grad; int ldg; int nrows; int ncols; int gate_h; float scale;
+        int atomic;      // != 0: several CTAs (split-K) add into the same elements -> red.global.add instead of a plain read-modify-write
     };
     template <class Cfg>
     __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
@@ -415,14 +416,16 @@ struct EpiGradStore {
                 int gr = m0 + r, u = n0 / 4 + ul;
                 if (gr >= p.nrows || u >= p.gate_h) continue;
                 float* dst = p.grad + (size_t)gr * p.ldg + (size_t)g * p.gate_h + u;
-                *dst += p.scale * Cs[r * Cfg::LDC + ul * 4 + g];
+                const float v = p.scale * Cs[r * Cfg::LDC + ul * 4 + g];
+                if (p.atomic) atomicAdd(dst, v); else *dst += v;
             }
         } else {
             for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::NTHREADS) {
                 int r = idx / Cfg::BN, c = idx % Cfg::BN, gr = m0 + r, gc = n0 + c;
                 if (gr >= p.nrows || gc >= p.ncols) continue;
                 float* dst = p.grad + (size_t)gr * p.ldg + gc;
-                *dst += p.scale * Cs[r * Cfg::LDC + c];
+                const float v = p.scale * Cs[r * Cfg::LDC + c];
+                if (p.atomic) atomicAdd(dst, v); else *dst += v;
             }
         }
     }
@@ -444,7 +447,7 @@ struct EpiLstmFwd {
         int M; int Hp;
         const float* bias;                 // [4Hp] packed
         const float* add0; int add0_mod;   // [*, 4Hp] input-side pre-activations; row = add0_mod > 0 ? row % add0_mod : row
-        const float* add1; const int* tok; // embedding table [V, 4Hp] gathered by tok[row] (nullable)
+        const T* add1; const int* tok;     // embedding table [V, 4Hp] gathered by tok[row] (nullable), in the forward operand type
         const float* pick_val; const int* pick_idx; int pick_ld, pick_nt;   // alternative to tok: per-tile candidates of EpiLogitsPick
         int* tok_out; int* ids_out; int ids_ld, ids_col;                    // ...resolved here; CTA column 0 records the word
         const float* c_prev; float* c_out; // [M, Hp]
@@ -471,7 +474,7 @@ struct EpiLstmFwd {
                 v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
             }
             if (p.add1) {
-                float4 a = *reinterpret_cast<const float4*>(p.add1 + (size_t)resolve_token(p, gr, gc) * G + gc);
+                float4 a = load_gates4(p.add1 + (size_t)resolve_token(p, gr, gc) * G + gc);
                 v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
             }
             float si = sigm<T>(v.x), tj = tanh_<T>(v.y), sf = sigm<T>(v.z + 1.0f), so = sigm<T>(v.w);
@@ -490,6 +493,26 @@ struct EpiLstmFwd {
     }
 };
 
+// 32 consecutive table values (one thread's 8 units x 4 gates) as 8 float4: 128 B of fp32 or 64 B of fp16 (four 16-byte loads in flight)
+__device__ __forceinline__ void load_row32(const float* a, float4* x) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = a ? reinterpret_cast<const float4*>(a)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void load_row32(const f16* a, float4* x) {
+    uint4 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = a ? reinterpret_cast<const uint4*>(a)[j] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __half2* hp = reinterpret_cast<const __half2*>(&u[j]);
+        const float2 a0 = __half22float2(hp[0]), a1 = __half22float2(hp[1]), a2 = __half22float2(hp[2]), a3 = __half22float2(hp[3]);
+        x[2 * j] = make_float4(a0.x, a0.y, a1.x, a1.y); x[2 * j + 1] = make_float4(a2.x, a2.y, a3.x, a3.y);
+    }
+}
+__device__ __forceinline__ void load_row32(const bf16* a, float4* x) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = a ? load_gates4(a + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
 template <class P>
 __device__ __forceinline__ int resolve_token(const P& p, int gr, int gc) {
     if (!p.pick_val) return p.tok[gr];
@@ -529,9 +552,8 @@ __device__ __forceinline__ void EpiLstmFwd<T>::prefetch(const Params& p, int gr,
 #pragma unroll
     for (int j = 0; j < 8; ++j) { pre.add[j] = b[j]; x0[j] = a0 ? a0[j] : make_float4(0.f, 0.f, 0.f, 0.f); }
     pre.c[0] = c[0]; pre.c[1] = c[1];
-    const float4* a1 = p.add1 ? reinterpret_cast<const float4*>(p.add1 + (size_t)resolve_token(p, gr, gc) * G + gc) : nullptr;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x1[j] = a1 ? a1[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const T* a1 = p.add1 ? p.add1 + (size_t)resolve_token(p, gr, gc) * G + gc : nullptr;
+    load_row32(a1, x1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) pre.add[j] = f4add(pre.add[j], f4add(x0[j], x1[j]));
 }

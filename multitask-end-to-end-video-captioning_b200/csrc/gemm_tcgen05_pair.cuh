@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(Threads<PAIR_BN, Epi>::N) gemm_tc_pair_kernel(
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * PAIR_BN;          // blockIdx.x = 2 * pair + rank: cluster dims (2, 1, 1)
     const int nb = n0 + 128 * (int)rank;                                  // this CTA's half of the B tile
-    const int KBL = MN ? (K + BK - 1) / BK : K / BK;
+    // gridDim.z > 1: split-K -- slice z multiplies K-blocks [kb0, kb0 + KBL); the epilogue functor must then accumulate atomically
+    const int KBT = MN ? (K + BK - 1) / BK : K / BK, KBS = (KBT + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * KBS;
+    const int KBL = KBT - kb0 < KBS ? (KBT - kb0 > 0 ? KBT - kb0 : 0) : KBS;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -87,13 +90,13 @@ __global__ void __launch_bounds__(Threads<PAIR_BN, Epi>::N) gemm_tc_pair_kernel(
                 unsigned char* a = smem + s * STAGE;
                 unsigned char* b = a + A_BYTES;
                 if constexpr (MN) {
-                    tma_load_2d_pair(a, &mapA, lbar, m0, i * BK);
-                    tma_load_2d_pair(a + 8192, &mapA, lbar, m0 + 64, i * BK);
-                    tma_load_2d_pair(b, &mapB, lbar, nb, i * BK);
-                    tma_load_2d_pair(b + 8192, &mapB, lbar, nb + 64, i * BK);
+                    tma_load_2d_pair(a, &mapA, lbar, m0, (kb0 + i) * BK);
+                    tma_load_2d_pair(a + 8192, &mapA, lbar, m0 + 64, (kb0 + i) * BK);
+                    tma_load_2d_pair(b, &mapB, lbar, nb, (kb0 + i) * BK);
+                    tma_load_2d_pair(b + 8192, &mapB, lbar, nb + 64, (kb0 + i) * BK);
                 } else {
-                    tma_load_2d_pair(a, &mapA, lbar, i * BK, m0);
-                    tma_load_2d_pair(b, &mapB, lbar, i * BK, nb);
+                    tma_load_2d_pair(a, &mapA, lbar, (kb0 + i) * BK, m0);
+                    tma_load_2d_pair(b, &mapB, lbar, (kb0 + i) * BK, nb);
                 }
             }
         }
@@ -114,14 +117,14 @@ __global__ void __launch_bounds__(Threads<PAIR_BN, Epi>::N) gemm_tc_pair_kernel(
                     mma_commit_pair(empty + s);
                 }
             }
-            if (leader_lane) mma_commit_pair(tmem_full);
+            if (leader_lane && KBL > 0) mma_commit_pair(tmem_full);
             __syncwarp();
         }
     } else {
         const int e = warp - 2, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        mbar_wait(tmem_full, 0);
+        if (KBL > 0) mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         constexpr int CPW = PAIR_BN / (Threads<PAIR_BN, Epi>::NEPI / 4);
         const int cbeg = (e >> 2) * CPW;
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(Threads<PAIR_BN, Epi>::N) gemm_tc_pair_kernel(
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
-    Epi::template apply<C>(ep, Cs, m0, n0);
+    if (KBL > 0) Epi::template apply<C>(ep, Cs, m0, n0);
     cluster_sync_all();                                                   // nobody leaves (or frees TMEM) while the peer may still signal / be read
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(Threads<PAIR_BN, Epi>::N) gemm_tc_pair_kernel(
 // N % 256 == 0.  MN == false: A [M, K], B [N, K] row-major; MN == true: A = X [K rows, M features], B = Y [K rows, N features].
 template <class Epi, bool MN = false>
 inline cudaError_t launch_pair(MapCache& cache, cudaStream_t st, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K,
-                               const typename Epi::Params& ep, bool pdl, uint32_t fmt) {
+                               const typename Epi::Params& ep, bool pdl, uint32_t fmt, int ksplit = 1) {
     if (M <= 0) return cudaSuccess;
     constexpr int NT = Threads<PAIR_BN, Epi>::N;
     using C = Cfg<PAIR_BN, NT>;
@@ -164,7 +167,7 @@ inline cudaError_t launch_pair(MapCache& cache, cudaStream_t st, const bf16* A, 
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(((M + 255) / 256) * 2, N / PAIR_BN, 1);
+    cfg.gridDim = dim3(((M + 255) / 256) * 2, N / PAIR_BN, ksplit < 1 ? 1 : ksplit);
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;

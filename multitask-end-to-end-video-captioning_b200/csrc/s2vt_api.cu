@@ -114,7 +114,7 @@ template <typename F> static void layout_state(s2vt_handle* h, Arena& a, F assig
     float* b2_p = a.take<float>(Gp);
     float* bo_p = a.take<float>(Vp);
     size_t copies_end = a.used;
-    float* Etab = a.take<float>((size_t)Vp * Gp);
+    float* Etab = reinterpret_cast<float*>(a.take<char>((size_t)Vp * Gp * e));   // forward operand type: fp16 in the bf16 mode (82 MB, L2-resident), fp32 in the fp32 mode
     assign(params, grads, m, v, sq, scal, WeT, W1xT, W1hT, W1h, W1x, W2xT, W2x, W2eT, W2e, W2hT, W2h, WoT, Wo, WembC, attrWT, be_p, b1_p, b2_p, bo_p, Etab,
            copies_begin, copies_end);
 }
@@ -265,7 +265,7 @@ template <typename T> struct EpiBytes<EpiLstmFwd<T>> {
         const double H = h->H, G = 4.0 * h->H;
         double b = M * H * 4 * 2 + M * H * sizeof(T);                       // c in, c out, h out
         if (p.add0) b += M * G * 4;
-        if (p.add1) b += M * G * 4;
+        if (p.add1) b += M * G * sizeof(T);                                 // Etab rows in the forward operand type
         if (p.gates_out) b += M * G * sizeof(T);
         if (p.hdrop_out) b += M * H * sizeof(T);
         return b;
@@ -338,7 +338,12 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
                 // large products: 256 x 256 tiles on CTA pairs (cta_group::2, 131 flop per fetched byte); gemm_backend 14 keeps them on single CTAs
                 bool paired = false;
                 if constexpr (!Epi::kDirect && !kPdlLogits<Epi>::value) {
-                    if ((h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05) && N % 256 == 0 && M >= 1024) {
+                    // isolated timings (scripts/gemm_shapes.py, profiles/r2_gemm_shapes.md): the pair tile wins where the single-CTA tile is fill-bound --
+                    // long contractions (K >= 8192: 1375 vs 1178 TF/s) and narrow outputs with K >= 4096; wide short-K products are bound by
+                    // their fp32 stores and the MMA rate, where the pair only adds its cluster hand-shakes
+                    const bool pair_wins = K >= 8192 || (K >= 4096 && N <= 512);
+                    if ((h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05 || h->cfg.gemm_backend == 15) && N % 256 == 0 && M >= 1024 &&
+                        (pair_wins || h->cfg.gemm_backend == 15)) {
                         CUDA_TRY(h, (tc::launch_pair<Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false, fmt)));
                         paired = true;
                     }
@@ -402,8 +407,15 @@ static int wgrad(s2vt_handle* h, cudaStream_t st, const F* X, int ldx, int Mf, c
             h->launches++;
             if (!h->tc_cache) h->tc_cache = new tc::MapCache();
             tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
-            if (Nf % 256 == 0 && Mf >= 256 && (h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05))
-                CUDA_TRY(h, (tc::launch_pair<EpiGradStore, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false, fmt)));
+            if (Nf % 256 == 0 && Mf >= 256 && (h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05 || h->cfg.gemm_backend == 15)) {
+                // few output tiles (e.g. dWe: 24, dW2[emb rows]: 64 on 148 SMs): split the long contraction over grid z, partial tiles are added atomically
+                const int tiles = ((Mf + 255) / 256) * 2 * (Nf / 256), kblocks = (R + tc::BK - 1) / tc::BK;
+                int ks = tiles >= 100 ? 1 : 148 / tiles;
+                if (ks > kblocks / 8) ks = kblocks / 8 > 0 ? kblocks / 8 : 1;
+                EpiGradStore::Params eps = ep;
+                eps.atomic = ks > 1;
+                CUDA_TRY(h, (tc::launch_pair<EpiGradStore, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, eps, false, fmt, ks)));
+            }
             else if (Nf % 256 == 0) CUDA_TRY(h, (tc::launch<256, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false, fmt)));
             else CUDA_TRY(h, (tc::launch<128, EpiGradStore, 1, 1, 1, true>(mc, st, (const bf16*)X, ldx, (const bf16*)Y, ldy, Mf, Nf, R, ep, false, fmt)));
             if (h->prof) { cudaEventRecord(rec.b, st); h->prof_recs.push_back(rec); }
@@ -563,7 +575,8 @@ static int refresh_impl(s2vt_handle* h, cudaStream_t st) {
     pack_vector_kernel<<<(G + 255) / 256, 256, 0, s2>>>(h->P_(h->ib2), G, h->b2_p, H); KCHECK(h);
     pack_vector_kernel<<<(V + 255) / 256, 256, 0, s2>>>(h->P_(h->ibo), V, h->bo_p, 0); KCHECK(h);
     // Etab[v, :] = Wemb[v, :] . W2[emb rows]  (packed gate order) -- the word-embedding contribution to LSTM2's gates
-    typename EpiStore<F>::Params ep = {h->Etab, nullptr, Gp, nullptr, Vp, 0};
+    typename EpiStore<F>::Params ep = {nullptr, nullptr, Gp, nullptr, Vp, 0};
+    if (std::is_same<F, float>::value) ep.outF = h->Etab; else ep.outT = reinterpret_cast<F*>(h->Etab);
     TRY((gemm<F, CfgBig, EpiStore<F>>(h, s2, h->WembC, Ep, h->W2eT, Ep, Vp, Gp, Ep, ep)));
     CUDA_TRY(h, cudaEventRecord(h->ev_refresh, s2));
     h->fresh = true;
@@ -715,7 +728,7 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
         typename EpiLstmFwd<F>::Params& ep = cells[i];
         memset(&ep, 0, sizeof ep);
         ep.M = R; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp; ep.add0_mod = B;
-        ep.add1 = h->Etab; ep.tok = r.tok[0];                     // step 0: <bos>; later steps resolve the previous step's candidates
+        ep.add1 = reinterpret_cast<const F*>(h->Etab); ep.tok = r.tok[0];                     // step 0: <bos>; later steps resolve the previous step's candidates
         static const int dbg_no_etab = getenv("S2VT_DEBUG_NO_ETAB") ? atoi(getenv("S2VT_DEBUG_NO_ETAB")) : 0;   // timing experiments only (wrong words)
         if (dbg_no_etab & 1) ep.add1 = nullptr;
         if (i > 0 && !(dbg_no_etab & 2)) { ep.pick_val = r.pick_val; ep.pick_idx = r.pick_idx; ep.pick_ld = r.pick_ld; ep.pick_nt = nt; ep.ids_out = r.ids; ep.ids_ld = Tc; ep.ids_col = i - 1; }
@@ -912,7 +925,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
             typename EpiLstmFwd<F>::Params ep;
             memset(&ep, 0, sizeof ep);
             ep.M = N; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = p.G2x + (size_t)t * N * Gp;
-            if (t >= Tv) { ep.add1 = h->Etab; ep.tok = p.prev_tok + (size_t)(t - Tv) * N; ep.hdrop_out = p.out2d + (size_t)(t - Tv) * N * Hp; }
+            if (t >= Tv) { ep.add1 = reinterpret_cast<const F*>(h->Etab); ep.tok = p.prev_tok + (size_t)(t - Tv) * N; ep.hdrop_out = p.out2d + (size_t)(t - Tv) * N * Hp; }
             ep.c_prev = p.c2_all + (size_t)t * N * Hp; ep.c_out = p.c2_all + (size_t)(t + 1) * N * Hp;
             ep.h_out = p.h2_all + (size_t)(t + 1) * N * Hp;
             ep.gates_out = p.gates2 ? p.gates2 + (size_t)t * N * Gp : nullptr;

@@ -115,7 +115,7 @@ def test_cta_pair_gemms_equal_single_cta_gemms():
     """Large batched GEMMs (projections, G2x, logits, d logits . Wo^T, MN-major weight gradients) on 256 x 256 cta_group::2 pair tiles
     (gemm_tcgen05_pair.cuh) against the single-CTA 128 x 256 tiles (gemm_backend single_cta): one accumulator, K ascending in both."""
     dims = dict(D=1536, E=500, H=1000, V=9972)
-    a = _run('auto', dims, 5, 35, 64, 3)
+    a = _run('pair_all', dims, 5, 35, 64, 3)
     p = _run('single_cta', dims, 5, 35, 64, 3)
     assert torch.equal(a['greedy'], p['greedy']) and torch.equal(a['samp'], p['samp'])
     assert torch.equal(a['logits'], p['logits'])
