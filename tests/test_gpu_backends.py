@@ -49,7 +49,10 @@ def test_tcgen05_variants_match_mma_sync(backend, reference_run):
         assert rel(got['logits'], ref['logits']) < 2e-3
         assert abs(got['loss'] - ref['loss']) < 2e-3 * max(1.0, abs(ref['loss']))
         assert rel(got['grads'], ref['grads']) < 2e-2
-        assert rel(got['params'], ref['params']) < 1e-3
+        # one clipped Adam step moves every element by about +-lr (1e-3) whatever its gradient's size: an element whose gradient is at the
+        # rounding noise of the two mainloops may move the other way (2 lr); anything systematic would show up everywhere
+        assert rel(got['params'], ref['params']) < 5e-3
+        assert float(((got['params'] - ref['params']).abs() > 1e-4).float().mean()) < 1e-3
 
 
 def test_full_size_multicast_chain_equals_plain_chain():
