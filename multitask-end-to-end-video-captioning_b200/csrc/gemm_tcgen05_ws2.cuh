@@ -21,9 +21,14 @@
 
 namespace tc {
 
-constexpr int WS2_BN = 96, WS2_STAGES = 4, WS2_EPI_WARPS = 12, WS2_THREADS = 64 + 32 * WS2_EPI_WARPS, WS2_KB_MAX = 16;
-constexpr int WS2_A_STAGE = 64 * 128, WS2_W_TILE = WS2_BN * 128;
-constexpr int WS2_SMEM = WS2_STAGES * WS2_A_STAGE + WS2_KB_MAX * WS2_W_TILE + 256 + 1024;
+constexpr int WS2_KB_MAX = 16, WS2_A_STAGE = 64 * 128;
+// BN: gate columns of the resident slab (96: 43 slabs x 3 row groups; 64: 64 slabs x 2 row groups, a smaller slab and a deeper ring)
+template <int BN> struct Ws2Cfg {
+    static constexpr int STAGES = (227 * 1024 - 2048 - WS2_KB_MAX * BN * 128) / WS2_A_STAGE;      // what the slab leaves of the 227 KB
+    static constexpr int EPI_WARPS = 4 * (BN / 32), THREADS = 64 + 32 * EPI_WARPS, W_TILE = BN * 128;
+    static constexpr int SMEM = STAGES * WS2_A_STAGE + WS2_KB_MAX * W_TILE + 256 + 1024;
+    static constexpr int RG = BN >= 96 ? 3 : 2;
+};
 
 #ifdef S2VT_CHAIN_PROBE
 #define WS2_PROBE(stmt) do { stmt; } while (0)
@@ -31,12 +36,13 @@ constexpr int WS2_SMEM = WS2_STAGES * WS2_A_STAGE + WS2_KB_MAX * WS2_W_TILE + 25
 #define WS2_PROBE(stmt) do { } while (0)
 #endif
 
-template <class Epi>
-__global__ void __launch_bounds__(WS2_THREADS) gemm_tc_ws2_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+template <class Epi, int WS2_BN = 96>
+__global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                         int K, int M, int rpg, int n_limit, int a_row0, int a_row_stride,
                                                                         const typename Epi::Params* __restrict__ steps, int nsteps,
                                                                         unsigned* __restrict__ flags, uint32_t fmt) {
     static_assert(Epi::kDirect, "register epilogue");
+    constexpr int WS2_STAGES = Ws2Cfg<WS2_BN>::STAGES, WS2_EPI_WARPS = Ws2Cfg<WS2_BN>::EPI_WARPS, WS2_W_TILE = Ws2Cfg<WS2_BN>::W_TILE;
     // instruction descriptor: F32 accumulate, BF16 formats (cleared to F16 by fmt), K-major operands, N = 96, M = 64
     const uint32_t IDESC = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WS2_BN >> 3) << 17) | ((uint32_t)(64 >> 4) << 24)) & ~fmt;
     extern __shared__ unsigned char smem_raw[];
@@ -204,10 +210,10 @@ __global__ void __launch_bounds__(WS2_THREADS) gemm_tc_ws2_chain_kernel(const __
 // on them (the engine's padded units between 4 H and N produce zeros in the plain kernels; here they are covered up to N because
 // the slab count is taken from N).  Returns cudaErrorLaunchOutOfResources (nothing launched) when the shape does not fit: M > 384,
 // K > 1024, or the grid cannot be co-resident.
-template <class Epi>
+template <class Epi, int WS2_BN = 96>
 inline cudaError_t launch_ws2_chain(MapCache& cache, cudaStream_t st, const bf16* A, int lda, int a_total_rows, int a_row0, int a_row_stride, const bf16* B,
                                     int ldb, int M, int N, int K, const typename Epi::Params* steps_dev, int nsteps, unsigned* flags, bool pdl, uint32_t fmt) {
-    constexpr int RG = 3;
+    constexpr int RG = Ws2Cfg<WS2_BN>::RG, WS2_SMEM = Ws2Cfg<WS2_BN>::SMEM, WS2_THREADS = Ws2Cfg<WS2_BN>::THREADS;
     if (K % BK != 0 || K / BK > WS2_KB_MAX || M <= 128 || M > RG * 128) return cudaErrorLaunchOutOfResources;
     const int rpg = ((M + RG - 1) / RG + 15) & ~15;                       // rows per row group, halves are multiples of 8 rows
     const int ncol = (N + WS2_BN - 1) / WS2_BN;
@@ -215,7 +221,7 @@ inline cudaError_t launch_ws2_chain(MapCache& cache, cudaStream_t st, const bf16
     const CUtensorMap* ma = get_map(cache, A, a_total_rows, K, lda, rpg / 2);
     const CUtensorMap* mb = get_map(cache, B, N, K, ldb, WS2_BN);
     if (!ma || !mb) return cudaErrorInvalidValue;
-    auto kern = gemm_tc_ws2_chain_kernel<Epi>;
+    auto kern = gemm_tc_ws2_chain_kernel<Epi, WS2_BN>;
     static int max_ctas = -1;
     if (max_ctas < 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WS2_SMEM);

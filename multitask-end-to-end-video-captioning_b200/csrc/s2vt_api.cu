@@ -474,7 +474,11 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
                     // > 128 rows: weights-stationary slabs + two software-pipelined halves per row group (gemm_tcgen05_ws2.cuh);
                     // the plain ring chain is the fallback (shape does not fit / gemm_backend 13)
                     e = cudaErrorLaunchOutOfResources;
-                    if (h->cfg.gemm_backend != 13 && h->cfg.gemm_backend != 10)
+                    static const int ws2_bn64 = getenv("S2VT_WS2_BN64") ? atoi(getenv("S2VT_WS2_BN64")) : 0;      // experiment: 64-column slabs, 2 row groups, 12-stage ring
+                    if (ws2_bn64 && c.M <= 256 && h->cfg.gemm_backend != 13 && h->cfg.gemm_backend != 10)
+                        e = tc::launch_ws2_chain<Epi, 64>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n,
+                                                          gbar + 32, true, fmt);
+                    else if (h->cfg.gemm_backend != 13 && h->cfg.gemm_backend != 10)
                         e = tc::launch_ws2_chain<Epi>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n,
                                                       gbar + 32, true, fmt);
                     if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<128, Epi, 1>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }
