@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
         // ---- MMA issuer: one M = 64 tile per half, accumulators at TMEM columns 0 and 128
         const bool leader = elect_one();
         mbar_wait(wfull, 0);
+        const uint64_t adesc0 = make_desc(smem_u32(ring)), bdesc0 = make_desc(smem_u32(wsm));   // start-address field: +bytes/16 per stage / K-block (no carry: smem < 256 KB)
         int g = 0;
         for (int s = 0; s < nsteps; ++s) {
 #pragma unroll
@@ -150,9 +151,8 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int i = 0; i < KBL; ++i, ++g) {
                     const int st = g % WS2_STAGES;
-                    mbar_wait(full + st, (g / WS2_STAGES) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t adesc = make_desc(smem_u32(ring + st * WS2_A_STAGE)), bdesc = make_desc(smem_u32(wsm + i * WS2_W_TILE));
+                    mbar_wait(full + st, (g / WS2_STAGES) & 1);      // (TMA completion: no tcgen05 fence needed, the per-half fence above orders the TMEM reuse)
+                    const uint64_t adesc = adesc0 + (uint64_t)((st * WS2_A_STAGE) >> 4), bdesc = bdesc0 + (uint64_t)((i * WS2_W_TILE) >> 4);
                     if (leader) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base + (uint32_t)(hf * 128), adesc + 2 * k, bdesc + 2 * k, IDESC, i > 0 || k != 0);
