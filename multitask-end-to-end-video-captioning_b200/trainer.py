@@ -26,6 +26,10 @@ def exponential_decay(lr0, global_step, decay_steps, rate=0.5):
 
 
 _AR_STREAMS = {}
+# which early-final gradient segments are all-reduced under the backward kernels (S2VT_AR_SEGMENTS="" disables the overlap, "0" keeps
+# only embed_word_W/b); measured on 8 B200: see DESIGN.md section 6
+import os as _os
+EARLY_SEGMENTS = tuple(int(x) for x in _os.environ.get('S2VT_AR_SEGMENTS', '0,1,2').split(',') if x.strip() != '')
 
 
 def allreduce_gradients(model, bucket_bytes=0, overlap=True):
@@ -47,7 +51,7 @@ def allreduce_gradients(model, bucket_bytes=0, overlap=True):
         st = _AR_STREAMS.get(dev)
         if st is None:
             st = _AR_STREAMS[dev] = torch.cuda.Stream(device=dev)
-        for segment in (0, 1, 2):
+        for segment in EARLY_SEGMENTS:
             seg = model.grad_segment_ready(st, segment)
             if seg is None:
                 continue
