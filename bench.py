@@ -565,8 +565,9 @@ def run_b200(args):
         collective = {'op': 'NCCL all-reduce(sum) of the flat fp32 gradient block, one call, nothing overlapped', 'bytes': nbytes, 'ms': ar_ms,
                       'algbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9, 'busbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
                       'nvlink5_per_direction_GBps': 900.0,
-                      'in_step': 'embed_word_W/b, Wemb and the LSTM2 gradients (~80 % of the bytes) are reduced under the backward kernels '
-                                 '(s2vt_grad_segment_ready); the rest follows the backward call'}
+                      'in_step': 'one collective after the backward call; reducing the early-final segments under the backward kernels '
+                                 '(s2vt_grad_segment_ready, S2VT_AR_SEGMENTS=0,1,2) measured slower on 8 B200: 9.37 vs 9.25 ms per iteration',
+                      'early_segments': list(s2vt_b200.trainer.EARLY_SEGMENTS)}
         if args.videos % world == 0:
             Bs = args.videos // world
             m2 = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=Bs,

@@ -26,20 +26,23 @@ def exponential_decay(lr0, global_step, decay_steps, rate=0.5):
 
 
 _AR_STREAMS = {}
-# which early-final gradient segments are all-reduced under the backward kernels (S2VT_AR_SEGMENTS="" disables the overlap, "0" keeps
-# only embed_word_W/b); measured on 8 B200: see DESIGN.md section 6
+# Which early-final gradient segments are all-reduced UNDER the backward kernels (S2VT_AR_SEGMENTS="0,1,2": embed_word_W/b, Wemb,
+# LSTM2).  Default: none.  Measured on 8 B200 (round 2, 20 iterations each): no overlap 9.25 ms per iteration, segment 0 only 9.28 ms,
+# segments 0,1,2 9.37 ms -- the NCCL kernels take SMs and L2 bandwidth from the persistent recurrent chains they run beside, which
+# costs more than the 0.39 ms the collective takes on an idle GPU.
 import os as _os
-EARLY_SEGMENTS = tuple(int(x) for x in _os.environ.get('S2VT_AR_SEGMENTS', '0,1,2').split(',') if x.strip() != '')
+EARLY_SEGMENTS = tuple(int(x) for x in _os.environ.get('S2VT_AR_SEGMENTS', '').split(',') if x.strip() != '')
 
 
 def allreduce_gradients(model, bucket_bytes=0, overlap=True):
     """Sum the flat fp32 gradient block (+ aux slots: slice norm, loss, sum(mask)) over the ranks.
 
     overlap: three ranges are final before the backward call's last kernel -- embed_word_W / embed_word_b before the BPTT chains
-    start, Wemb and the LSTM2 weights while the LSTM1 chain still runs -- and their all-reduces are enqueued on a stream that waits
-    for exactly those points (`s2vt_grad_segment_ready`), so they run under the remaining kernels.  What is left (frame projection,
-    LSTM1, aux slots) follows once the backward call has finished, one collective per contiguous range (bucket_bytes > 0 splits
-    ranges into buckets; NVSwitch bandwidth does not ask for it)."""
+    start, Wemb and the LSTM2 weights while the LSTM1 chain still runs.  For the segments listed in EARLY_SEGMENTS the all-reduce is
+    enqueued on a stream that waits for exactly that point (`s2vt_grad_segment_ready`), so it runs under the remaining kernels; the
+    default list is empty because that overlap measured SLOWER than one collective after the backward call (see EARLY_SEGMENTS).
+    What is left follows once the backward call has finished, one collective per contiguous range (bucket_bytes > 0 splits ranges
+    into buckets; NVSwitch bandwidth does not ask for it)."""
     rank, world = _world()
     if world == 1:
         return
