@@ -33,9 +33,9 @@ GOLD = os.path.join(ROOT, 'tests', 'golden')
 DIMS = dict(D=1536, E=500, H=1000, V=9972)
 METRIC = 'reinforce_train_videos_per_s'
 # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the persistent chain kernels at the bench configuration, keyed by
-# (rows, N, K) (profiles/r1_chain_ncu_full_f.md; the two 64-row forward chains -- 115 and 80 steps -- are averaged)
-STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = {(320, 1024, 4096): 790878208, (320, 4096, 1024): 1189724160,
-                                     (64, 4096, 1024): 123086336, (64, 1024, 4096): 170185472}
+# (rows, N, K) (profiles/r2_chain_ncu_full.md; the 64-row forward figure is the 80-step LSTM2 encoder chain)
+STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = {(320, 1024, 4096): 788933120, (320, 4096, 1024): 1149113600,
+                                     (64, 4096, 1024): 98099456, (64, 1024, 4096): 166935040}
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -717,7 +717,7 @@ def run_b200(args):
                       % (chain_kernel_name(dM, dN, dK), dM, dN, dK, 'backward' if dK > dN else 'forward'),
             'bound': 'hbm', 'achieved': d_ach, 'peak': hbm, 'unit': 'GB/s', 'frac': d_ach / hbm if hbm else None,
             'traffic': STEP_KERNEL_DRAM_BYTES_PER_LAUNCH.get((dM, dN, dK)),
-            'traffic_source': 'ncu --set full dram__bytes_read+write per launch, cold caches (profiles/)',
+            'traffic_source': 'ncu --set full dram__bytes_read+write per launch, cold caches (profiles/r2_chain_ncu_full.md)',
             'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)',
             'launches_per_step': dln / args.steps, 'recurrent_steps_per_launch': dcnt / dln if dln else None,
             'us_per_launch': 1e3 * dms / dln if dln else None, 'ms_per_step': dms / args.steps,
