@@ -41,8 +41,12 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // A peer may multicast into this CTA before it has armed its own `full` barrier for the step: the transaction count simply goes
 // negative until the local expect_tx; it cannot run a phase ahead because peers pass the grid barrier only after this CTA's epilogue.
 // (ChainAcc<BN>::N, gemm_tcgen05.cuh, is shared with the per-step kernels so both sum in the same order.)
+// MMA2 (weights stationary, KS == 1, two accumulators): a SECOND issuing warp -- the last warp of the CTA -- takes the odd K-blocks (accumulator 1) while
+// warp 1 takes the even ones (accumulator 0).  In situ one warp issues a tcgen05.mma every ~100 cycles (mbarrier wait, descriptors, four MMAs per K-block)
+// against 62 in a tight loop (scripts/micro/mma_rate.cu); the K loop of a 64-row step is that issue chain.
+template <int BN, class Epi, int KS, bool WS> struct ChainMma2 { static constexpr bool value = WS && KS == 1 && ChainAcc<BN>::N == 2; };
 template <int BN, class Epi, int KS, bool WS, int CX = 1>
-__global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+__global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, WS>::value ? 32 : 0)) gemm_tc_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                             int K, int a_rows, int a_row0, int a_row_stride,
                                                                             const typename Epi::Params* __restrict__ steps, int nsteps,
                                                                             unsigned* __restrict__ gbar, uint32_t fmt) {
@@ -52,6 +56,8 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
     static_assert(KS == 1 || KS == 4, "split-K cluster of 4 or none");
     static_assert(CX == 1 || (WS && KS == 1), "activation multicast: weights-stationary forward chains only");
     constexpr int NACC = ChainAcc<BN>::N;
+    constexpr bool MMA2 = ChainMma2<BN, Epi, KS, WS>::value;
+    constexpr int MMA2_WARP = Threads<BN, Epi>::N / 32;               // index of the second issuing warp (appended after the epilogue warps)
     constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
     static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation: power of two <= 512 columns");
     uint32_t crank = 0;
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
         for (int s = 0; s < NBAR; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(tmem_full, 1);
+        mbar_init(tmem_full, MMA2 ? 2 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if constexpr (WS) {   // the whole weight slab, once (weights never depend on the previous kernel)
             mbar_expect_tx(empty, (uint32_t)(KBL * C::B_BYTES));
@@ -180,13 +186,14 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_chain_kernel(cons
                 }
             }
             __syncwarp();
-        } else if (warp == 1) {
+        } else if (warp == 1 || (MMA2 && warp == MMA2_WARP)) {
             const bool leader = elect_one();
             if constexpr (WS) {
                 if (s == 0) mbar_wait(empty, 0);           // weight slab has landed
-                for (int i = 0; i < KBL; ++i) {
+                const int i0 = (MMA2 && warp != 1) ? 1 : 0, istep = MMA2 ? 2 : 1;      // MMA2: this warp's K-blocks (even / odd)
+                for (int i = i0; i < KBL; i += istep) {
                     mbar_wait(full + i, s & 1);
-                    if (i == 0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   // once per step: orders the MMAs after the previous epilogue's TMEM reads
+                    if (i == i0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   // once per step: orders the MMAs after the previous epilogue's TMEM reads
                     CHAIN_PROBE(if (probe && i == 0 && leader) probe[8 * s + 2] = gtimer()); CHAIN_PROBE(if (probe && i == KBL - 1 && leader) probe[8 * s + 7] = gtimer());
                     const uint64_t adesc = make_desc(smem_u32(smem + i * WS_A)), bdesc = make_desc(smem_u32(wsm + i * C::B_BYTES));
                     if (leader) {
@@ -302,6 +309,7 @@ template <int BN, class Epi, int KS, bool WS = false, int CX = 1>
 inline cudaError_t launch_chain(MapCache& cache, cudaStream_t st, const bf16* A, int lda, int a_total_rows, int a_row0, int a_row_stride, const bf16* B,
                                 int ldb, int M, int N, int K, const typename Epi::Params* steps_dev, int nsteps, unsigned* gbar, bool pdl, uint32_t fmt = 0) {
     constexpr int NT = Threads<BN, Epi>::N;
+    constexpr int NTL = NT + (ChainMma2<BN, Epi, KS, WS>::value ? 32 : 0);       // + the second issuing warp
     using C = Cfg<BN, NT>;
     constexpr int SMEM = (WS ? 16 * (64 * 128 + C::B_BYTES) + 512 + 1024 : C::SMEM_BYTES + 512) + (KS > 1 ? KS * 32 * BN * 4 : 0);
     if (WS && (M > 64 || K / BK / KS > 16)) return cudaErrorLaunchOutOfResources;
@@ -319,12 +327,12 @@ inline cudaError_t launch_chain(MapCache& cache, cudaStream_t st, const bf16* A,
         int per_sm = 0, dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, SMEM);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NTL, SMEM);
         if (e != cudaSuccess) return e;
         max_ctas = per_sm * sms;
         if (CX > 1) {   // clusters must fit inside GPCs: ask how many can be resident at once
             cudaLaunchConfig_t q = {};
-            q.gridDim = dim3(N / BN, (M + BM - 1) / BM, KS); q.blockDim = dim3(NT); q.dynamicSmemBytes = SMEM;
+            q.gridDim = dim3(N / BN, (M + BM - 1) / BM, KS); q.blockDim = dim3(NTL); q.dynamicSmemBytes = SMEM;
             cudaLaunchAttribute qa[1];
             qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = CX; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = KS;
             q.attrs = qa; q.numAttrs = 1;
@@ -343,7 +351,7 @@ inline cudaError_t launch_chain(MapCache& cache, cudaStream_t st, const bf16* A,
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(NT);
+    cfg.blockDim = dim3(NTL);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
