@@ -180,9 +180,7 @@ int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* 
 int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int64_t* offset, int64_t* count);
 /* tuning: which independent pieces use the library's internal side stream (bit 0: late half of s2vt_refresh, bit 1: the
  * vocabulary weight gradient, bit 2: the LSTM1 backward chain); default 7.  Bit 3 (debug) makes s2vt_beam_search use its un-fused
- * step -- materialised logits and separate top-k / bookkeeping / state-gather launches -- the checker of the fused one; bit 4 (debug)
- * makes s2vt_rollout run its decode loop (> 128 rows) as one persistent sampling chain instead of two launches per step (measured
- * slower on B200, kept for A/B runs; bit 5 selects its variant without the MMA / epilogue overlap) */
+ * step -- materialised logits and separate top-k / bookkeeping / state-gather launches -- the checker of the fused one. */
 int s2vt_set_overlap(s2vt_handle* h, int mask);
 /* debug / measurement: one GEMM of the given (padded) shape on scratch operands inside the bound workspace, through the engine's own
  * dispatch (tile shape, CTA pairs, gemm_backend) -- scripts/gemm_shapes.py times every shape of an iteration in isolation with it.

@@ -41,10 +41,10 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // A peer may multicast into this CTA before it has armed its own `full` barrier for the step: the transaction count simply goes
 // negative until the local expect_tx; it cannot run a phase ahead because peers pass the grid barrier only after this CTA's epilogue.
 // (ChainAcc<BN>::N, gemm_tcgen05.cuh, is shared with the per-step kernels so both sum in the same order.)
-// MMA2 (weights stationary, KS == 1, two accumulators): a SECOND issuing warp -- the last warp of the CTA -- takes the odd K-blocks (accumulator 1) while
+// MMA2 (two accumulators): a SECOND issuing warp -- the last warp of the CTA -- takes the odd K-blocks (accumulator 1) while
 // warp 1 takes the even ones (accumulator 0).  In situ one warp issues a tcgen05.mma every ~100 cycles (mbarrier wait, descriptors, four MMAs per K-block)
 // against 62 in a tight loop (scripts/micro/mma_rate.cu); the K loop of a 64-row step is that issue chain.
-template <int BN, class Epi, int KS, bool WS> struct ChainMma2 { static constexpr bool value = WS && KS == 1 && ChainAcc<BN>::N == 2; };
+template <int BN, class Epi, int KS, bool WS> struct ChainMma2 { static constexpr bool value = ChainAcc<BN>::N == 2; };
 template <int BN, class Epi, int KS, bool WS, int CX = 1>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, WS>::value ? 32 : 0)) gemm_tc_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                             int K, int a_rows, int a_row0, int a_row_stride,
@@ -202,10 +202,11 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, 
                     }
                 }
             } else {
-                for (int i = 0; i < KBL; ++i) {
+                const int i0 = (MMA2 && warp != 1) ? 1 : 0, istep = MMA2 ? 2 : 1;
+                for (int i = i0; i < KBL; i += istep) {
                     const int g = g0 + i, st = g % C::STAGES;
                     mbar_wait(full + st, (g / C::STAGES) & 1);
-                    if (i == 0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (i == i0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     CHAIN_PROBE(if (probe && i == 0 && leader) probe[8 * s + 2] = gtimer()); CHAIN_PROBE(if (probe && i == KBL - 1 && leader) probe[8 * s + 7] = gtimer());
                     const uint32_t a = smem_u32(smem + st * C::STAGE_BYTES);
                     const uint64_t adesc = make_desc(a), bdesc = make_desc(a + C::A_BYTES);
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
         if constexpr (KS > 1) {
-            if (warp < 2) cluster_sync_all();      // pairs with the exchange barrier of the epilogue warps
+            if (warp < 2 || (MMA2 && warp == MMA2_WARP)) cluster_sync_all();      // pairs with the exchange barrier of the epilogue warps
             // No second cluster barrier: a peer writes into this CTA's recv buffers again only after the NEXT grid barrier, which it
             // passes only after every CTA -- this one included -- has finished the epilogue that reads them.
         }

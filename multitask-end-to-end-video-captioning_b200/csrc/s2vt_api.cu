@@ -16,7 +16,6 @@
 #include "gemm_tcgen05_chain.cuh"
 #include "gemm_tcgen05_ws2.cuh"
 #include "gemm_tcgen05_pair.cuh"
-#include "gemm_tcgen05_sample.cuh"
 #include "kernels.cuh"
 
 template <typename T, typename F>
@@ -741,52 +740,10 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
         typename EpiLogitsPick<T>::Params el = {R, h->V, h->bo_p, K * B, seed, (uint32_t)i, row_base, r.pick_val, r.pick_idx, r.pick_ld};
         picks[i] = el;
     }
-    bool chained = false;
-    if constexpr (std::is_same<T, bf16>::value) {
-        // > 128 rows (the K+1 rollout of a training iteration), opt-in through s2vt_set_overlap bit 4: every step of the loop in ONE
-        // persistent launch, cell phase and vocabulary-pick phase separated by grid barriers (gemm_tcgen05_sample.cuh).  Measured at the
-        // bench shape: 40.5 us per step against ~37 us for the two programmatic-dependent launches per step (9.46-9.56 vs 9.31 ms per
-        // iteration) -- the barriers and the 21 CTAs idle in the cell phase cost more than the kernel boundaries that PDL already hides;
-        // it stays as the base of the version that overlaps step s+1's h.W2h with step s's pick epilogue.
-        const size_t pick_off = (Tc * sizeof(cells[0]) + 15) & ~(size_t)15;
-        if ((h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05) && (h->overlap & 16) && R > 128 && logits_bn == 256 &&
-            pick_off + Tc * sizeof(picks[0]) <= (size_t)(h->T + 1) * 512) {
-            if (!h->tc_cache) h->tc_cache = new tc::MapCache();
-            tc::MapCache& mc = *static_cast<tc::MapCache*>(h->tc_cache);
-            char* dev = (char*)r.chain;
-            CUDA_TRY(h, cudaMemcpyAsync(dev, cells.data(), Tc * sizeof(cells[0]), cudaMemcpyHostToDevice, st));
-            CUDA_TRY(h, cudaMemcpyAsync(dev + pick_off, picks.data(), Tc * sizeof(picks[0]), cudaMemcpyHostToDevice, st));
-            chain_begin(h, st);
-            auto launcher = (h->overlap & 32) ? tc::launch_sample_chain<EpiLstmFwd<F>, EpiLogitsPick<bf16>, false>      // bit 5: without the overlap
-                                              : tc::launch_sample_chain<EpiLstmFwd<F>, EpiLogitsPick<bf16>, true>;
-            cudaError_t e = launcher(
-                mc, st, (const bf16*)r.h2r[0], (const bf16*)r.h2r[1], Hp, R, (const bf16*)h->W2hT, Hp, Gp, (const bf16*)h->WoT, Hp, Vp, Hp,
-                (const typename EpiLstmFwd<F>::Params*)dev, (const typename EpiLogitsPick<bf16>::Params*)(dev + pick_off), Tc, h->gbar + (st == h->side ? 16 : 0), true,
-                tc::FmtOf<F>::A | tc::FmtOf<F>::B);
-            if (e == cudaSuccess) {
-                chained = true;
-                h->launches++;
-                if (h->prof && h->chain_open) {   // one record: per step the cell GEMM + the vocabulary GEMM and their epilogue traffic
-                    const double lm = logical_dim(h, R), lk = logical_dim(h, Hp);
-                    for (int i = 0; i < Tc; ++i) {
-                        h->chain.flops += 2.0 * lm * lk * (logical_dim(h, Gp) + logical_dim(h, Vp));
-                        h->chain.bytes += (2.0 * lm * lk + (logical_dim(h, Gp) + logical_dim(h, Vp)) * lk) * sizeof(T) + EpiBytes<EpiLstmFwd<F>>::get(h, cells[i], R);
-                    }
-                    h->chain.count += Tc; h->chain.launches += 1; h->chain.M = R; h->chain.N = Gp + Vp; h->chain.K = Hp;
-                }
-            } else if (e != cudaErrorLaunchOutOfResources) {
-                return h->fail(S2VT_ECUDA, "sampling chain launch failed: %s", cudaGetErrorString(e));
-            } else {
-                (void)cudaGetLastError();
-            }
-            chain_end(h, st);
-        }
+    for (int i = 0; i < Tc; ++i) {
+        TRY((gemm<F, CfgStep, EpiLstmFwd<F>>(h, st, r.h2r[i & 1], Hp, h->W2hT, Hp, R, Gp, Hp, cells[i])));
+        TRY((gemm<F, CfgBig, EpiLogitsPick<T>>(h, st, r.h2r[(i + 1) & 1], Hp, h->WoT, Hp, R, Vp, Hp, picks[i])));
     }
-    if (!chained)
-        for (int i = 0; i < Tc; ++i) {
-            TRY((gemm<F, CfgStep, EpiLstmFwd<F>>(h, st, r.h2r[i & 1], Hp, h->W2hT, Hp, R, Gp, Hp, cells[i])));
-            TRY((gemm<F, CfgBig, EpiLogitsPick<T>>(h, st, r.h2r[(i + 1) & 1], Hp, h->WoT, Hp, R, Vp, Hp, picks[i])));
-        }
     resolve_picks_kernel<<<(R + 127) / 128, 128, 0, st>>>(r.pick_val, r.pick_idx, r.pick_ld, nt, R, r.ids, Tc, Tc - 1); KCHECK(h);
     if (K > 0 && sampled_out)
         CUDA_TRY(h, cudaMemcpyAsync(sampled_out, r.ids, (size_t)K * B * Tc * sizeof(int), cudaMemcpyDeviceToDevice, st));
