@@ -6,7 +6,7 @@
 // epilogue -- one after the other.  This kernel changes three things:
 //   * the CTA's weight slab (96 gate columns x K, 192 KB) is loaded ONCE and stays in shared memory: a step streams activations only;
 //     grid = ceil(N / 96) column slabs x 3 row groups (43 x 3 = 129 CTAs at H = 1000, one per SM);
-//   * every row group is cut into two independent HALVES (<= 64 rows, multiplied as the top half of a tcgen05.mma M = 128 tile; two TMEM accumulators each: even / odd K-blocks).
+//   * every row group is cut into two independent HALVES (<= 64 rows, one tcgen05.mma M = 64 tile and one TMEM accumulator each).
 //     Step s+1 of a half needs step s of THAT half only, so while the epilogue warps run the cell of half 0 the TMA / MMA warps
 //     already fetch and multiply half 1, and vice versa: barrier latency, fill and MMAs hide under the other half's epilogue;
 //   * the dependency is a counter per (row group, half) that only the 43 CTAs of that row group touch -- arrivals from the epilogue
@@ -14,8 +14,8 @@
 //     CTA-wide or grid-wide barrier exists inside the time loop.
 // Accumulation order equals the other tcgen05 kernels (one accumulator, K ascending), so results are bit-identical to them.
 //
-// (tcgen05.mma M = 64 (cta_group::1) would place accumulator row m in TMEM lane  (m % 16) + 32 (m / 16)  -- cute tmem_frg_1sm, "half sub-partition"
-// atom; the first version of this kernel used it and was correct, but an M = 64 instruction holds the tensor pipe twice as long as an M = 128 one.)
+// tcgen05.mma M = 64 (cta_group::1) places accumulator row m in TMEM lane  (m % 16) + 32 (m / 16)  (cute tmem_frg_1sm, "half
+// sub-partition" atom): warp quarter q holds rows 16 q .. 16 q + 15 in its lanes 0 .. 15.
 #pragma once
 #include "gemm_tcgen05_chain.cuh"
 
@@ -44,11 +44,8 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
     static_assert(Epi::kDirect, "register epilogue");
     constexpr int WS2_STAGES = Ws2Cfg<WS2_BN>::STAGES, WS2_EPI_WARPS = Ws2Cfg<WS2_BN>::EPI_WARPS, WS2_W_TILE = Ws2Cfg<WS2_BN>::W_TILE;
     constexpr int WS2_MMA2_WARP = 2 + WS2_EPI_WARPS;
-    // instruction descriptor: F32 accumulate, BF16 formats (cleared to F16 by fmt), K-major operands, N = 96, M = 128.
-    // A half has <= 64 rows, but an M = 64 tcgen05.mma occupies the pipe for ~126 cycles against 62 for M = 128 (measured: the issue phase of a half
-    // took 4.1 us with M = 64 whatever the ring depth or the number of issuing warps), so the halves are multiplied as M = 128 tiles whose rows 64..127
-    // are whatever follows the 8 KB stage in shared memory (the next stage / the head of the weight slab): those accumulator rows are never read.
-    const uint32_t IDESC = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WS2_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) & ~fmt;
+    // instruction descriptor: F32 accumulate, BF16 formats (cleared to F16 by fmt), K-major operands, N = 96, M = 64
+    const uint32_t IDESC = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WS2_BN >> 3) << 17) | ((uint32_t)(64 >> 4) << 24)) & ~fmt;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = smem;                                           // [STAGES][64 rows x 128 B]   activation K-blocks
@@ -174,7 +171,7 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
         }
         __syncwarp();
     } else {
-        // ---- epilogue: 12 warps = 4 TMEM lane quarters x 3 chunks of 32 gate columns (8 units); a lane owns accumulator row 32 q + lane (rows < 64 are real)
+        // ---- epilogue: 12 warps = 4 TMEM lane quarters x 3 chunks of 32 gate columns (8 units); lanes 0..15 of a warp own a row each
         const int e = warp - 2, q = warp & 3, chunk = e >> 2;
         const int gc = n0 + 32 * chunk;
         const bool col_ok = gc < n_limit;
@@ -183,8 +180,8 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 if (valid[hf] == 0) continue;
-                const int rih = 32 * q + lane;                            // row inside the half = TMEM lane (M = 128 layout); quarters 2, 3 hold no valid row
-                const int gr = (rih < valid[hf] && col_ok) ? row_lo[hf] + rih : M;   // M: "no row" for the epilogue functor
+                const int rih = 16 * q + lane;                            // row inside the half (lanes >= 16 hold no accumulator row)
+                const int gr = (lane < 16 && rih < valid[hf] && col_ok) ? row_lo[hf] + rih : M;   // M: "no row" for the epilogue functor
                 typename Epi::Pre pre;
                 Epi::prefetch(ep, gr, gc, pre);
                 mbar_wait(acc_full + hf, s & 1);
