@@ -209,10 +209,11 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
 // hypothesis that back-to-back tcgen05.mma into one tile wait for each other: scripts/micro/mma_rate.cu shows they do not (a
 // 128 x N x 16 MMA costs ~64 cycles for every N <= 128, dependent or not), while every extra tile costs a full TMEM read in the
 // epilogue (64 B/clk: 0.5 us per 128 x 128 tile).  Kept at 1; the plumbing stays for experiments.
-// Round 2: tiles of up to 128 columns (all recurrent-step kernels and chains) use TWO accumulators, even K-blocks into the first and odd ones into the second, summed by
-// the epilogue -- so that the weights-stationary forward chain can issue from two warps (gemm_tcgen05_chain.cuh, MMA2) and still sum in the order of the
-// per-step kernels (bit-identical results across the variants).
-template <int BN> struct ChainAcc { static constexpr int N = BN <= 128 ? 2 : 1; };
+// Round 2: the 32-column tiles (64-row chains and per-step kernels) use TWO accumulators, even K-blocks into the first and odd ones into the second, summed by
+// the epilogue -- so that the 64-row chains can issue from two warps (gemm_tcgen05_chain.cuh, MMA2) and still sum in the order of the per-step kernels
+// (bit-identical results across the variants).  Measured: 64-row forward chain 5.46 -> 4.90 us per step, 64-row BPTT chain 7.76 -> 7.2; for the 128-column
+// tiles of the 320-row chains (fill- / exchange-bound) and the M = 64 halves of the pipelined chain a second issuing warp changed nothing or cost time.
+template <int BN> struct ChainAcc { static constexpr int N = BN == 32 ? 2 : 1; };
 
 template <int BN, class Epi, int KS, int CX = 1, int CY = 1, bool MN = false>
 __global__ void __launch_bounds__(Threads<BN, Epi>::N) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,

@@ -25,7 +25,7 @@ constexpr int WS2_KB_MAX = 16, WS2_A_STAGE = 64 * 128;
 // BN: gate columns of the resident slab (96: 43 slabs x 3 row groups; 64: 64 slabs x 2 row groups, a smaller slab and a deeper ring)
 template <int BN> struct Ws2Cfg {
     static constexpr int STAGES = (227 * 1024 - 2048 - WS2_KB_MAX * BN * 128) / WS2_A_STAGE;      // what the slab leaves of the 227 KB
-    static constexpr int EPI_WARPS = 4 * (BN / 32), THREADS = 64 + 32 * EPI_WARPS + 32, W_TILE = BN * 128;      // + 32: the second MMA-issuing warp (last warp)
+    static constexpr int EPI_WARPS = 4 * (BN / 32), THREADS = 64 + 32 * EPI_WARPS, W_TILE = BN * 128;
     static constexpr int SMEM = STAGES * WS2_A_STAGE + WS2_KB_MAX * W_TILE + 256 + 1024;
     static constexpr int RG = BN >= 96 ? 3 : 2;
 };
@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
                                                                         unsigned* __restrict__ flags, uint32_t fmt) {
     static_assert(Epi::kDirect, "register epilogue");
     constexpr int WS2_STAGES = Ws2Cfg<WS2_BN>::STAGES, WS2_EPI_WARPS = Ws2Cfg<WS2_BN>::EPI_WARPS, WS2_W_TILE = Ws2Cfg<WS2_BN>::W_TILE;
-    constexpr int WS2_MMA2_WARP = 2 + WS2_EPI_WARPS;
     // instruction descriptor: F32 accumulate, BF16 formats (cleared to F16 by fmt), K-major operands, N = 96, M = 64
     const uint32_t IDESC = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WS2_BN >> 3) << 17) | ((uint32_t)(64 >> 4) << 24)) & ~fmt;
     extern __shared__ unsigned char smem_raw[];
@@ -85,14 +84,14 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
         for (int s = 0; s < WS2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(wfull, 1);
-        for (int hf = 0; hf < 2; ++hf) { mbar_init(acc_full + hf, 2); mbar_init(acc_free + hf, WS2_EPI_WARPS); }      // acc_full: one commit per issuing warp
+        for (int hf = 0; hf < 2; ++hf) { mbar_init(acc_full + hf, 1); mbar_init(acc_free + hf, WS2_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the weight slab, once: weights never depend on the previous kernel (only s2vt_refresh writes them)
         mbar_expect_tx(wfull, (uint32_t)(KBL * WS2_W_TILE));
         for (int i = 0; i < KBL; ++i) tma_load_2d_raw(wsm + i * WS2_W_TILE, &mapB, wfull, i * BK, n0);
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -138,11 +137,9 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
             }
         }
         __syncwarp();
-    } else if (warp == 1 || warp == WS2_MMA2_WARP) {
-        // ---- two MMA issuers (one warp issues a tcgen05.mma every ~126 cycles in situ, the pipe takes one every 62): warp 1 multiplies the even
-        // K-blocks into accumulator 0 of the half, the last warp the odd ones into accumulator 1; the epilogue adds them.  TMEM columns: half * 256 + acc * 128
+    } else if (warp == 1) {
+        // ---- MMA issuer: one M = 64 tile per half, accumulators at TMEM columns 0 and 128
         const bool leader = elect_one();
-        const int par = warp == 1 ? 0 : 1;
         mbar_wait(wfull, 0);
         const uint64_t adesc0 = make_desc(smem_u32(ring)), bdesc0 = make_desc(smem_u32(wsm));   // start-address field: +bytes/16 per stage / K-block (no carry: smem < 256 KB)
         int g = 0;
@@ -153,19 +150,18 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
                 if (s > 0) mbar_wait(acc_free + hf, (s - 1) & 1);         // the epilogue of step s-1 has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int i = 0; i < KBL; ++i, ++g) {
-                    if ((i & 1) != par) continue;                    // the other warp's K-block (g keeps counting: the ring position is shared)
                     const int st = g % WS2_STAGES;
                     mbar_wait(full + st, (g / WS2_STAGES) & 1);      // (TMA completion: no tcgen05 fence needed, the per-half fence above orders the TMEM reuse)
                     const uint64_t adesc = adesc0 + (uint64_t)((st * WS2_A_STAGE) >> 4), bdesc = bdesc0 + (uint64_t)((i * WS2_W_TILE) >> 4);
                     if (leader) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base + (uint32_t)(hf * 256 + par * 128), adesc + 2 * k, bdesc + 2 * k, IDESC, i > 1 || k != 0);
+                        for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base + (uint32_t)(hf * 128), adesc + 2 * k, bdesc + 2 * k, IDESC, i > 0 || k != 0);
                         mma_commit(empty + st);
                     }
                 }
                 if (leader) {
                     mma_commit(acc_full + hf);
-                    WS2_PROBE(if (probe && par == 1) probe[8 * s + 4 * hf + 1] = gtimer());      // all MMAs of the half issued
+                    WS2_PROBE(if (probe) probe[8 * s + 4 * hf + 1] = gtimer());                  // all MMAs of the half issued
                 }
             }
         }
@@ -188,13 +184,7 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
                 WS2_PROBE(if (probe && threadIdx.x == 64) probe[8 * s + 4 * hf + 2] = gtimer());        // accumulator ready, epilogue starts
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * 256 + 32 * chunk), v);
-                if (KBL > 1) {                                           // + the odd K-blocks' accumulator (same order as ChainAcc<128> in the other kernels)
-                    float w[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * 256 + 128 + 32 * chunk), w);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += w[j];
-                }
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * 128 + 32 * chunk), v);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_free + hf)) : "memory");
@@ -211,7 +201,7 @@ __global__ void __launch_bounds__(Ws2Cfg<WS2_BN>::THREADS) gemm_tc_ws2_chain_ker
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
     }
 }
 
