@@ -213,6 +213,7 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, f
 // the epilogue -- so that the 64-row chains can issue from two warps (gemm_tcgen05_chain.cuh, MMA2) and still sum in the order of the per-step kernels
 // (bit-identical results across the variants).  Measured: 64-row forward chain 5.46 -> 4.90 us per step, 64-row BPTT chain 7.76 -> 7.2; for the 128-column
 // tiles of the 320-row chains (fill- / exchange-bound) and the M = 64 halves of the pipelined chain a second issuing warp changed nothing or cost time.
+// (four warps / four accumulators measured slower than two: 8.75 vs 8.67 ms per iteration)
 template <int BN> struct ChainAcc { static constexpr int N = BN == 32 ? 2 : 1; };
 
 template <int BN, class Epi, int KS, int CX = 1, int CY = 1, bool MN = false>

@@ -44,9 +44,9 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // MMA2 (two accumulators): a SECOND issuing warp -- the last warp of the CTA -- takes the odd K-blocks (accumulator 1) while
 // warp 1 takes the even ones (accumulator 0).  In situ one warp issues a tcgen05.mma every ~100 cycles (mbarrier wait, descriptors, four MMAs per K-block)
 // against 62 in a tight loop (scripts/micro/mma_rate.cu); the K loop of a 64-row step is that issue chain.
-template <int BN, class Epi, int KS, bool WS> struct ChainMma2 { static constexpr bool value = ChainAcc<BN>::N == 2; };
+template <int BN, class Epi, int KS, bool WS> struct ChainMma2 { static constexpr bool value = ChainAcc<BN>::N >= 2; };
 template <int BN, class Epi, int KS, bool WS, int CX = 1>
-__global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, WS>::value ? 32 : 0)) gemm_tc_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+__global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, WS>::value ? 32 * (ChainAcc<BN>::N - 1) : 0)) gemm_tc_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                             int K, int a_rows, int a_row0, int a_row_stride,
                                                                             const typename Epi::Params* __restrict__ steps, int nsteps,
                                                                             unsigned* __restrict__ gbar, uint32_t fmt) {
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, 
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
         for (int s = 0; s < NBAR; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(tmem_full, MMA2 ? 2 : 1);
+        mbar_init(tmem_full, MMA2 ? NACC : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if constexpr (WS) {   // the whole weight slab, once (weights never depend on the previous kernel)
             mbar_expect_tx(empty, (uint32_t)(KBL * C::B_BYTES));
@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, 
                 }
             }
             __syncwarp();
-        } else if (warp == 1 || (MMA2 && warp == MMA2_WARP)) {
+        } else if (warp == 1 || (MMA2 && warp >= MMA2_WARP)) {
             const bool leader = elect_one();
             if constexpr (WS) {
                 if (s == 0) mbar_wait(empty, 0);           // weight slab has landed
-                const int i0 = (MMA2 && warp != 1) ? 1 : 0, istep = MMA2 ? 2 : 1;      // MMA2: this warp's K-blocks (even / odd)
+                const int i0 = (MMA2 && warp != 1) ? warp - MMA2_WARP + 1 : 0, istep = MMA2 ? NACC : 1;      // MMA2: this warp's K-blocks (i mod NACC)
                 for (int i = i0; i < KBL; i += istep) {
                     mbar_wait(full + i, s & 1);
                     if (i == i0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   // once per step: orders the MMAs after the previous epilogue's TMEM reads
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, 
                     }
                 }
             } else {
-                const int i0 = (MMA2 && warp != 1) ? 1 : 0, istep = MMA2 ? 2 : 1;
+                const int i0 = (MMA2 && warp != 1) ? warp - MMA2_WARP + 1 : 0, istep = MMA2 ? NACC : 1;
                 for (int i = i0; i < KBL; i += istep) {
                     const int g = g0 + i, st = g % C::STAGES;
                     mbar_wait(full + st, (g / C::STAGES) & 1);
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(Threads<BN, Epi>::N + (ChainMma2<BN, Epi, KS, 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
         if constexpr (KS > 1) {
-            if (warp < 2 || (MMA2 && warp == MMA2_WARP)) cluster_sync_all();      // pairs with the exchange barrier of the epilogue warps
+            if (warp < 2 || (MMA2 && warp >= MMA2_WARP)) cluster_sync_all();      // pairs with the exchange barrier of the epilogue warps
             // No second cluster barrier: a peer writes into this CTA's recv buffers again only after the NEXT grid barrier, which it
             // passes only after every CTA -- this one included -- has finished the epilogue that reads them.
         }
@@ -310,7 +310,7 @@ template <int BN, class Epi, int KS, bool WS = false, int CX = 1>
 inline cudaError_t launch_chain(MapCache& cache, cudaStream_t st, const bf16* A, int lda, int a_total_rows, int a_row0, int a_row_stride, const bf16* B,
                                 int ldb, int M, int N, int K, const typename Epi::Params* steps_dev, int nsteps, unsigned* gbar, bool pdl, uint32_t fmt = 0) {
     constexpr int NT = Threads<BN, Epi>::N;
-    constexpr int NTL = NT + (ChainMma2<BN, Epi, KS, WS>::value ? 32 : 0);       // + the second issuing warp
+    constexpr int NTL = NT + (ChainMma2<BN, Epi, KS, WS>::value ? 32 * (ChainAcc<BN>::N - 1) : 0);       // + the additional issuing warps
     using C = Cfg<BN, NT>;
     constexpr int SMEM = (WS ? 16 * (64 * 128 + C::B_BYTES) + 512 + 1024 : C::SMEM_BYTES + 512) + (KS > 1 ? KS * 32 * BN * 4 : 0);
     if (WS && (M > 64 || K / BK / KS > 16)) return cudaErrorLaunchOutOfResources;
