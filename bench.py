@@ -676,8 +676,21 @@ def run_b200(args):
             model.xe_step(feats_dev, cap_ids, cap_mask, 1e-4)
         xe_ms = timed(5, lambda: model.xe_step(feats_dev, cap_ids, cap_mask, 1e-4))
         beam.update({'xe_train_videos_per_s': 5 * B / (xe_ms / 1e3), 'xe_ms_per_step': xe_ms / 5})
-        # BASELINE config 5: latency vs throughput of beam-5 captioning over the batch size (one GPU here; `--workload beam` shards it)
-        beam['beam5_sweep'] = beam_sweep(s2vt_b200, torch, dist, args, bias, rank, world, [int(x) for x in args.beam_batches.split(',')])
+        # same-precision reference point: the whole iteration in the fp32 mode (fp32 operands and storage, SIMT FMA GEMMs, one launch per recurrent
+        # step -- the 1e-5 parity mode, not a tuned product path; the reference computes in fp32)
+        m32f = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=B,
+                                                 n_video_lstm_step=Tv, n_caption_lstm_step=35, bias_init_vector=bias, dropout_rate=0.9,
+                                                 precision='fp32', max_videos=B, max_rows=K * B, seed=4)
+        m32f.variable('embed_word_W').mul_(3.0); m32f.refresh()
+        t32 = s2vt_b200.trainer.ReinforceTrainer(m32f, scorer, n_samples=K, start_learning_rate=1e-6, decay_steps=1000, clip_norm=5.0, seed=2024)
+        t32.step(feats_dev, vidx_dev)
+        f32_ms = timed(2, lambda: t32.step(feats_dev, vidx_dev)) / 2
+        beam['same_precision_fp32'] = {'videos_per_s': B / (f32_ms / 1e3), 'ms_per_step': f32_ms, 'note': 'precision=fp32: SIMT fp32 GEMMs + per-step launches (parity mode)'}
+        del t32, m32f
+        torch.cuda.empty_cache()
+    # BASELINE config 5: latency vs throughput of beam-5 captioning over the batch size, sharded over the ranks with no collective (N > 1: fewer batch sizes)
+    sweep_batches = [int(x) for x in args.beam_batches.split(',')] if world == 1 else [64, 1024, 1024 * world]
+    beam['beam5_sweep'] = beam_sweep(s2vt_b200, torch, dist, args, bias, rank, world, sweep_batches)
     if rank != 0:
         return
     peaks = {}
