@@ -255,4 +255,253 @@ inline cudaError_t launch_ws2_chain(MapCache& cache, cudaStream_t st, const bf16
     return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, M, rpg, N, a_row0, a_row_stride, steps_dev, nsteps, flags, fmt);
 }
 
+// -------------------------------------------------------------------------------------------------------------------------------
+// The same scheme for the BPTT chain:  dh_rec[rows, units] = dG(t+1)[rows, 4 H] . W_h^T  ->  fused BasicLSTMCell backward.
+// The contraction is 4 H = 4096 long, so it is split over KS = 4 CTAs (K slices of 1024 gate columns): CTA (c, rg, ks) keeps the
+// 96-unit x 1024 slab of W_h in shared memory (192 KB), streams the K slice of its half's gate-gradient rows, and leaves a partial
+// 64 x 96 tile in TMEM.  Instead of the 4-CTA DSMEM exchange of the ring chain (cluster barrier, 7 us epilogue) the partial tiles go
+// through L2: every CTA stores its partial into its own slot of a scratch matrix (plain vector stores, deterministic), announces it on
+// a counter per (row group, half, column slab), and -- once the four partials are there -- finishes a quarter of the half's rows:
+// sums the four slots in slice order and runs the cell backward.  The wait for the three peers costs an L2 round trip, but it sits in
+// one half's dependency cycle while the TMA / MMA warps are already busy with the other half.
+// grid (ceil(N / 96), 3, 4) = 11 x 3 x 4 = 132 CTAs at H = 1000; flags: [2 * 3] step flags + [2 * 3 * ncol] partial counters.
+template <class Epi>
+__global__ void __launch_bounds__(Ws2Cfg<96>::THREADS) gemm_tc_ws2_bwd_chain_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                                                    int K, int M, int rpg, int n_limit, int a_row0, int a_row_stride,
+                                                                                    const typename Epi::Params* __restrict__ steps, int nsteps,
+                                                                                    unsigned* __restrict__ flags, float* __restrict__ scratch, uint32_t fmt) {
+    constexpr int WS2_BN = 96, KS = 4;
+    constexpr int WS2_STAGES = Ws2Cfg<WS2_BN>::STAGES, WS2_EPI_WARPS = Ws2Cfg<WS2_BN>::EPI_WARPS, WS2_W_TILE = Ws2Cfg<WS2_BN>::W_TILE;
+    static_assert(Epi::kDirect && Epi::kUnitsPerChunk == 8, "cell-backward register epilogue (8 units per call)");
+    const uint32_t IDESC = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(WS2_BN >> 3) << 17) | ((uint32_t)(64 >> 4) << 24)) & ~fmt;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = smem;
+    unsigned char* wsm = smem + WS2_STAGES * WS2_A_STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(wsm + WS2_KB_MAX * WS2_W_TILE);
+    uint64_t* empty = full + WS2_STAGES;
+    uint64_t* wfull = empty + WS2_STAGES;
+    uint64_t* acc_full = wfull + 1;
+    uint64_t* acc_free = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * WS2_BN, rg = blockIdx.y, ks = blockIdx.z;
+    const int KBL = K / BK / KS, kb0 = ks * KBL;                          // this CTA's K-blocks
+    const unsigned ncol = gridDim.x;
+    const int hr = rpg >> 1;
+    const int ldn = (int)ncol * WS2_BN;                                    // scratch row length (units, padded to whole slabs)
+    int row_lo[2], valid[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        row_lo[hf] = rg * rpg + hf * hr;
+        int v = M - row_lo[hf];
+        valid[hf] = v < 0 ? 0 : (v > hr ? hr : v);
+    }
+    unsigned* step_flag = flags;                                           // [rg * 2 + hf]: CTAs of the row group that finished the step of this half
+    unsigned* part_cnt = flags + 8;                                        // [(rg * 2 + hf) * ncol + c]: partial tiles stored for this column slab
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int s = 0; s < WS2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(wfull, 1);
+        for (int hf = 0; hf < 2; ++hf) { mbar_init(acc_full + hf, 1); mbar_init(acc_free + hf, WS2_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(wfull, (uint32_t)(KBL * WS2_W_TILE));
+        for (int i = 0; i < KBL; ++i) tma_load_2d_raw(wsm + i * WS2_W_TILE, &mapB, wfull, (kb0 + i) * BK, n0);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp == 0) {
+        const bool leader = elect_one();
+        int g = 0;
+        for (int s = 0; s < nsteps; ++s) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (valid[hf] == 0) continue;
+                if (s > 0) {
+                    if (lane == 0) {
+                        const unsigned* f = step_flag + (rg * 2 + hf);
+                        const unsigned target = (unsigned)s * ncol * KS;
+                        long long t0 = clock64();
+                        for (unsigned spins = 1; ld_acquire_gpu(f) < target; ++spins) {
+                            if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+                                printf("s2vt: ws2 bwd chain flag timed out (step %d half %d block %d,%d,%d)\n", s, hf, blockIdx.x, blockIdx.y, blockIdx.z);
+                                __trap();
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (leader) asm volatile("fence.proxy.async;" ::: "memory");
+                const int arow = a_row0 + s * a_row_stride + row_lo[hf];
+                for (int i = 0; i < KBL; ++i, ++g) {
+                    const int st = g % WS2_STAGES;
+                    if (g >= WS2_STAGES) mbar_wait(empty + st, ((g / WS2_STAGES) - 1) & 1);
+                    if (leader) {
+                        mbar_expect_tx(full + st, (uint32_t)(hr * 128));
+                        tma_load_2d_raw(ring + st * WS2_A_STAGE, &mapA, full + st, (kb0 + i) * BK, arow);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        const bool leader = elect_one();
+        mbar_wait(wfull, 0);
+        const uint64_t adesc0 = make_desc(smem_u32(ring)), bdesc0 = make_desc(smem_u32(wsm));
+        int g = 0;
+        for (int s = 0; s < nsteps; ++s) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (valid[hf] == 0) continue;
+                if (s > 0) mbar_wait(acc_free + hf, (s - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int i = 0; i < KBL; ++i, ++g) {
+                    const int st = g % WS2_STAGES;
+                    mbar_wait(full + st, (g / WS2_STAGES) & 1);
+                    const uint64_t adesc = adesc0 + (uint64_t)((st * WS2_A_STAGE) >> 4), bdesc = bdesc0 + (uint64_t)((i * WS2_W_TILE) >> 4);
+                    if (leader) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) mma_bf16(tmem_base + (uint32_t)(hf * 128), adesc + 2 * k, bdesc + 2 * k, IDESC, i > 0 || k != 0);
+                        mma_commit(empty + st);
+                    }
+                }
+                if (leader) mma_commit(acc_full + hf);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int e = warp - 2, q = warp & 3, chunk = e >> 2;
+        const int t = (int)threadIdx.x - 64;                              // 0 .. 383: finishing task id
+        for (int s = 0; s < nsteps; ++s) {
+            const typename Epi::Params& ep = steps[s];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (valid[hf] == 0) continue;
+                // this CTA finishes rows [ks * rq, ks * rq + rq) of the half, 12 tasks of 8 units per row
+                const int rq = (valid[hf] + KS - 1) / KS;
+                const int frow = ks * rq + t / 12, fu = n0 + 8 * (t % 12);
+                const bool ftask = t / 12 < rq && frow < valid[hf] && fu < n_limit;
+                const int fgr = ftask ? row_lo[hf] + frow : M;
+                typename Epi::Pre pre;
+                Epi::prefetch(ep, fgr, fu, pre);                          // gates, c, dc, dh_ext of the task: in flight while the MMAs run
+                mbar_wait(acc_full + hf, s & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(hf * 128 + 32 * chunk), v);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc_free + hf)) : "memory");
+                // ---- partial tile -> this K slice's slot of the scratch matrix [rg][hf][ks][64 rows][ldn]
+                float* slot = scratch + ((size_t)((rg * 2 + hf) * KS + ks) * 64) * ldn;
+                const int rih = 16 * q + lane;
+                if (lane < 16 && rih < valid[hf]) {
+                    float4* d = reinterpret_cast<float4*>(slot + (size_t)rih * ldn + n0 + 32 * chunk);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * WS2_EPI_WARPS) : "memory");
+                unsigned* pc = part_cnt + ((rg * 2 + hf) * ncol + blockIdx.x);
+                if (threadIdx.x == 64) {
+                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(pc), "r"(1u) : "memory");
+                    const unsigned target = (unsigned)(s + 1) * KS;
+                    long long t0 = clock64();
+                    for (unsigned spins = 1; ld_acquire_gpu(pc) < target; ++spins) {
+                        if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+                            printf("s2vt: ws2 bwd chain partial counter timed out (step %d half %d block %d,%d,%d)\n", s, hf, blockIdx.x, blockIdx.y, blockIdx.z);
+                            __trap();
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * WS2_EPI_WARPS) : "memory");      // the four partials are visible (acquire by thread 64 + barrier)
+                // ---- finish: sum the four slices in order, cell backward for 8 units of one row
+                if (ftask) {
+                    const float* base = scratch + ((size_t)((rg * 2 + hf) * KS) * 64 + frow) * ldn + fu;
+                    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k4 = 0; k4 < KS; ++k4) {
+                        const float4* pp = reinterpret_cast<const float4*>(base + (size_t)k4 * 64 * ldn);
+                        float4 x0, x1;
+                        asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "l"(pp));
+                        asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x1.x), "=f"(x1.y), "=f"(x1.z), "=f"(x1.w) : "l"(pp + 1));
+                        acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w; acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+                    }
+                    Epi::direct(ep, fgr, fu, acc, pre);
+                }
+                // publish the finished quarter to the row group
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * WS2_EPI_WARPS) : "memory");
+                if (threadIdx.x == 64) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(step_flag + (rg * 2 + hf)), "r"(1u) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    }
+}
+
+// floats of scratch the backward chain needs for M rows and N units
+inline size_t ws2_bwd_scratch_floats(int N) { return (size_t)3 * 2 * 4 * 64 * (size_t)((N + 95) / 96 * 96); }
+
+// B: [N units, K] K-major (K = 4 H gate columns).  flags: >= 8 + 6 * ceil(N / 96) unsigned.
+template <class Epi>
+inline cudaError_t launch_ws2_bwd_chain(MapCache& cache, cudaStream_t st, const bf16* A, int lda, int a_total_rows, int a_row0, int a_row_stride, const bf16* B,
+                                        int ldb, int M, int N, int K, const typename Epi::Params* steps_dev, int nsteps, unsigned* flags, int flags_cap,
+                                        float* scratch, bool pdl, uint32_t fmt) {
+    constexpr int RG = 3, KS = 4, BN = 96;
+    if (K % (BK * KS) != 0 || K / BK / KS > WS2_KB_MAX || M <= 128 || M > RG * 128 || !scratch) return cudaErrorLaunchOutOfResources;
+    const int rpg = ((M + RG - 1) / RG + 15) & ~15;
+    const int ncol = (N + BN - 1) / BN;
+    if (8 + 2 * RG * ncol > flags_cap) return cudaErrorLaunchOutOfResources;
+    if (cache.size() > 32768) cache.clear();
+    const CUtensorMap* ma = get_map(cache, A, a_total_rows, K, lda, rpg / 2);
+    const CUtensorMap* mb = get_map(cache, B, N, K, ldb, BN);
+    if (!ma || !mb) return cudaErrorInvalidValue;
+    auto kern = gemm_tc_ws2_bwd_chain_kernel<Epi>;
+    constexpr int SMEM = Ws2Cfg<BN>::SMEM, NT = Ws2Cfg<BN>::THREADS;
+    static int max_ctas = -1;
+    if (max_ctas < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, SMEM);
+        if (e != cudaSuccess) return e;
+        max_ctas = per_sm * sms;
+    }
+    static const bool debug = getenv("S2VT_DEBUG_CHAIN") != nullptr;
+    if (debug) fprintf(stderr, "s2vt ws2 bwd chain: rows=%d rpg=%d N=%d K=%d steps=%d grid=%d x %d x %d co-resident limit=%d\n", M, rpg, N, K, nsteps, ncol, RG, KS, max_ctas);
+    if (ncol * RG * KS > max_ctas) return cudaErrorLaunchOutOfResources;
+    cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)(8 + 2 * RG * ncol) * sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncol, RG, KS);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kern, *ma, *mb, K, M, rpg, N, a_row0, a_row_stride, steps_dev, nsteps, flags, scratch, fmt);
+}
+
 }  // namespace tc

@@ -442,6 +442,7 @@ struct StepChain {
     std::vector<typename Epi::Params> eps;
     const T* A; int lda, a_total_rows, a_row0, a_row_stride;   // step s reads rows [a_row0 + s * a_row_stride, + M) of A
     const T* B; int ldb, M, N, K;
+    float* ws2_scratch = nullptr; unsigned* ws2_flags = nullptr; int ws2_flags_cap = 0;   // backward chains > 128 rows: partial-tile scratch / counters (gemm_tcgen05_ws2.cuh)
 };
 template <typename T, class Epi>
 static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void* dev_params) {
@@ -462,7 +463,15 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
             constexpr bool bwd = IsCellBwd<Epi>::value;
             if constexpr (bwd) {
                 if ((c.K / tc::BK) % 4 != 0) e = cudaErrorLaunchOutOfResources;
-                else if (c.M > 128) e = tc::launch_chain<128, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt);
+                else if (c.M > 128) {
+                    // > 128 rows: weights-stationary K-slice slabs, two pipelined halves, partial tiles reduced through L2; fallback: the ring chain with its
+                    // 4-CTA DSMEM exchange (shape does not fit / no scratch / gemm_backend 13)
+                    e = cudaErrorLaunchOutOfResources;
+                    if (h->cfg.gemm_backend != 13 && h->cfg.gemm_backend != 10 && c.ws2_scratch)
+                        e = tc::launch_ws2_bwd_chain<Epi>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n,
+                                                          c.ws2_flags, c.ws2_flags_cap, c.ws2_scratch, true, fmt);
+                    if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<128, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }
+                }
                 else {
                     e = cudaErrorLaunchOutOfResources;
                     if (c.M <= 64 && h->cfg.gemm_backend != 10) e = tc::launch_chain<32, Epi, 4, true>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt);
@@ -791,6 +800,7 @@ struct Train {
     T *tA, *tB;   // transposed operand scratch (largest: [Vp, Mp])
     T *tA2, *tB2; // same for the LSTM1 chain on the side stream
     void *chain_f, *chain_b2, *chain_b1;   // per-step parameters of the persistent chains
+    float* ws2_scratch; unsigned* ws2_flags;   // partial tiles / counters of the weights-stationary BPTT chain (> 128 rows)
     F* emb;
 };
 
@@ -824,6 +834,8 @@ static void plan_train(const s2vt_handle* h, Arena& a, int B, int N, bool backwa
     p.dimgF = a.take<float>((size_t)Tv * B * Ep);
     p.dimgT_src = a.take<T>((size_t)Tv * B * Ep);
     p.emb = a.take<F>((size_t)Tc * N * Ep);
+    p.ws2_scratch = N > 128 ? a.take<float>(tc::ws2_bwd_scratch_floats(Hp)) : nullptr;
+    p.ws2_flags = a.take<unsigned>(256);
     size_t ta = (size_t)Hp * Mp2;                       // activations^T : at most [max(Hp,Ep,Dp), Mp2]
     if ((size_t)Dp * Mp1 > ta) ta = (size_t)Dp * Mp1;
     if ((size_t)Ep * MpD > ta) ta = (size_t)Ep * MpD;
@@ -938,15 +950,20 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     cudaStream_t s3 = (h->overlap & 4) ? h->side : st;   // stream of the LSTM1 backward chain
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
-    {   // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums
+    // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums.  overlap bit 6: not beside the LSTM2 BPTT chain (whose steps it slows from 12 to
+    // 15 us) but later on the caller's stream, among the LSTM2 weight gradients that run beside the LSTM1 chain.
+    const bool dwo_late = (h->overlap & 64) != 0;
+    auto dwo = [&](cudaStream_t sx) -> int {
         EpiGradStore::Params ep = {h->G_(h->iWo), V, H, V, 0, 1.f};
-        TRY((wgrad<T, F>(h, s2, p.out2d, Hp, Hp, p.dlogits, Vp, Vp, MD, ep, p.tA, p.tB, H)));
-        TRY(bias_grad<T>(h, s2, p.dlogits, Vp, Vp, MD, V, 0, h->G_(h->ibo)));
-    }
+        TRY((wgrad<T, F>(h, sx, p.out2d, Hp, Hp, p.dlogits, Vp, Vp, MD, ep, p.tA, p.tB, H)));
+        TRY(bias_grad<T>(h, sx, p.dlogits, Vp, Vp, MD, V, 0, h->G_(h->ibo)));
+        return 0;
+    };
+    if (!dwo_late) TRY(dwo(s2));
     CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));
     // Data-parallel hook: in the REINFORCE objective nothing touches these two gradients again (no weight decay, no accumulation
     // pass), so a caller may start their all-reduce now, under the BPTT chains (s2vt_grad_segment_ready).
-    h->wo_grad_early = mode == 0 && !accumulate && grad_scale == 1.f;
+    h->wo_grad_early = mode == 0 && !accumulate && grad_scale == 1.f && !dwo_late;
     if (h->wo_grad_early) CUDA_TRY(h, cudaEventRecord(h->ev_wo, s2));
     h->seg_ready = h->wo_grad_early ? 1u : 0u;
     // LSTM2 BPTT
@@ -955,6 +972,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         StepChain<T, EpiLstmBwd<T, F>> ch;    // step s of the chain is time t = T-2-s; its A operand is dG2 of time t+1
         ch.A = p.dG2; ch.lda = Gp; ch.a_total_rows = T_ * N; ch.a_row0 = (T_ - 1) * N; ch.a_row_stride = -N;
         ch.B = (const T*)h->W2h; ch.ldb = Gp; ch.M = N; ch.N = Hp; ch.K = Gp;
+        ch.ws2_scratch = p.ws2_scratch; ch.ws2_flags = p.ws2_flags; ch.ws2_flags_cap = 256;
         for (int t = T_ - 1; t >= 0; --t) {
             LstmBwdArgs b;
             memset(&b, 0, sizeof b);
@@ -1021,7 +1039,8 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         TRY((wgrad<T, F>(h, s3, p.f.Xc, Dp, Dp, p.dimgT_src, Ep, Ep, ME, e, p.tA2, p.tB2, D)));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_join, s3));
-    // ---- main stream meanwhile: embedding and LSTM2 weight gradients
+    // ---- main stream meanwhile: embedding and LSTM2 weight gradients (and, with overlap bit 6, the vocabulary-projection ones)
+    if (dwo_late) TRY(dwo(st));
     {   // word-embedding gradient
         typename EpiStore<T>::Params ee = {p.dEmb, nullptr, Ep, nullptr, MD, 0};
         TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2 + (size_t)Tv * N * Gp, Gp, h->W2e, Gp, MD, Ep, Gp, ee)));
