@@ -53,7 +53,8 @@ enum { S2VT_GEMM_AUTO = 0, S2VT_GEMM_MMA_SYNC = 1, S2VT_GEMM_TCGEN05 = 2,
        S2VT_GEMM_CHAIN_NOMC = 12,    /* weights-stationary chains without activation multicast */
        S2VT_GEMM_CHAIN_PLAIN = 13,   /* > 128-row forward chains on the plain ring kernel instead of the pipelined weights-stationary one */
        S2VT_GEMM_SINGLE_CTA = 14,    /* large batched GEMMs on single-CTA 128 x 256 tiles instead of cta_group::2 pairs (256 x 256) */
-       S2VT_GEMM_PAIR_ALL = 15 };    /* every large batched GEMM on pairs (default: only where the isolated timings say the pair wins) */
+       S2VT_GEMM_PAIR_ALL = 15,      /* every large batched GEMM on pairs (default: only where the isolated timings say the pair wins) */
+       S2VT_GEMM_CHAIN_WS2_BWD = 16 }; /* > 128-row BPTT chain on the weights-stationary pipelined kernel (partial tiles through L2) instead of the ring chain: measured slower */
 
 /* Model dimensions: the "Train Parameters" constants of reinforcement_multisampling_tf_s2vt.py:505-511
  * (dim_image, word_dim, lstm_dim, n_video_lstm_step, n_caption_lstm_step) and n_words = len(wordtoix) (:617). */
@@ -180,7 +181,8 @@ int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* 
 int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int64_t* offset, int64_t* count);
 /* tuning: which independent pieces use the library's internal side stream (bit 0: late half of s2vt_refresh, bit 1: the
  * vocabulary weight gradient, bit 2: the LSTM1 backward chain); default 7.  Bit 3 (debug) makes s2vt_beam_search use its un-fused
- * step -- materialised logits and separate top-k / bookkeeping / state-gather launches -- the checker of the fused one. */
+ * step -- materialised logits and separate top-k / bookkeeping / state-gather launches -- the checker of the fused one.  Bit 6 (64) moves the
+ * vocabulary weight gradient from beside the LSTM2 BPTT chain to after it (measured slower: 8.80 vs 8.63 ms per iteration). */
 int s2vt_set_overlap(s2vt_handle* h, int mask);
 /* debug / measurement: one GEMM of the given (padded) shape on scratch operands inside the bound workspace, through the engine's own
  * dispatch (tile shape, CTA pairs, gemm_backend) -- scripts/gemm_shapes.py times every shape of an iteration in isolation with it.

@@ -464,10 +464,12 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
             if constexpr (bwd) {
                 if ((c.K / tc::BK) % 4 != 0) e = cudaErrorLaunchOutOfResources;
                 else if (c.M > 128) {
-                    // > 128 rows: weights-stationary K-slice slabs, two pipelined halves, partial tiles reduced through L2; fallback: the ring chain with its
-                    // 4-CTA DSMEM exchange (shape does not fit / no scratch / gemm_backend 13)
+                    // > 128 rows: the ring chain with its 4-CTA DSMEM exchange; alternative: weights-stationary K-slice slabs, two pipelined halves, partial tiles
+                    // reduced through L2 (gemm_tcgen05_ws2.cuh).
                     e = cudaErrorLaunchOutOfResources;
-                    if (h->cfg.gemm_backend != 13 && h->cfg.gemm_backend != 10 && c.ws2_scratch)
+                    // Measured at the bench shape (round 2): 16.3 us per step against 15.3 us for the ring chain inside the iteration -- the L2 round trip of the
+                    // partial tiles and the 132-CTA grid (which leaves the concurrent dW_o GEMM 16 SMs) cost more than the resident weights save: opt-in, gemm_backend 16.
+                    if (h->cfg.gemm_backend == 16 && c.ws2_scratch)
                         e = tc::launch_ws2_bwd_chain<Epi>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n,
                                                           c.ws2_flags, c.ws2_flags_cap, c.ws2_scratch, true, fmt);
                     if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<128, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }

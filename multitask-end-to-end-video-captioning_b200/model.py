@@ -44,7 +44,7 @@ class Video_Caption_Generator(object):
         self.n_attributes = n_attributes
         cfg = _lib.S2vtConfig(dim_image, word_dim, lstm_dim, n_words, n_video_lstm_step, n_caption_lstm_step, n_attributes,
                               {'bf16': _lib.PREC_BF16, 'fp32': _lib.PREC_FP32}[precision],
-                              {'auto': _lib.GEMM_AUTO, 'mma_sync': _lib.GEMM_MMA_SYNC, 'tcgen05': _lib.GEMM_TCGEN05, 'tcgen05_n128': 3, 'tcgen05_mc2x2': 4, 'step_mc8': 5, 'step_mc4': 6, 'step_n64': 7, 'wgrad_transposed': 8, 'per_step': 9, 'chain_ring': 10, 'chain_mc4': 11, 'chain_nomc': 12, 'chain_plain': 13, 'single_cta': 14, 'pair_all': 15}[gemm_backend],
+                              {'auto': _lib.GEMM_AUTO, 'mma_sync': _lib.GEMM_MMA_SYNC, 'tcgen05': _lib.GEMM_TCGEN05, 'tcgen05_n128': 3, 'tcgen05_mc2x2': 4, 'step_mc8': 5, 'step_mc4': 6, 'step_n64': 7, 'wgrad_transposed': 8, 'per_step': 9, 'chain_ring': 10, 'chain_mc4': 11, 'chain_nomc': 12, 'chain_plain': 13, 'single_cta': 14, 'pair_all': 15, 'chain_ws2_bwd': 16}[gemm_backend],
                               float(dropout_rate))
         self.precision = precision
         h = C.c_void_p()

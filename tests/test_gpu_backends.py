@@ -88,6 +88,11 @@ def test_pipelined_weights_stationary_chain_equals_plain_chain(b, k, tv):
     rel = float((a['grads'] - p['grads']).abs().max() / p['grads'].abs().max())
     assert rel < 1e-5, rel
     assert abs(a['loss'] - p['loss']) < 1e-6 * max(1.0, abs(p['loss']))
+    # the opt-in weights-stationary BPTT chain (partial tiles summed through L2 in K-slice order) gives the same gradients
+    w = _run('chain_ws2_bwd', dims, tv, 35, b, k)
+    assert torch.equal(w['logits'], p['logits'])
+    rel = float((w['grads'] - p['grads']).abs().max() / p['grads'].abs().max())
+    assert rel < 1e-5, rel
 
 
 def test_cta_pair_gemms_equal_single_cta_gemms():
