@@ -80,3 +80,14 @@ class FeatureFile(object):
         """{vid: float32 [T_v, D]} of the whole file (what get_video_feature_caption_pair returns), parsed in one call."""
         all_ = self.read(np.arange(self.n_videos, dtype=np.int64))
         return {v: all_[i] for i, v in enumerate(self.ids)}
+
+    def cache_fp16(self, pin=True):
+        """The whole file as ONE float16 tensor [n_videos, T_v, D] in (pinned) host memory -- the feed cache for `trainer.FeaturePipe`: the tensor-core
+        mode consumes the frames in fp16, so batches gathered from this cache give bit-identical results at half the host -> device traffic.
+        Values beyond fp16's range (|x| > 65504) would become inf: pooled CNN features are O(1); checked here."""
+        import torch
+        all_ = self.read(np.arange(self.n_videos, dtype=np.int64))
+        if not np.isfinite(all_).all() or np.abs(all_).max() > 65504.0:
+            raise ValueError('features outside the fp16 range: keep the float32 feed')
+        t = torch.from_numpy(all_.astype(np.float16))
+        return t.pin_memory() if pin and torch.cuda.is_available() else t

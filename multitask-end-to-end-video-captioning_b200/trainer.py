@@ -91,12 +91,17 @@ class FeaturePipe(object):
         v, vi, slot = pipe.get()                  # device tensors of the oldest staged step, ordered after its copy
         ... launch the step ...
         pipe.release(slot)                        # the step's kernels have been enqueued; the slot may be refilled
+
+    Host features may be float32 (the reference feed) or float16 (`ingest.FeatureFile.cache_fp16`): the tensor-core mode rounds the frames
+    to fp16 before its first product anyway, so an fp16 host cache feeds bit-identical numbers with half the host -> device bytes (which
+    matters when eight ranks share one host's memory and PCIe bandwidth).  The device-side fp16 -> fp32 widening runs on the copy stream.
     """
 
     def __init__(self, device, batch, n_frames, dim_image, depth=2):
         self.device = torch.device(device)
         self.bufs = [(torch.empty(batch, n_frames, dim_image, dtype=torch.float32, device=self.device),
                       torch.empty(batch, dtype=torch.int32, device=self.device)) for _ in range(depth)]
+        self.half = [None] * depth                  # fp16 landing buffers, allocated on first use
         self.stream = torch.cuda.Stream(device=self.device)
         self.ready = [torch.cuda.Event() for _ in range(depth)]
         self.free = [None] * depth
@@ -107,13 +112,19 @@ class FeaturePipe(object):
         i = self.n_put % len(self.bufs)
         if self.n_put - self.n_get >= len(self.bufs):
             raise RuntimeError('FeaturePipe: every slot holds a staged step; get() one first')
-        f = features if torch.is_tensor(features) else torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+        f = features if torch.is_tensor(features) else torch.from_numpy(np.ascontiguousarray(features, dtype=(np.float16 if getattr(features, 'dtype', None) == np.float16 else np.float32)))
         vi = video_index if torch.is_tensor(video_index) else torch.from_numpy(np.ascontiguousarray(video_index, dtype=np.int32))
         v, x = self.bufs[i]
         if self.free[i] is not None:
             self.stream.wait_event(self.free[i])       # kernels of the step that last read this slot
         with torch.cuda.stream(self.stream):
-            v[:f.shape[0]].copy_(f, non_blocking=True)
+            if f.dtype == torch.float16:
+                if self.half[i] is None:
+                    self.half[i] = torch.empty_like(v, dtype=torch.float16)
+                self.half[i][:f.shape[0]].copy_(f, non_blocking=True)
+                v[:f.shape[0]].copy_(self.half[i][:f.shape[0]])          # widen on the device
+            else:
+                v[:f.shape[0]].copy_(f, non_blocking=True)
             x[:vi.shape[0]].copy_(vi, non_blocking=True)
             self.ready[i].record(self.stream)
         self.rows[i] = f.shape[0]

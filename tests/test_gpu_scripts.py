@@ -163,3 +163,24 @@ def test_feature_pipe_stages_batches_ahead():
     pipe.put(short, torch.zeros(2, dtype=torch.int32))
     v, vi, slot = pipe.get()
     assert tuple(v.shape) == (2, 3, 8) and tuple(vi.shape) == (2,)
+
+
+def test_feature_pipe_fp16_host_cache_feeds_identical_numbers():
+    """trainer.FeaturePipe staging from an fp16 host cache: in the tensor-core mode the frames are rounded to fp16 before the first product anyway, so the
+    rollout is bit-identical to the float32 feed -- at half the host -> device bytes."""
+    import s2vt_b200
+    B, Tv, D = 8, 4, 96
+    m = s2vt_b200.Video_Caption_Generator(dim_image=D, n_words=120, word_dim=32, lstm_dim=48, batch_size=B, n_video_lstm_step=Tv, n_caption_lstm_step=6,
+                                          precision='bf16', max_videos=B, max_rows=2 * B, seed=3)
+    video = torch.from_numpy(M.synthetic_features(B, Tv, D))
+    pipe = s2vt_b200.trainer.FeaturePipe(m.device, B, Tv, D)
+    idx = torch.arange(B, dtype=torch.int32)
+    out = []
+    for feed in (video.pin_memory(), video.to(torch.float16).pin_memory()):
+        pipe.put(feed, idx)
+        v, vi, slot = pipe.get()
+        samp, greedy = m.rollout(v, 2, seed=5)
+        pipe.release(slot)
+        out.append((samp.cpu(), greedy.cpu(), v.clone().cpu()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert torch.equal(out[1][2], video.to(torch.float16).to(torch.float32))
