@@ -743,9 +743,7 @@ static int rollout_impl(s2vt_handle* h, cudaStream_t st, const float* video, int
         memset(&ep, 0, sizeof ep);
         ep.M = R; ep.Hp = Hp; ep.bias = h->b2_p; ep.add0 = r.G2x + (size_t)t * B * Gp; ep.add0_mod = B;
         ep.add1 = reinterpret_cast<const F*>(h->Etab); ep.tok = r.tok[0];                     // step 0: <bos>; later steps resolve the previous step's candidates
-        static const int dbg_no_etab = getenv("S2VT_DEBUG_NO_ETAB") ? atoi(getenv("S2VT_DEBUG_NO_ETAB")) : 0;   // timing experiments only (wrong words)
-        if (dbg_no_etab & 1) ep.add1 = nullptr;
-        if (i > 0 && !(dbg_no_etab & 2)) { ep.pick_val = r.pick_val; ep.pick_idx = r.pick_idx; ep.pick_ld = r.pick_ld; ep.pick_nt = nt; ep.ids_out = r.ids; ep.ids_ld = Tc; ep.ids_col = i - 1; }
+        if (i > 0) { ep.pick_val = r.pick_val; ep.pick_idx = r.pick_idx; ep.pick_ld = r.pick_ld; ep.pick_nt = nt; ep.ids_out = r.ids; ep.ids_ld = Tc; ep.ids_col = i - 1; }
         ep.c_prev = r.c2r[i & 1]; ep.c_out = r.c2r[(i + 1) & 1]; ep.h_out = r.h2r[(i + 1) & 1]; ep.keep = 1.f;
         // :332-336 logit_words -> log_softmax -> tf.multinomial / :386-387 argmax, fused: the logits stay on chip
         typename EpiLogitsPick<T>::Params el = {R, h->V, h->bo_p, K * B, seed, (uint32_t)i, row_base, r.pick_val, r.pick_idx, r.pick_ld};
