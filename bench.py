@@ -607,6 +607,17 @@ def run_b200(args):
     prof = model.profile_read()
     model.profile(False)
     loss = float(trainer.step(feats_dev, vidx_dev)[1].item())
+    # every batched-GEMM shape of the iteration timed ALONE (no side-stream kernels beside it) through the engine's own dispatch
+    iso = None
+    if world == 1:
+        sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+        import gemm_shapes
+        t_iso = gemm_shapes.time_shapes(model, torch, reps=10)
+        iso_rows = [{'product': k[0], 'M': k[1], 'N': k[2], 'K': k[3], 'form': 'X^T.Y' if k[4] else 'A.B^T', 'us': us,
+                     'tflops': 2.0 * k[1] * k[2] * k[3] / (us * 1e-6) / 1e12} for k, us in t_iso.items()]
+        twice = lambda r: 2 if r['product'].startswith('dW2[out1]') else 1      # the h2 rows of dW2 have the same shape
+        iso = {'shapes': iso_rows, 'us_total': sum(r['us'] * twice(r) for r in iso_rows),
+               'tflop_total': sum(2.0 * r['M'] * r['N'] * r['K'] * twice(r) for r in iso_rows) / 1e12}
     # secondary BASELINE metric: beam-5 decode captions/s (e2e_beam_search.py semantics, length normalisation 1), batch = B videos
     beam = {}
     if world == 1:
@@ -764,7 +775,14 @@ def run_b200(args):
            'roofline_batched_gemm': {'kernel': 'tc::gemm_tc_kernel<256, EpiStore|EpiGradStore> (128x256 tcgen05 tiles: projections, vocab logits, weight gradients)',
                                      'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach_tf / peak_tf if peak_tf else None,
                                      'peak_source': peak_src, 'launches_per_step': bn / args.steps, 'ms_per_step': bms / args.steps,
-                                     'algorithmic_gflop_per_step': bfl / args.steps / 1e9}}
+                                     'algorithmic_gflop_per_step': bfl / args.steps / 1e9,
+                                     'note': 'measured INSIDE the step: side-stream kernels (persistent chains) share the GPU with several of these GEMMs; '
+                                             'roofline_batched_gemm_isolated times every shape alone'}}
+    if iso:
+        ach_iso = iso['tflop_total'] / (iso['us_total'] * 1e-6)
+        out['roofline_batched_gemm_isolated'] = {'bound': 'tensor', 'achieved': ach_iso, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach_iso / peak_tf if peak_tf else None,
+                                                 'peak_source': peak_src, 'us_total': iso['us_total'], 'padded_tflop_total': iso['tflop_total'], 'shapes': iso['shapes'],
+                                                 'how': 's2vt_debug_gemm: each padded shape of the iteration alone on the GPU, 10 repetitions, CUDA events'}
     if world == 1 and not args.no_cpu_baseline:
         use_all_host_threads()
         OracleIteration(args.samples, 5, 2, vocab, by, order, bias).step()        # page in BLAS / the corpus on a tiny case

@@ -1223,6 +1223,7 @@ extern "C" int s2vt_debug_gemm(s2vt_handle* h, int M, int N, int K, int mn_major
     if (h->cfg.precision != S2VT_PREC_BF16) return h->fail(S2VT_EINVAL, "debug_gemm: bf16 mode only");
     if (M <= 0 || N % 128 != 0 || (!mn_major && K % 128 != 0) || (mn_major && M % 128 != 0)) return h->fail(S2VT_EINVAL, "debug_gemm: N (and K, or M for mn_major) must be multiples of 128");
     cudaStream_t st = (cudaStream_t)st_;
+    h->front_valid = false;      // the scratch operands overwrite the workspace (incl. a cached LSTM1 pass)
     Arena a(h->ws, h->ws_bytes);
     bf16* A = a.take<bf16>((size_t)(mn_major ? K : M) * (mn_major ? M : K));
     bf16* B = a.take<bf16>((size_t)(mn_major ? K : N) * (mn_major ? N : K));

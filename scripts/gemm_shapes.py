@@ -10,7 +10,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge
-ge.build()
+if __name__ == '__main__':
+    ge.build()
 import s2vt_b200
 
 # (name, M, N, K, mn_major, fp32_out) -- padded sizes as the engine launches them
@@ -32,13 +33,10 @@ SHAPES = [
     ('dW1[x] = img^T.dG1', 512, 4096, 5120, 1, 1),
     ('dWe = X^T.dimg', 1536, 512, 5120, 1, 1),
 ]
-backends = sys.argv[1:] or ['auto', 'single_cta']
-peaks = json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')) else {}
-peak = peaks.get('bf16_tflops', 1681.8)
-rows = {}
-for be in backends:
-    m = s2vt_b200.Video_Caption_Generator(batch_size=64, n_video_lstm_step=80, max_videos=64, max_rows=320, gemm_backend=be)
+def time_shapes(m, torch, reps=20):
+    """{(name, M, N, K, mn): us} for every shape, each alone on the GPU through the handle's own dispatch."""
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = {}
     for name, M, N, K, mn, f32 in SHAPES:
         run = lambda: m._check(m.lib.s2vt_debug_gemm(m.h, M, N, K, mn, f32, st))
         for _ in range(3):
@@ -46,21 +44,37 @@ for be in backends:
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(20):
+        for _ in range(reps):
             run()
         e1.record(); torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / 20
-        rows.setdefault((name, M, N, K, mn), {})[be] = us
-    del m
-    torch.cuda.empty_cache()
-print('| product | M | N | K | form | ' + ' | '.join('%s us | TF/s | of %.0f' % (b, peak) for b in backends) + ' |')
-print('|---|---:|---:|---:|---|' + '---:|---:|---:|' * len(backends))
-out = []
-for (name, M, N, K, mn), r in rows.items():
-    cells = []
-    for b in backends:
-        tf = 2.0 * M * N * K / (r[b] * 1e-6) / 1e12
-        cells.append('%.1f | %.0f | %.2f' % (r[b], tf, tf / peak))
-    print('| %s | %d | %d | %d | %s | %s |' % (name, M, N, K, 'X^T.Y' if mn else 'A.B^T', ' | '.join(cells)))
-    out.append(dict(name=name, M=M, N=N, K=K, mn_major=mn, us=r))
-json.dump(dict(peak_tflops=peak, shapes=out), open('gpurun_out/gemm_shapes.json', 'w'))
+        out[(name, M, N, K, mn)] = e0.elapsed_time(e1) * 1e3 / reps
+    return out
+
+
+def main():
+    backends = sys.argv[1:] or ['auto', 'single_cta']
+    pk = os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')
+    peaks = json.load(open(pk)) if os.path.exists(pk) else {}
+    peak = peaks.get('bf16_tflops', 1681.8)
+    rows = {}
+    for be in backends:
+        m = s2vt_b200.Video_Caption_Generator(batch_size=64, n_video_lstm_step=80, max_videos=64, max_rows=320, gemm_backend=be)
+        for k, us in time_shapes(m, torch).items():
+            rows.setdefault(k, {})[be] = us
+        del m
+        torch.cuda.empty_cache()
+    print('| product | M | N | K | form | ' + ' | '.join('%s us | TF/s | of %.0f' % (b, peak) for b in backends) + ' |')
+    print('|---|---:|---:|---:|---|' + '---:|---:|---:|' * len(backends))
+    out = []
+    for (name, M, N, K, mn), r in rows.items():
+        cells = []
+        for b in backends:
+            tf = 2.0 * M * N * K / (r[b] * 1e-6) / 1e12
+            cells.append('%.1f | %.0f | %.2f' % (r[b], tf, tf / peak))
+        print('| %s | %d | %d | %d | %s | %s |' % (name, M, N, K, 'X^T.Y' if mn else 'A.B^T', ' | '.join(cells)))
+        out.append(dict(name=name, M=M, N=N, K=K, mn_major=mn, us=r))
+    json.dump(dict(peak_tflops=peak, shapes=out), open('gpurun_out/gemm_shapes.json', 'w'))
+
+
+if __name__ == '__main__':
+    main()
