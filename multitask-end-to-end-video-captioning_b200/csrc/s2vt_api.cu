@@ -16,6 +16,7 @@
 #include "gemm_tcgen05_chain.cuh"
 #include "gemm_tcgen05_ws2.cuh"
 #include "gemm_tcgen05_pair.cuh"
+#include "gemm_tcgen05_persist.cuh"
 #include "kernels.cuh"
 
 template <typename T, typename F>
@@ -344,6 +345,14 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
                     if ((h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05 || h->cfg.gemm_backend == 15) && N % 256 == 0 && M >= 1024 &&
                         (pair_wins || h->cfg.gemm_backend == 15)) {
                         CUDA_TRY(h, (tc::launch_pair<Epi>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep, false, fmt)));
+                        paired = true;
+                    }
+                }
+                // wide short-K products with fp32 output (G1x, G2x, logits): persistent tile loop, the stores of tile i under the mainloop of tile i+1
+                if constexpr (std::is_same<Epi, EpiStore<T>>::value) {
+                    if (!paired && (h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05 || h->cfg.gemm_backend == 15) && N % 256 == 0 &&
+                        (long long)((M + 127) / 128) * (N / 256) >= 296 && ep.outF && !ep.outT && !ep.accumulate && ep.M == M) {
+                        CUDA_TRY(h, (tc::launch_persist(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep.outF, ep.ldo, ep.bias, false, fmt)));
                         paired = true;
                     }
                 }
