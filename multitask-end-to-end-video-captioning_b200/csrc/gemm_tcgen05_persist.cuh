@@ -1,4 +1,4 @@
-// Persistent tcgen05 GEMM for the wide short-K products with fp32 output (G1x, G2x, logits):  C[M,N] = A[M,K] . B[N,K]^T + bias.
+// Persistent tcgen05 GEMM for the wide products with plain stores (G1x, G2x, logits, Etab, dout1; fp32 and / or 16-bit output):  C[M,N] = A[M,K] . B[N,K]^T + bias.
 //
 // With K = 512 .. 1024 a 128 x 256 tile is 8 .. 16 K-blocks of mainloop followed by 128 KB of fp32 stores; in gemm_tc_kernel the two
 // run one after the other in every CTA (the staged epilogue re-uses the pipeline's shared memory), and at 1 CTA per SM nothing else
@@ -18,8 +18,9 @@ constexpr int PS_STAGE_BYTES = BM * BK * 2 + PS_BN * BK * 2;               // 48
 constexpr int PS_PATCH = 32 * 33 * 4;                                      // per-warp transpose patch
 constexpr int PS_SMEM = PS_STAGES * PS_STAGE_BYTES + PS_EPI_WARPS * PS_PATCH + 256 + 1024;
 
+template <typename T16>
 __global__ void __launch_bounds__(PS_THREADS) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                                                                     int M, int N, int K, uint32_t fmt, float* __restrict__ out, int ldo,
+                                                                     int M, int N, int K, uint32_t fmt, float* __restrict__ out, T16* __restrict__ out16, int ldo,
                                                                      const float* __restrict__ bias) {
     const uint32_t IDESC = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PS_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24)) & ~fmt;
     extern __shared__ unsigned char smem_raw[];
@@ -116,7 +117,11 @@ __global__ void __launch_bounds__(PS_THREADS) gemm_tc_persist_kernel(const __gri
 #pragma unroll 4
                 for (int r = 0; r < 32; ++r) {
                     const int gr = rbase + r;
-                    if (gr < M) out[(size_t)gr * ldo + gc + lane] = patch[r * 33 + lane] + bv;      // 32 lanes: one 128-byte line
+                    if (gr < M) {
+                        const float x = patch[r * 33 + lane] + bv;
+                        if (out) out[(size_t)gr * ldo + gc + lane] = x;                             // 32 lanes: one 128-byte line
+                        if (out16) out16[(size_t)gr * ldo + gc + lane] = from_f32<T16>(x);          // ... or one 64-byte half line
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -131,8 +136,9 @@ __global__ void __launch_bounds__(PS_THREADS) gemm_tc_persist_kernel(const __gri
     }
 }
 
-// fp32 output (ldo floats per row), optional bias[N]; N % 256 == 0, K % 64 == 0.
-inline cudaError_t launch_persist(MapCache& cache, cudaStream_t st, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, float* out, int ldo,
+// fp32 and / or 16-bit output (ldo elements per row), optional bias[N]; N % 256 == 0, K % 64 == 0.
+template <typename T16>
+inline cudaError_t launch_persist(MapCache& cache, cudaStream_t st, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, float* out, T16* out16, int ldo,
                                   const float* bias, bool pdl, uint32_t fmt) {
     if (M <= 0) return cudaSuccess;
     if (cache.size() > 32768) cache.clear();
@@ -141,7 +147,7 @@ inline cudaError_t launch_persist(MapCache& cache, cudaStream_t st, const bf16* 
     if (!ma || !mb) return cudaErrorInvalidValue;
     static int sms = 0;
     if (!sms) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_persist_kernel<T16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM);
         if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -162,7 +168,7 @@ inline cudaError_t launch_persist(MapCache& cache, cudaStream_t st, const bf16* 
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_persist_kernel, *ma, *mb, M, N, K, fmt, out, ldo, bias);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_persist_kernel<T16>, *ma, *mb, M, N, K, fmt, out, out16, ldo, bias);
 }
 
 }  // namespace tc

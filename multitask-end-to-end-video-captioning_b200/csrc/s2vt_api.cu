@@ -351,8 +351,8 @@ static int gemm(s2vt_handle* h, cudaStream_t st, const void* A, int lda, const v
                 // wide short-K products with fp32 output (G1x, G2x, logits): persistent tile loop, the stores of tile i under the mainloop of tile i+1
                 if constexpr (std::is_same<Epi, EpiStore<T>>::value) {
                     if (!paired && (h->cfg.gemm_backend == S2VT_GEMM_AUTO || h->cfg.gemm_backend == S2VT_GEMM_TCGEN05 || h->cfg.gemm_backend == 15) && N % 256 == 0 &&
-                        (long long)((M + 127) / 128) * (N / 256) >= 296 && ep.outF && !ep.outT && !ep.accumulate && ep.M == M) {
-                        CUDA_TRY(h, (tc::launch_persist(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep.outF, ep.ldo, ep.bias, false, fmt)));
+                        (long long)((M + 127) / 128) * (N / 256) >= 296 && (ep.outF || ep.outT) && !ep.accumulate && ep.M == M) {
+                        CUDA_TRY(h, (tc::launch_persist<T>(mc, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, ep.outF, ep.outT, ep.ldo, ep.bias, false, fmt)));
                         paired = true;
                     }
                 }
