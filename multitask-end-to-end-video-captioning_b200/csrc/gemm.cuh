@@ -408,24 +408,34 @@ struct EpiGradStore {
     };
     template <class Cfg>
     __device__ static void apply(const Params& p, const float* Cs, int m0, int n0) {
-        if (p.gate_h > 0) {
-            // thread -> (row, gate, unit): consecutive threads take consecutive units of one gate (coalesced stores)
-            constexpr int UN = Cfg::BN / 4;
-            for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::NTHREADS) {
-                int r = idx / Cfg::BN, rem = idx % Cfg::BN, g = rem / UN, ul = rem % UN;
-                int gr = m0 + r, u = n0 / 4 + ul;
-                if (gr >= p.nrows || u >= p.gate_h) continue;
-                float* dst = p.grad + (size_t)gr * p.ldg + (size_t)g * p.gate_h + u;
-                const float v = p.scale * Cs[r * Cfg::LDC + ul * 4 + g];
-                if (p.atomic) atomicAdd(dst, v); else *dst += v;
+        // read-modify-write of 128 x BN gradient elements per CTA: 8 independent elements per thread and round, all loads of a round issued before the first
+        // store (one element at a time the loop was a chain of dependent L2 round trips: ~85 us per launch, more than the mainloop of most weight gradients)
+        constexpr int PER = 8, UN = Cfg::BN / 4;
+        for (int base = threadIdx.x; base < Cfg::BM * Cfg::BN; base += Cfg::NTHREADS * PER) {
+            float* dst[PER]; float v[PER], old[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int idx = base + i * Cfg::NTHREADS;
+                dst[i] = nullptr;
+                if (idx < Cfg::BM * Cfg::BN) {
+                    const int r = idx / Cfg::BN, rem = idx % Cfg::BN, gr = m0 + r;
+                    if (p.gate_h > 0) {      // thread -> (row, gate, unit): consecutive threads take consecutive units of one gate (coalesced stores)
+                        const int g = rem / UN, ul = rem % UN, u = n0 / 4 + ul;
+                        if (gr < p.nrows && u < p.gate_h) { dst[i] = p.grad + (size_t)gr * p.ldg + (size_t)g * p.gate_h + u; v[i] = p.scale * Cs[r * Cfg::LDC + ul * 4 + g]; }
+                    } else {
+                        const int gc = n0 + rem;
+                        if (gr < p.nrows && gc < p.ncols) { dst[i] = p.grad + (size_t)gr * p.ldg + gc; v[i] = p.scale * Cs[r * Cfg::LDC + rem]; }
+                    }
+                }
             }
-        } else {
-            for (int idx = threadIdx.x; idx < Cfg::BM * Cfg::BN; idx += Cfg::NTHREADS) {
-                int r = idx / Cfg::BN, c = idx % Cfg::BN, gr = m0 + r, gc = n0 + c;
-                if (gr >= p.nrows || gc >= p.ncols) continue;
-                float* dst = p.grad + (size_t)gr * p.ldg + gc;
-                const float v = p.scale * Cs[r * Cfg::LDC + c];
-                if (p.atomic) atomicAdd(dst, v); else *dst += v;
+            if (p.atomic) {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) if (dst[i]) atomicAdd(dst[i], v[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) if (dst[i]) old[i] = *dst[i];
+#pragma unroll
+                for (int i = 0; i < PER; ++i) if (dst[i]) *dst[i] = old[i] + v[i];
             }
         }
     }
