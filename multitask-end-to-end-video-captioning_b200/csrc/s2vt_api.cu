@@ -437,7 +437,7 @@ static int wgrad(s2vt_handle* h, cudaStream_t st, const F* X, int ldx, int Mf, c
 }
 template <typename T>
 static int bias_grad(s2vt_handle* h, cudaStream_t st, const T* Y, int ldy, int Cpad, int R, int ncols, int gate_h, float* grad) {
-    dim3 grid(Cpad / 64, R >= 4096 ? 16 : (R >= 256 ? 4 : 1)), block(32, 8);
+    dim3 grid(Cpad / 64, R >= 16384 ? 32 : (R >= 4096 ? 16 : (R >= 256 ? 4 : 1))), block(32, 8);
     colsum_grad_kernel<T><<<grid, block, 0, st>>>(Y, ldy, R, ncols, gate_h, grad);
     KCHECK(h);
     return 0;
