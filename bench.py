@@ -34,8 +34,8 @@ DIMS = dict(D=1536, E=500, H=1000, V=9972)
 METRIC = 'reinforce_train_videos_per_s'
 # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the persistent chain kernels at the bench configuration, keyed by
 # (rows, N, K) (profiles/r2_chain_ncu_full.md; the 64-row forward figure is the 80-step LSTM2 encoder chain)
-STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = {(320, 1024, 4096): 788933120, (320, 4096, 1024): 1149113600,
-                                     (64, 4096, 1024): 98099456, (64, 1024, 4096): 166935040}
+STEP_KERNEL_DRAM_BYTES_PER_LAUNCH = {(320, 1024, 4096): 791533056, (320, 4096, 1024): 1147060992,
+                                     (64, 4096, 1024): 98122496, (64, 1024, 4096): 166504960}
 
 def parse():
     ap = argparse.ArgumentParser()
