@@ -180,7 +180,9 @@ int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* 
  * objectives add weight decay or a second pass) or the segment was already handed out. */
 int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int64_t* offset, int64_t* count);
 /* tuning: which independent pieces use the library's internal side stream (bit 0: late half of s2vt_refresh, bit 1: the
- * vocabulary weight gradient, bit 2: the LSTM1 backward chain); default 7.  Bit 3 (debug) makes s2vt_beam_search use its un-fused
+ * vocabulary weight gradient, bit 2: the LSTM1 backward chain, bit 7 (128): the part of dout1 and of the two large LSTM2 weight gradients that
+ * belongs to the time steps the LSTM2 BPTT chain finishes first runs beside the rest of that chain, behind a watcher of its grid-barrier counter);
+ * default 135.  Bit 3 (debug) makes s2vt_beam_search use its un-fused
  * step -- materialised logits and separate top-k / bookkeeping / state-gather launches -- the checker of the fused one.  Bit 6 (64) moves the
  * vocabulary weight gradient from beside the LSTM2 BPTT chain to after it (measured slower: 8.80 vs 8.63 ms per iteration). */
 int s2vt_set_overlap(s2vt_handle* h, int mask);

@@ -65,10 +65,11 @@ struct s2vt_handle {
     // internal side stream for the LSTM1 backward chain (fork/join inside one call; invisible to the caller)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_refresh = nullptr, ev_wo = nullptr;
     bool wo_grad_early = false;           // the last backward recorded ev_wo when d embed_word_W / d embed_word_b became final (s2vt_grad_segment_ready)
+    cudaEvent_t ev_gate = nullptr;        // the gated side-stream part of dout1 (rows the LSTM2 BPTT chain finished first) is complete
     cudaEvent_t ev_seg[2] = {nullptr, nullptr};   // ... and these when d Wemb (segment 1) / d LSTM2 weights + biases (segment 2) became final
     unsigned seg_ready = 0;               // bit i: segment i of the last backward may be handed out
     bool copies_zeroed = false;
-    int overlap = 7;                      // bit 0: late refresh, bit 1: dWo, bit 2: LSTM1 backward chain run on the side stream             // tc::MapCache (TMA tensor maps keyed by pointer / shape)
+    int overlap = 135;                    // bit 0: late refresh, bit 1: dWo, bit 2: LSTM1 backward chain run on the side stream; bit 7: gated consumption of dG2 under the LSTM2 BPTT chain           // tc::MapCache (TMA tensor maps keyed by pointer / shape)
     // variable indices
     int iWemb, iWe, ibe, iWo, ibo, iW1, ib1, iW2, ib2, iAW, iAb;
     mutable std::string err;

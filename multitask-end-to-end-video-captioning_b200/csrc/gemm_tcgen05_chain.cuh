@@ -32,6 +32,20 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     return v;
 }
 
+// Watcher for work that consumes a chain's output WHILE the chain runs (another stream): returns once the chain's grid-barrier counter has reached
+// `target` = steps * CTAs, i.e. every CTA has released its stores of that many steps (the acquire here + the kernel boundary after this kernel order the
+// consumer's reads, TMA included, behind them).  One warp, one polling lane; a 20 s watchdog traps instead of hanging (the watcher may start
+// well before the chain does).
+__global__ void chain_progress_wait_kernel(const unsigned* __restrict__ gbar, unsigned target) {
+    if (threadIdx.x == 0) {
+        long long t0 = clock64();
+        for (unsigned spins = 1; ld_acquire_gpu(gbar) < target; ++spins) {
+            __nanosleep(200);
+            if ((spins & 255u) == 0 && clock64() - t0 > 40000000000LL) { printf("s2vt: chain progress watcher timed out (target %u, seen %u)\n", target, ld_acquire_gpu(gbar)); __trap(); }
+        }
+    }
+}
+
 // WS (weights stationary, a_rows <= 64 and K/KS <= 16 K-blocks): this CTA's weight slab (BN x K/KS, <= 64 KB) is fetched once
 // and stays in shared memory for the whole chain; every A K-block of a step has its own stage (no ring, no `empty`
 // barriers: the end-of-step barrier frees all stages), so all loads of a step are in flight at once.

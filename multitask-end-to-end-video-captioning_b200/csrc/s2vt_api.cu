@@ -177,7 +177,7 @@ extern "C" int s2vt_set_reuse_frontend(s2vt_handle* h, int enable) {
     return 0;
 }
 extern "C" void s2vt_destroy(s2vt_handle* h) {
-    if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_refresh); cudaEventDestroy(h->ev_wo); cudaEventDestroy(h->ev_seg[0]); cudaEventDestroy(h->ev_seg[1]); }
+    if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_refresh); cudaEventDestroy(h->ev_wo); cudaEventDestroy(h->ev_seg[0]); cudaEventDestroy(h->ev_seg[1]); cudaEventDestroy(h->ev_gate); }
     if (h && h->tc_cache) delete static_cast<tc::MapCache*>(h->tc_cache);
     delete h;
 }
@@ -452,6 +452,7 @@ struct StepChain {
     const T* A; int lda, a_total_rows, a_row0, a_row_stride;   // step s reads rows [a_row0 + s * a_row_stride, + M) of A
     const T* B; int ldb, M, N, K;
     float* ws2_scratch = nullptr; unsigned* ws2_flags = nullptr; int ws2_flags_cap = 0;   // backward chains > 128 rows: partial-tile scratch / counters (gemm_tcgen05_ws2.cuh)
+    int gate_ncta = 0;    // out: CTAs of the persistent launch when its progress can be watched on h->gbar (count >= s * gate_ncta <=> steps 0..s-1 are complete), else 0
 };
 template <typename T, class Epi>
 static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void* dev_params) {
@@ -481,7 +482,11 @@ static int run_chain(s2vt_handle* h, cudaStream_t st, StepChain<T, Epi>& c, void
                     if (h->cfg.gemm_backend == 16 && c.ws2_scratch)
                         e = tc::launch_ws2_bwd_chain<Epi>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n,
                                                           c.ws2_flags, c.ws2_flags_cap, c.ws2_scratch, true, fmt);
-                    if (e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); e = tc::launch_chain<128, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt); }
+                    if (e == cudaErrorLaunchOutOfResources) {
+                        (void)cudaGetLastError();
+                        e = tc::launch_chain<128, Epi, 4>(mc, st, (const bf16*)c.A, c.lda, c.a_total_rows, c.a_row0, c.a_row_stride, (const bf16*)c.B, c.ldb, c.M, c.N, c.K, dp, n, gbar, true, fmt);
+                        if (e == cudaSuccess) c.gate_ncta = (c.N / 128) * ((c.M + tc::BM - 1) / tc::BM) * 4;
+                    }
                 }
                 else {
                     e = cudaErrorLaunchOutOfResources;
@@ -546,6 +551,7 @@ static int ensure_side(s2vt_handle* h) {
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_wo, cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_seg[0], cudaEventDisableTiming));
     CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_seg[1], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_gate, cudaEventDisableTiming));
     return 0;
 }
 // The "late" half of a refresh (everything but the frame projection / LSTM1 forward weights) runs on the side stream;
@@ -957,6 +963,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     TRY(ensure_side(h));
     cudaStream_t s2 = (h->overlap & 2) ? h->side : st;
     cudaStream_t s3 = (h->overlap & 4) ? h->side : st;   // stream of the LSTM1 backward chain
+    CUDA_TRY(h, cudaMemsetAsync(h->gbar, 0, sizeof(unsigned), st));   // the chain-progress watcher on the side stream must never see the count of an earlier chain
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
     CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev_fork, 0));
     // d embed_word_W = out2^T . dlogits ; d embed_word_b = column sums.  overlap bit 6: not beside the LSTM2 BPTT chain (whose steps it slows from 12 to
@@ -977,6 +984,7 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
     h->seg_ready = h->wo_grad_early ? 1u : 0u;
     // LSTM2 BPTT
     CUDA_TRY(h, cudaMemsetAsync(p.dc2, 0, (size_t)N * Hp * sizeof(float), st));
+    int gate_ncta = 0;
     {
         StepChain<T, EpiLstmBwd<T, F>> ch;    // step s of the chain is time t = T-2-s; its A operand is dG2 of time t+1
         ch.A = p.dG2; ch.lda = Gp; ch.a_total_rows = T_ * N; ch.a_row0 = (T_ - 1) * N; ch.a_row_stride = -N;
@@ -998,10 +1006,39 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
             }
         }
         TRY((run_chain<T, EpiLstmBwd<T, F>>(h, st, ch, p.chain_b2)));
+        gate_ncta = ch.gate_ncta;
     }
+    // ---- side stream 2/2, gated (overlap bit 7): the chain produces dG2 from the last time step down; once it has passed time t_gate, the rows of the times
+    //      >= t_gate are final, and what consumes them -- their part of dout1 = dG2 . W2[x rows]^T and of the two large LSTM2 weight gradients -- runs on the SMs
+    //      the 96-CTA chain leaves idle, behind a watcher of the chain's grid-barrier counter, instead of after the chain.  The rest (times < t_gate) follows on
+    //      the caller's stream as before; the weight gradients are read-modify-write sums, so the two parts simply add up.
+    int t_gate = T_;
+    {
+        static const float gate_frac = getenv("S2VT_GATE_FRAC") ? (float)atof(getenv("S2VT_GATE_FRAC")) : 0.4f;
+        if ((h->overlap & 128) && s2 == h->side && s2 != st && gate_ncta > 0 && !h->prof && T_ >= 16 && gate_frac > 0.f) {
+            t_gate = T_ - (int)(T_ * gate_frac);
+            if (t_gate < 1) t_gate = 1;
+        }
+    }
+    if (t_gate < T_) {
+        const int rowsA = (T_ - t_gate) * N;
+        const size_t off = (size_t)t_gate * N;
+        tc::chain_progress_wait_kernel<<<1, 32, 0, s2>>>(h->gbar, (unsigned)(T_ - 1 - t_gate) * (unsigned)gate_ncta); KCHECK(h);   // chain step s handles time T-2-s
+        typename EpiStore<T>::Params ep = {p.dout1 + off * Hp, nullptr, Hp, nullptr, rowsA, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, s2, p.dG2 + off * Gp, Gp, h->W2x, Gp, rowsA, Hp, Gp, ep)));
+        CUDA_TRY(h, cudaEventRecord(h->ev_gate, s2));
+        float* gW2 = h->G_(h->iW2);
+        EpiGradStore::Params e1 = {gW2, G, H, G, H, 1.f};
+        TRY((wgrad<T, F>(h, s2, p.out1d + off * Hp, Hp, Hp, p.dG2 + off * Gp, Gp, Gp, rowsA, e1, p.tA, p.tB, H)));
+        EpiGradStore::Params e3 = {gW2 + (size_t)(H + E) * G, G, H, G, H, 1.f};
+        TRY((wgrad<T, F>(h, s2, p.h2_all + off * Hp, Hp, Hp, p.dG2 + off * Gp, Gp, Gp, rowsA, e3, p.tA, p.tB, H)));
+        CUDA_TRY(h, cudaEventRecord(h->ev_join, s2));     // tA / tB are free after these
+    }
+    const int MB2 = t_gate * N;     // rows (times < t_gate) handled on the caller's stream
     {   // gradient flowing into LSTM1's (dropped, shared-per-video) output
-        typename EpiStore<T>::Params ep = {p.dout1, nullptr, Hp, nullptr, M2, 0};
-        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2, Gp, h->W2x, Gp, M2, Hp, Gp, ep)));
+        typename EpiStore<T>::Params ep = {p.dout1, nullptr, Hp, nullptr, MB2, 0};
+        TRY((gemm<T, CfgBig, EpiStore<T>>(h, st, p.dG2, Gp, h->W2x, Gp, MB2, Hp, Gp, ep)));
+        if (t_gate < T_) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_gate, 0));
         reduce_dropout_kernel<<<M1, 256, 0, st>>>(p.dout1, B, N, Hp, p.dh1, drop_seed, S2VT_STREAM_DROP1, row_base, keep); KCHECK(h);
     }
     // ---- fork: the LSTM1 chain (B rows, few CTAs per step) runs on the side stream while the main stream computes the
@@ -1060,9 +1097,9 @@ static int train_impl(s2vt_handle* h, cudaStream_t st, int mode, const float* vi
         float* gW2 = h->G_(h->iW2);
         TRY(bias_grad<T>(h, st, p.dG2, Gp, Gp, M2, 0, H, h->G_(h->ib2)));
         EpiGradStore::Params e1 = {gW2, G, H, G, H, 1.f};
-        TRY((wgrad<T, F>(h, st, p.out1d, Hp, Hp, p.dG2, Gp, Gp, M2, e1, p.tA, p.tB, H)));
+        TRY((wgrad<T, F>(h, st, p.out1d, Hp, Hp, p.dG2, Gp, Gp, MB2, e1, p.tA, p.tB, H)));            // times < t_gate (all of them without the gated part)
         EpiGradStore::Params e3 = {gW2 + (size_t)(H + E) * G, G, H, G, H, 1.f};
-        TRY((wgrad<T, F>(h, st, p.h2_all, Hp, Hp, p.dG2, Gp, Gp, M2, e3, p.tA, p.tB, H)));          // h2 before step t = h2_all[t]
+        TRY((wgrad<T, F>(h, st, p.h2_all, Hp, Hp, p.dG2, Gp, Gp, MB2, e3, p.tA, p.tB, H)));           // h2 before step t = h2_all[t]
         // embedding rows: decode steps only
         gather_rows_kernel<F><<<MD, 128, 0, st>>>((const F*)h->WembC, Ep, p.prev_tok, MD, p.emb); KCHECK(h);
         EpiGradStore::Params e2 = {gW2 + (size_t)H * G, G, E, G, H, 1.f};

@@ -13,13 +13,15 @@ DIMS = dict(D=200, E=60, H=72, V=301)
 Tv, Tc, B, K = 3, 7, 4, 2
 
 
-def _run(backend, dims=DIMS, tv=Tv, tc=Tc, b=B, k=K, keep=0.9):
+def _run(backend, dims=DIMS, tv=Tv, tc=Tc, b=B, k=K, keep=0.9, overlap=None):
     import s2vt_b200
     p = M.init_params(seed=4, dtype=np.float32, **dims)
     m = s2vt_b200.Video_Caption_Generator(dim_image=dims['D'], n_words=dims['V'], word_dim=dims['E'], lstm_dim=dims['H'], batch_size=b,
                                           n_video_lstm_step=tv, n_caption_lstm_step=tc, dropout_rate=keep, precision='bf16',
                                           gemm_backend=backend, max_videos=b, max_rows=k * b)
     m.load_variables(p)
+    if overlap is not None:
+        m.lib.s2vt_set_overlap(m.h, overlap)
     video = M.synthetic_features(b, tv, dims['D'])
     samp, greedy = m.rollout(video, k, seed=5)
     mask, _ = m.caption_masks(samp)
@@ -28,8 +30,10 @@ def _run(backend, dims=DIMS, tv=Tv, tc=Tc, b=B, k=K, keep=0.9):
     logp, logits = m.teacher_forward(video, samp, drop_seed=9, want_logits=True)
     loss = m.rl_backward(video, samp, mask, r, base, drop_seed=9).item()
     grads = m.grads[:m.n_params].clone()
+    w2 = m.variable('s2vt/LSTM2/basic_lstm_cell/weights', grad=True)
+    w2_big = torch.cat([w2[:dims['H']], w2[dims['H'] + dims['E']:]]).clone().cpu()      # the [out1 rows] and [h rows] blocks: plain (non-atomic) sums
     m.optimizer_step(1e-3, 5.0)
-    return dict(samp=samp.cpu(), greedy=greedy.cpu(), logits=logits.cpu(), loss=loss, grads=grads.cpu(), params=m.params.cpu().clone())
+    return dict(samp=samp.cpu(), greedy=greedy.cpu(), logits=logits.cpu(), loss=loss, grads=grads.cpu(), params=m.params.cpu().clone(), w2_big=w2_big)
 
 
 @pytest.fixture(scope='module')
@@ -105,3 +109,21 @@ def test_cta_pair_gemms_equal_single_cta_gemms():
     assert torch.equal(a['logits'], p['logits'])
     rel = float((a['grads'] - p['grads']).abs().max() / p['grads'].abs().max())
     assert rel < 1e-5, rel
+
+
+@pytest.mark.parametrize('b,k,tv', [(64, 5, 5), (40, 4, 11)])
+def test_gated_consumption_under_the_bptt_chain_equals_the_sequential_order(b, k, tv):
+    """> 128 caption rows: 40 % of dout1 and of the two large LSTM2 weight gradients (the time steps the LSTM2 BPTT chain finishes first) are computed on
+    the side stream WHILE the chain runs, behind a watcher of its grid-barrier counter (s2vt_set_overlap bit 7, default on), against everything after the
+    chain (mask 7).  Same products; the weight gradients are summed in two parts instead of one -> fp32 summation order only."""
+    dims = dict(D=1536, E=500, H=1000, V=9972)
+    a = _run('auto', dims, tv, 35, b, k, overlap=135)
+    p = _run('auto', dims, tv, 35, b, k, overlap=7)
+    assert torch.equal(a['samp'], p['samp']) and torch.equal(a['logits'], p['logits'])
+    rel = float((a['grads'] - p['grads']).abs().max() / p['grads'].abs().max())
+    assert rel < 1e-5, rel
+    assert a['loss'] == p['loss']
+    again = _run('auto', dims, tv, 35, b, k, overlap=135)
+    # deterministic: the split point is fixed, never "whatever the chain had finished" (the rest of the block holds atomically summed gradients)
+    assert torch.equal(a['w2_big'], again['w2_big'])
+    assert float((a['grads'] - again['grads']).abs().max() / a['grads'].abs().max()) < 1e-6
