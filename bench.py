@@ -560,13 +560,23 @@ def run_b200(args):
     strong, collective = None, None
     if world > 1:
         nbytes = int(model.grads.numel() * 4)
-        s2vt_b200.trainer.allreduce_gradients(model, overlap=False)
-        ar_ms = timed(10, lambda: s2vt_b200.trainer.allreduce_gradients(model, overlap=False)) / 10
-        collective = {'op': 'NCCL all-reduce(sum) of the flat fp32 gradient block, one call, nothing overlapped', 'bytes': nbytes, 'ms': ar_ms,
+        def time_exchange():
+            s2vt_b200.trainer.allreduce_gradients(model, overlap=False)
+            return timed(10, lambda: s2vt_b200.trainer.allreduce_gradients(model, overlap=False)) / 10
+        peer_on = getattr(model, 'peer_world', 0) == world
+        ar_ms = time_exchange()                      # the exchange the timed steps used
+        nccl_ms = ar_ms
+        if peer_on:                                  # ... and NCCL's all-reduce of the same block beside it
+            model.peer_world = 0
+            nccl_ms = time_exchange()
+            model.peer_world = world
+        collective = {'op': ('own kernel over NVLink peer memory (csrc/peer.cuh): reduce-scatter by 128-bit peer loads, all-gather by remote stores from the registers, '
+                             'two flag barriers, one launch per rank' if peer_on else 'NCCL all-reduce(sum)') + ' of the flat fp32 gradient block, nothing overlapped',
+                      'bytes': nbytes, 'ms': ar_ms,
                       'algbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9, 'busbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
-                      'nvlink5_per_direction_GBps': 900.0,
-                      'in_step': 'one collective after the backward call; reducing the early-final segments under the backward kernels '
-                                 '(s2vt_grad_segment_ready, S2VT_AR_SEGMENTS=0,1,2) measured slower on 8 B200: 9.37 vs 9.25 ms per iteration',
+                      'nccl_allreduce_ms': nccl_ms, 'nvlink5_per_direction_GBps': 900.0,
+                      'in_step': 'one exchange after the backward call; reducing the early-final segments under the backward kernels '
+                                 '(s2vt_grad_segment_ready, S2VT_AR_SEGMENTS=0,1,2, NCCL) measured slower on 8 B200: 9.37 vs 9.25 ms per iteration',
                       'early_segments': list(s2vt_b200.trainer.EARLY_SEGMENTS)}
         if args.videos % world == 0:
             Bs = args.videos // world

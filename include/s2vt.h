@@ -179,6 +179,25 @@ int s2vt_profile_shapes(s2vt_handle* h, int cap, int* cls, int* M, int* N, int* 
  * the remaining kernels and reduce the rest afterwards.  S2VT_ESTATE if the last backward call gives no such guarantee (XE / mixed
  * objectives add weight decay or a second pass) or the segment was already handed out. */
 int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int64_t* offset, int64_t* count);
+/* ---- data-parallel gradient exchange over NVLink peer memory (replaces the NCCL all-reduce of trainer.allreduce_gradients; the reference
+ * is single-GPU).  One process per GPU, all GPUs of one NVSwitch node.  Every rank exports its bound state block and a small flag
+ * block as CUDA IPC handles (64 bytes each; state_offset = position of the state block inside its device allocation), the host exchanges them
+ * by any means (trainer.py: torch.distributed all_gather_object), s2vt_peer_connect maps the peers.  s2vt_peer_allreduce then sums the flat
+ * gradient block (+ aux slots) over the ranks with ONE kernel per rank: slice r is summed by rank r in rank order from all blocks
+ * (reduce-scatter by 128-bit loads over NVLink) and written from the registers into every rank's block (all-gather by remote stores), one
+ * flag barrier before and one behind -- identical bits on every rank, independent of timing.  Collective: every rank makes the call, in the same order.  Errors:
+ * S2VT_ECUDA when the memory cannot be shared or mapped (the caller keeps NCCL), S2VT_ESTATE before connect. */
+#define S2VT_PEER_HANDLE_BYTES 64
+int s2vt_peer_export(s2vt_handle* h, unsigned char* state_handle, int64_t* state_offset, unsigned char* comm_handle);
+int s2vt_peer_connect(s2vt_handle* h, int rank, int world, const unsigned char* state_handles, const int64_t* state_offsets, const unsigned char* comm_handles);
+int s2vt_peer_allreduce(s2vt_handle* h, s2vt_stream st);
+/* The exchange fused with s2vt_optimizer_step (same arguments, same arithmetic per element): reduce-scatter, global norm from per-rank partial
+ * sums (added in rank order: the same value everywhere), clip + TF Adam on this rank's slice only, the updated PARAMETERS pushed to every rank.  The
+ * Adam slots are then current in the own slice only: s2vt_optimizer_step refuses (S2VT_ESTATE) and a checkpoint writer calls
+ * s2vt_peer_gather_state (collective) first, which makes them whole on every rank again. */
+int s2vt_peer_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int flags, float* out, s2vt_stream st);
+int s2vt_peer_gather_state(s2vt_handle* h, s2vt_stream st);
+int s2vt_peer_disconnect(s2vt_handle* h);
 /* tuning: which independent pieces use the library's internal side stream (bit 0: late half of s2vt_refresh, bit 1: the
  * vocabulary weight gradient, bit 2: the LSTM1 backward chain, bit 7 (128): the part of dout1 and of the two large LSTM2 weight gradients that
  * belongs to the time steps the LSTM2 BPTT chain finishes first runs beside the rest of that chain, behind a watcher of its grid-barrier counter);

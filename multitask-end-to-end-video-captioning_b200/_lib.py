@@ -58,6 +58,12 @@ SIGNATURES = {
     's2vt_attribute_backward': (_i32, [_vp, _vp, _i32, _vp, _f32, _vp, _vp]),
     's2vt_optimizer_step': (_i32, [_vp, _f32, _f32, _i64, _i32, _vp, _vp]),
     's2vt_grad_segment_ready': (_i32, [_vp, _i32, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    's2vt_peer_export': (_i32, [_vp, _vp, C.POINTER(_i64), _vp]),
+    's2vt_peer_connect': (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    's2vt_peer_allreduce': (_i32, [_vp, _vp]),
+    's2vt_peer_optimizer_step': (_i32, [_vp, _f32, _f32, _i64, _i32, _vp, _vp]),
+    's2vt_peer_gather_state': (_i32, [_vp, _vp]),
+    's2vt_peer_disconnect': (_i32, [_vp]),
     's2vt_launch_count': (C.c_longlong, [_vp]),
     's2vt_profile': (_i32, [_vp, _i32]),
     's2vt_profile_read': (_i32, [_vp, _vp, _vp, _vp]),

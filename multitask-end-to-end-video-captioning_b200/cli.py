@@ -101,6 +101,7 @@ def run_xe(args):
             it += 1
             if args.max_iters and it >= args.max_iters:
                 break
+        model.gather_optimizer_state()      # collective: the Adam slots may be sharded over the ranks (trainer.DP_EXCHANGE)
         if rank == 0:
             pkg.checkpoint.save(model, os.path.join(args.model_path, '%s-%d' % (args.model_name, epoch)), trainer.global_step, step_name='Variable')
         if args.max_iters and it >= args.max_iters:
@@ -134,6 +135,7 @@ def run_rl(args):
             it += 1
             if args.max_iters and it >= args.max_iters:
                 break
+        model.gather_optimizer_state()      # collective: the Adam slots may be sharded over the ranks (trainer.DP_EXCHANGE)
         if rank == 0:
             pkg.checkpoint.save(model, os.path.join(args.model_path, '%s-%d' % (args.model_name, epoch)), trainer.global_step, step_name='g_step')
         if args.max_iters and it >= args.max_iters:
@@ -188,6 +190,7 @@ def run_stage3(args):
                 print('idx: ', start, ' Epoch: ', epoch, ' loss: ', float(xe[0].item()))
             if args.max_iters and it >= args.max_iters:
                 break
+        model.gather_optimizer_state()      # collective: the Adam slots may be sharded over the ranks (trainer.DP_EXCHANGE)
         if rank == 0:
             pkg.checkpoint.save(model, os.path.join(args.model_path, '%s-%d' % (args.model_name, epoch)), step, step_name='g_step')
         if args.max_iters and it >= args.max_iters:
@@ -238,6 +241,7 @@ def run_attribute_loss(args):
                 print('idx: ', start, ' Epoch: ', epoch, ' loss: ', float(rl[0].item()) + alpha * float(at[0].item()))
             if args.max_iters and it >= args.max_iters:
                 break
+        model.gather_optimizer_state()      # collective: the Adam slots may be sharded over the ranks (trainer.DP_EXCHANGE)
         if rank == 0:
             pkg.checkpoint.save(model, os.path.join(args.model_path, '%s-%d' % (args.model_name, epoch)), step, step_name='Variable')
         if args.max_iters and it >= args.max_iters:

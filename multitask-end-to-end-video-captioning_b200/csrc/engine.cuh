@@ -65,6 +65,10 @@ struct s2vt_handle {
     // internal side stream for the LSTM1 backward chain (fork/join inside one call; invisible to the caller)
     cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_refresh = nullptr, ev_wo = nullptr;
     bool wo_grad_early = false;           // the last backward recorded ev_wo when d embed_word_W / d embed_word_b became final (s2vt_grad_segment_ready)
+    // data-parallel exchange over NVLink peer memory (peer.cuh): mapped gradient blocks / flag blocks of all ranks
+    int peer_rank = -1, peer_world = 0, peer_grid = 0; unsigned peer_epoch = 0;
+    void* peer_comm = nullptr; void* peer_opened[32] = {nullptr}; char* peer_s[16] = {nullptr}; void* peer_c[16] = {nullptr};   // state blocks / flag blocks of all ranks
+    bool opt_sharded = false;             // the Adam slots are current in this rank's slice only (s2vt_peer_optimizer_step; s2vt_peer_gather_state clears it)
     cudaEvent_t ev_gate = nullptr;        // the gated side-stream part of dout1 (rows the LSTM2 BPTT chain finished first) is complete
     cudaEvent_t ev_seg[2] = {nullptr, nullptr};   // ... and these when d Wemb (segment 1) / d LSTM2 weights + biases (segment 2) became final
     unsigned seg_ready = 0;               // bit i: segment i of the last backward may be handed out

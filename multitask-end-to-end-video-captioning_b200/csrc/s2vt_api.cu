@@ -18,6 +18,7 @@
 #include "gemm_tcgen05_pair.cuh"
 #include "gemm_tcgen05_persist.cuh"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 template <typename T, typename F>
 __global__ void lstm_bwd_elem_kernel(LstmBwdArgs a, T* dg_out) {
@@ -176,8 +177,10 @@ extern "C" int s2vt_set_reuse_frontend(s2vt_handle* h, int enable) {
     h->front_valid = false;
     return 0;
 }
+static int peer_close(s2vt_handle* h);
 extern "C" void s2vt_destroy(s2vt_handle* h) {
     if (h && h->side) { cudaStreamDestroy(h->side); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_refresh); cudaEventDestroy(h->ev_wo); cudaEventDestroy(h->ev_seg[0]); cudaEventDestroy(h->ev_seg[1]); cudaEventDestroy(h->ev_gate); }
+    if (h) { peer_close(h); if (h->peer_comm) cudaFree(h->peer_comm); }
     if (h && h->tc_cache) delete static_cast<tc::MapCache*>(h->tc_cache);
     delete h;
 }
@@ -1222,6 +1225,7 @@ extern "C" int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, in
     const int wemb_slice_norm = flags & 1, normalize = (flags >> 1) & 1;
     if (!h || !h->bound) return S2VT_ESTATE;
     if (step < 1) return h->fail(S2VT_EINVAL, "Adam step is 1-based");
+    if (h->opt_sharded) return h->fail(S2VT_ESTATE, "the Adam slots are sharded over the ranks (s2vt_peer_optimizer_step): call s2vt_peer_gather_state first");
     cudaStream_t st = (cudaStream_t)st_;
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
     TRY(wait_late_weights(h, st));   // a previous refresh may still be reading the parameters on the side stream
@@ -1235,6 +1239,131 @@ extern "C" int s2vt_optimizer_step(s2vt_handle* h, float lr, float clip_norm, in
     KCHECK(h);
     h->fresh = false;
     return s2vt_refresh(h, st_);
+}
+
+// ---- data-parallel gradient exchange over NVLink peer memory (peer.cuh) -------------------------------------------------------
+static int peer_close(s2vt_handle* h) {
+    for (void*& p : h->peer_opened) if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+    h->peer_rank = -1; h->peer_world = 0;
+    return 0;
+}
+extern "C" int s2vt_peer_export(s2vt_handle* h, unsigned char* state_handle, int64_t* state_offset, unsigned char* comm_handle) {
+    if (!h || !h->bound) return S2VT_ESTATE;
+    if (!state_handle || !state_offset || !comm_handle) return S2VT_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == S2VT_PEER_HANDLE_BYTES, "handle size");
+    typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static RangeFn range = nullptr;
+    if (!range) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            return h->fail(S2VT_ECUDA, "cuMemGetAddressRange is not available");
+        range = (RangeFn)p;
+    }
+    CUdeviceptr base = 0; size_t size = 0;
+    if (range(&base, &size, (CUdeviceptr)h->state) != CUDA_SUCCESS) return h->fail(S2VT_ECUDA, "the state block is not a device allocation");
+    cudaIpcMemHandle_t hs, hc;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hs, (void*)base));    // fails for memory that cannot be shared (e.g. expandable segments): the caller falls back to NCCL
+    if (!h->peer_comm) {
+        CUDA_TRY(h, cudaMalloc(&h->peer_comm, (size_t)2 << 20));     // its own 2 MB block: never part of an allocation that is exported twice
+        CUDA_TRY(h, cudaMemset(h->peer_comm, 0, (size_t)2 << 20));
+    }
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hc, h->peer_comm));
+    memcpy(state_handle, &hs, sizeof hs); memcpy(comm_handle, &hc, sizeof hc);
+    *state_offset = (int64_t)((CUdeviceptr)h->state - base);
+    return S2VT_OK;
+}
+extern "C" int s2vt_peer_connect(s2vt_handle* h, int rank, int world, const unsigned char* state_handles, const int64_t* state_offsets, const unsigned char* comm_handles) {
+    if (!h || !h->bound || !h->peer_comm) return S2VT_ESTATE;
+    if (world < 2 || world > peer::MAXW || rank < 0 || rank >= world || !state_handles || !state_offsets || !comm_handles) return S2VT_EINVAL;
+    peer_close(h);
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) { h->peer_s[q] = h->state; h->peer_c[q] = h->peer_comm; continue; }
+        cudaIpcMemHandle_t hs, hc;
+        memcpy(&hs, state_handles + (size_t)q * sizeof hs, sizeof hs); memcpy(&hc, comm_handles + (size_t)q * sizeof hc, sizeof hc);
+        void *ps = nullptr, *pc = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ps, hs, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) { h->peer_opened[2 * q] = ps; e = cudaIpcOpenMemHandle(&pc, hc, cudaIpcMemLazyEnablePeerAccess); }
+        if (e != cudaSuccess) { (void)cudaGetLastError(); peer_close(h); return h->fail(S2VT_ECUDA, "peer exchange: cannot map rank %d's memory: %s", q, cudaGetErrorString(e)); }
+        h->peer_opened[2 * q + 1] = pc;
+        h->peer_s[q] = (char*)ps + state_offsets[q];
+        h->peer_c[q] = pc;
+    }
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    CUDA_TRY(h, cudaFuncSetAttribute(peer::peer_allreduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, peer::TMA_SMEM));
+    CUDA_TRY(h, cudaFuncSetAttribute(peer::peer_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, peer::TMA_SMEM));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer::peer_step_kernel, 512, peer::TMA_SMEM));
+    if (per_sm < 1) return h->fail(S2VT_ECUDA, "peer exchange: kernel does not fit");
+    h->peer_grid = sms;      // one CTA per SM, co-resident by construction (cooperative launch)
+    h->peer_rank = rank; h->peer_world = world;
+    return S2VT_OK;
+}
+extern "C" int s2vt_peer_disconnect(s2vt_handle* h) {
+    if (!h) return S2VT_EINVAL;
+    return peer_close(h);
+}
+static void peer_args(s2vt_handle* h, peer::Args& a, const float* block) {      // block: which per-rank block a.p points at (params / adam_m / adam_v)
+    memset(&a, 0, sizeof a);
+    const size_t goff = (size_t)((char*)h->grads - h->state), boff = (size_t)((const char*)block - h->state);
+    for (int q = 0; q < h->peer_world; ++q) {
+        a.g[q] = reinterpret_cast<float*>(h->peer_s[q] + goff);
+        a.p[q] = reinterpret_cast<float*>(h->peer_s[q] + boff);
+        a.comm[q] = reinterpret_cast<peer::Comm*>(h->peer_c[q]);
+    }
+    a.rank = h->peer_rank; a.world = h->peer_world; a.epoch = ++h->peer_epoch;
+    a.P = h->P; a.n = h->P + 8; a.n4 = a.n / 4;
+    a.slice4 = (a.n4 + a.world - 1) / a.world;
+    static const int use_tma = getenv("S2VT_PEER_TMA") ? atoi(getenv("S2VT_PEER_TMA")) : 1;
+    a.tma = use_tma && a.world <= peer::TMA_WMAX;
+}
+// grads (+ aux slots) <- sum over the ranks, identical bits on every rank; every rank must make the call (same order of calls everywhere)
+extern "C" int s2vt_peer_allreduce(s2vt_handle* h, s2vt_stream st_) {
+    if (!h || !h->bound || h->peer_world < 2) return S2VT_ESTATE;
+    peer::Args a;
+    peer_args(h, a, h->params);
+    void* args[] = {&a};
+    CUDA_TRY(h, cudaLaunchCooperativeKernel((const void*)peer::peer_allreduce_kernel, dim3(h->peer_grid), dim3(512), args, peer::TMA_SMEM, (cudaStream_t)st_));
+    h->launches++;
+    return S2VT_OK;
+}
+// s2vt_peer_allreduce + s2vt_optimizer_step in one kernel per rank: every rank reduces, clips and applies TF Adam to its own slice of the flat vector
+// and the updated PARAMETERS are gathered instead of the gradients.  Arguments as s2vt_optimizer_step.
+extern "C" int s2vt_peer_optimizer_step(s2vt_handle* h, float lr, float clip_norm, int64_t step, int flags, float* gnorm_out, s2vt_stream st_) {
+    if (!h || !h->bound || h->peer_world < 2) return S2VT_ESTATE;
+    if (step < 1) return h->fail(S2VT_EINVAL, "Adam step is 1-based");
+    cudaStream_t st = (cudaStream_t)st_;
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    TRY(wait_late_weights(h, st));   // a previous refresh may still be reading the parameters on the side stream
+    peer::Args a;
+    peer_args(h, a, h->params);
+    const Var& we = h->vars[h->iWemb];
+    a.m = h->adam_m; a.v = h->adam_v;
+    a.wemb_lo = we.off; a.wemb_hi = we.off + we.count();
+    a.use_slice_norm = flags & 1; a.normalize = (flags >> 1) & 1;
+    a.clip = clip_norm; a.b1 = b1; a.b2 = b2; a.eps = eps; a.gnorm_out = gnorm_out;
+    a.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step)));
+    void* args[] = {&a};
+    CUDA_TRY(h, cudaLaunchCooperativeKernel((const void*)peer::peer_step_kernel, dim3(h->peer_grid), dim3(512), args, peer::TMA_SMEM, st));
+    h->launches++;
+    h->opt_sharded = true;
+    h->fresh = false;
+    return s2vt_refresh(h, st_);
+}
+// Adam slots of all slices into this rank's blocks (collective).  After it the slots are whole again on every rank: checkpoints, s2vt_optimizer_step.
+extern "C" int s2vt_peer_gather_state(s2vt_handle* h, s2vt_stream st_) {
+    if (!h || !h->bound || h->peer_world < 2) return S2VT_ESTATE;
+    for (int which = 0; which < 2; ++which) {
+        peer::Args a;
+        peer_args(h, a, which ? h->adam_v : h->adam_m);
+        int phase0 = 0;
+        void* args[] = {&a, &phase0};
+        CUDA_TRY(h, cudaLaunchCooperativeKernel((const void*)peer::peer_gather_kernel, dim3(h->peer_grid), dim3(512), args, 0, (cudaStream_t)st_));
+        h->launches++;
+    }
+    h->opt_sharded = false;
+    return S2VT_OK;
 }
 
 // ---- workspace sizing ---------------------------------------------------------------------------------------------

@@ -74,6 +74,8 @@ class Video_Caption_Generator(object):
             shp = (shape[0], shape[1]) if nd.value == 2 else (shape[0],)
             self.variables[name.value.decode()] = (off.value, shp)
         self.adam_step = 0
+        self.peer_world = 0          # > 0 once peer_connect mapped the other ranks' gradient blocks
+        self.optimizer_sharded = False
         self._loss = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.initialize(seed, bias_init_vector)
 
@@ -246,6 +248,46 @@ class Video_Caption_Generator(object):
             return None
         self._check(rc)
         return off.value, cnt.value
+
+    # ---- data-parallel exchange over NVLink peer memory (include/s2vt.h: s2vt_peer_*) -----------------------------------
+    def peer_export(self):
+        """(state handle, offset of the state block in its allocation, flag-block handle) to hand to the other ranks."""
+        hs, hc, off = (C.c_ubyte * 64)(), (C.c_ubyte * 64)(), C.c_int64()
+        self._check(self.lib.s2vt_peer_export(self.h, hs, C.byref(off), hc))
+        return bytes(hs), off.value, bytes(hc)
+
+    def peer_connect(self, rank, exports):
+        """exports: the peer_export() tuples of all ranks, in rank order."""
+        world = len(exports)
+        hs = (C.c_ubyte * (64 * world)).from_buffer_copy(b''.join(e[0] for e in exports))
+        hc = (C.c_ubyte * (64 * world)).from_buffer_copy(b''.join(e[2] for e in exports))
+        offs = (C.c_int64 * world)(*[e[1] for e in exports])
+        self._check(self.lib.s2vt_peer_connect(self.h, int(rank), world, hs, offs, hc))
+        self.peer_world = world
+
+    def peer_allreduce(self):
+        self._check(self.lib.s2vt_peer_allreduce(self.h, _stream()))
+
+    def peer_optimizer_step(self, lr, clip_norm, wemb_slice_norm=True, normalize=True):
+        """allreduce_gradients + optimizer_step as one kernel per rank (collective): every rank clips and applies Adam to its own slice of the
+        flat vector, the updated parameters are gathered.  The Adam slots stay sharded until gather_optimizer_state()."""
+        self.adam_step += 1
+        out = torch.empty(2, dtype=torch.float32, device=self.device)
+        flags = (1 if wemb_slice_norm else 0) | (2 if normalize else 0)
+        self._check(self.lib.s2vt_peer_optimizer_step(self.h, float(lr), float(clip_norm), self.adam_step, flags, _ptr(out), _stream()))
+        self.optimizer_sharded = True
+        return out
+
+    def gather_optimizer_state(self):
+        """Collective when the Adam slots are sharded (after peer_optimizer_step): make them whole on every rank (before saving them)."""
+        if getattr(self, 'optimizer_sharded', False):
+            self._check(self.lib.s2vt_peer_gather_state(self.h, _stream()))
+            self.optimizer_sharded = False
+
+    def peer_disconnect(self):
+        self.gather_optimizer_state()
+        self.peer_world = 0
+        self._check(self.lib.s2vt_peer_disconnect(self.h))
 
     def set_reuse_frontend(self, enable=True):
         """Share the LSTM1 forward of a rollout with the training call that follows on the same video tensor."""

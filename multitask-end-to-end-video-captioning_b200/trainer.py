@@ -34,6 +34,44 @@ import os as _os
 EARLY_SEGMENTS = tuple(int(x) for x in _os.environ.get('S2VT_AR_SEGMENTS', '').split(',') if x.strip() != '')
 
 
+# The gradient exchange itself: 'peer' = the library's own kernels over NVLink peer memory (csrc/peer.cuh; every rank maps the other ranks'
+# state blocks through CUDA IPC) with the exchange FUSED with the optimiser step where a trainer allows it (reduce-scatter, Adam on the own
+# slice, all-gather of the parameters), 'peer_allreduce' = the peer kernel as a plain all-reduce + the full Adam pass, 'nccl' =
+# torch.distributed all-reduce.  S2VT_DP_EXCHANGE overrides; the default tries 'peer' and keeps NCCL when the memory cannot be shared
+# (another node, an allocator that does not hand out IPC-capable memory).
+DP_EXCHANGE = _os.environ.get('S2VT_DP_EXCHANGE', 'peer')
+
+
+def connect_peers(model):
+    """Collective: map the gradient blocks of all ranks of the default process group into this rank's library handle.  Returns True when
+    allreduce_gradients will use the peer kernel from now on; every rank gets the same answer."""
+    rank, world = _world()
+    if world == 1 or not model.grads.is_cuda or DP_EXCHANGE not in ('peer', 'peer_allreduce') or not hasattr(model, 'peer_export'):
+        return False
+    try:
+        mine = model.peer_export()
+    except Exception as e:          # not shareable: say so once, keep NCCL
+        mine = None
+        if rank == 0:
+            print('s2vt: peer exchange unavailable (%s); using the NCCL all-reduce' % e)
+    exports = [None] * world
+    dist.all_gather_object(exports, mine)
+    ok = all(e is not None for e in exports)
+    if ok:
+        try:
+            model.peer_connect(rank, exports)
+        except Exception as e:
+            ok = False
+            print('s2vt: rank %d cannot map its peers (%s); using the NCCL all-reduce' % (rank, e))
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok))
+    if not all(flags):
+        if getattr(model, 'peer_world', 0):
+            model.peer_disconnect()
+        return False
+    return True
+
+
 def allreduce_gradients(model, bucket_bytes=0, overlap=True):
     """Sum the flat fp32 gradient block (+ aux slots: slice norm, loss, sum(mask)) over the ranks.
 
@@ -45,6 +83,9 @@ def allreduce_gradients(model, bucket_bytes=0, overlap=True):
     into buckets; NVSwitch bandwidth does not ask for it)."""
     rank, world = _world()
     if world == 1:
+        return
+    if getattr(model, 'peer_world', 0) == world:
+        model.peer_allreduce()       # one kernel per rank over NVLink peer memory, on the current stream
         return
     g = model.grads
     n = g.numel()
@@ -161,6 +202,7 @@ class ReinforceTrainer(object):
         self.global_step = 0
         self.last = {}
         model.set_reuse_frontend(True)      # rollout and update run on the same feature tensor within step()
+        self.peer_exchange = connect_peers(model)      # collective under torch.distributed; False -> NCCL all-reduce
 
     def step(self, video, video_index):
         """video: float32 [B, T_v, D] on the device or in (pinned) host memory; video_index: int32 [B] corpus video
@@ -180,9 +222,12 @@ class ReinforceTrainer(object):
         b = scores[K * B:].repeat(K)                                                              # :790-795
         drop_seed = (self.seed * 7919 + it + 1) if self.dropout else 0
         m.rl_backward(v, samp, mask, r, b, norm=1.0, drop_seed=drop_seed, row_base=row_base)      # :643-650, norm deferred
-        allreduce_gradients(m)
         lr = exponential_decay(self.lr0, it, self.decay_steps)
-        out = m.optimizer_step(lr, self.clip, wemb_slice_norm=self.wemb_slice_norm, normalize=True)   # :650-652
+        if self.peer_exchange and DP_EXCHANGE == 'peer':      # exchange + clip + Adam in one kernel per rank
+            out = m.peer_optimizer_step(lr, self.clip, wemb_slice_norm=self.wemb_slice_norm, normalize=True)
+        else:
+            allreduce_gradients(m)
+            out = m.optimizer_step(lr, self.clip, wemb_slice_norm=self.wemb_slice_norm, normalize=True)   # :650-652
         self.global_step += 1
         self.last = dict(samples=samp, greedy=greedy, rewards=r, baseline=b, mask=mask)
         return out
@@ -194,6 +239,7 @@ class XETrainer(object):
     def __init__(self, model, start_learning_rate=1e-3, decay_steps=5000, clip_norm=10.0, seed=2024, dropout=True):
         self.model, self.lr0, self.decay_steps, self.clip = model, start_learning_rate, decay_steps, clip_norm
         self.seed, self.dropout, self.global_step = int(seed), dropout, 0
+        self.peer_exchange = connect_peers(model)
 
     def step(self, video, captions, mask):
         m = self.model

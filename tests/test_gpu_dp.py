@@ -33,7 +33,7 @@ def _model(p):
     return m
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, exchange):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
@@ -42,20 +42,46 @@ def _worker(rank, world, port, out):
     p, video, cap, mask, r, b = _inputs()
     m = _model(p)
     m.rl_backward(video[rank * B:(rank + 1) * B], cap[rank], mask[rank], r[rank], b[rank], norm=1.0, drop_seed=11, row_base=rank * K * B)
+    if exchange != 'nccl':
+        assert s2vt_b200.trainer.connect_peers(m), 'the peer exchange did not come up'
+        g_before = m.grads.clone()
+    if exchange == 'peer_fused':      # exchange + clip + Adam on the own slice + parameter gather in one kernel per rank
+        out_t = m.peer_optimizer_step(1e-3, 0.05, wemb_slice_norm=True, normalize=True)
+        with pytest.raises(RuntimeError):
+            m.optimizer_step(1e-3, 0.05)          # the Adam slots are sharded: the plain step refuses
+        m.adam_step -= 1
+        m.gather_optimizer_state()
+        torch.cuda.synchronize()
+        if rank == 0:
+            torch.save({'params': m.params.cpu(), 'out': out_t.cpu(), 'm': m.adam_m.cpu(), 'v': m.adam_v.cpu()}, out)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     s2vt_b200.trainer.allreduce_gradients(m)
+    if exchange == 'peer':      # the same sum through NCCL
+        g_peer = m.grads.clone()
+        m.grads.copy_(g_before)
+        m.peer_world = 0
+        s2vt_b200.trainer.allreduce_gradients(m)
+        err = float((g_peer - m.grads).abs().max() / m.grads.abs().max())
+        assert err < 1e-6, err
+        m.grads.copy_(g_peer)
     out_t = m.optimizer_step(1e-3, 0.05, wemb_slice_norm=True, normalize=True)
     torch.cuda.synchronize()
     if rank == 0:
-        torch.save({'params': m.params.cpu(), 'out': out_t.cpu()}, out)
+        torch.save({'params': m.params.cpu(), 'out': out_t.cpu(), 'm': m.adam_m.cpu(), 'v': m.adam_v.cpu()}, out)
+    dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_update_equals_single_process_update(tmp_path):
+@pytest.mark.parametrize('exchange', ['nccl', 'peer', 'peer_fused'])
+def test_two_rank_update_equals_single_process_update(tmp_path, exchange):
+    """exchange: the NCCL all-reduce, or the library's own kernel over NVLink peer memory (csrc/peer.cuh; also held equal to NCCL's sum)."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
     out = str(tmp_path / 'dp.pt')
-    mp.spawn(_worker, args=(2, 29633, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29633 + ['nccl', 'peer', 'peer_fused'].index(exchange), out, exchange), nprocs=2, join=True)
     got = torch.load(out)
     # single process: the same rows as one batch.  Rows are sample-major per rank, so the concatenated batch keeps each
     # rank's block with its own videos: use one video per row (the literal feed) and the matching Philox row ids.
@@ -69,4 +95,7 @@ def test_two_rank_update_equals_single_process_update(tmp_path):
     print('\n[dp] 2-rank vs 1-process parameters rel diff %.3e, grad norm %.5f vs %.5f, loss %.6f vs %.6f'
           % (e, got['out'][0], ref[0].item(), got['out'][1], ref[1].item()))
     assert e < 1e-5
+    for slot, ref_slot in (('m', m2.adam_m), ('v', m2.adam_v)):       # the Adam slots (gathered from their slices in the fused form)
+        es = float((got[slot] - ref_slot.cpu()).abs().max() / ref_slot.abs().max().item())
+        assert es < 1e-4, (slot, es)
     assert abs(got['out'][0] - ref[0].item()) < 1e-4 * ref[0].item() and abs(got['out'][1] - ref[1].item()) < 1e-4 * abs(ref[1].item()) + 1e-7
