@@ -577,7 +577,10 @@ def run_b200(args):
                       'nccl_allreduce_ms': nccl_ms, 'nvlink5_per_direction_GBps': 900.0,
                       'in_step': 'one exchange after the backward call; reducing the early-final segments under the backward kernels '
                                  '(s2vt_grad_segment_ready, S2VT_AR_SEGMENTS=0,1,2, NCCL) measured slower on 8 B200: 9.37 vs 9.25 ms per iteration',
-                      'early_segments': list(s2vt_b200.trainer.EARLY_SEGMENTS)}
+                      'early_segments': list(s2vt_b200.trainer.EARLY_SEGMENTS),
+                      'exchange_in_the_timed_steps': ('peer kernel fused with clip + Adam on the own slice (s2vt_peer_optimizer_step)'
+                                                      if peer_on and s2vt_b200.trainer.DP_EXCHANGE == 'peer' else
+                                                      'peer kernel all-reduce + full Adam' if peer_on else 'NCCL all-reduce + full Adam')}
         if args.videos % world == 0:
             Bs = args.videos // world
             m2 = s2vt_b200.Video_Caption_Generator(dim_image=DIMS['D'], n_words=DIMS['V'], word_dim=DIMS['E'], lstm_dim=DIMS['H'], batch_size=Bs,

@@ -108,6 +108,7 @@ def _dp_worker(rank, world, port, out):
     m.grads = torch.arange(n + 8, dtype=torch.float32) * (rank + 1)
     m.grads[n + 2] = 10.0 * (rank + 1)                           # aux slot: local sum(mask)
     from s2vt_b200 import trainer
+    assert trainer.connect_peers(m) is False                      # host memory cannot be mapped by peers: the NCCL / gloo all-reduce stays
     trainer.allreduce_gradients(m, bucket_bytes=1024)            # several buckets
     if rank == 0:
         torch.save(m.grads, out)
