@@ -570,7 +570,7 @@ def run_b200(args):
             model.peer_world = 0
             nccl_ms = time_exchange()
             model.peer_world = world
-        collective = {'op': ('own kernel over NVLink peer memory (csrc/peer.cuh): reduce-scatter by 128-bit peer loads, all-gather by remote stores from the registers, '
+        collective = {'op': ('own kernel over NVLink peer memory (csrc/peer.cuh): reduce-scatter by cp.async.bulk loads from every rank, sums pushed into every rank by bulk stores, '
                              'two flag barriers, one launch per rank' if peer_on else 'NCCL all-reduce(sum)') + ' of the flat fp32 gradient block, nothing overlapped',
                       'bytes': nbytes, 'ms': ar_ms,
                       'algbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9, 'busbw_GBps': nbytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world,
