@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-kernel SASS opcode summary of libs2vt_b200.so (tcgen05 / TMEM / TMA evidence): python scripts/sass_summary.py > profiles/<name>.md
 UTCHMMA = tcgen05.mma (".2CTA": cta_group::2), LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor (TMA load; ".MULTICAST" variants),
-UTCBAR = tcgen05.commit, SYNCS = mbarrier operations, HMMA = mma.sync (the checker mainloop)."""
+UTCBAR = tcgen05.commit, SYNCS = mbarrier operations, HMMA = mma.sync (the checker mainloop), UBLKCP = cp.async.bulk (1-D bulk copies: the
+peer exchange kernels' loads from / stores to other GPUs)."""
 import collections
 import os
 import re
@@ -10,7 +11,7 @@ import sys
 
 lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'multitask-end-to-end-video-captioning_b200', 'libs2vt_b200.so')
 out = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
-ops = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'UTMALDG', 'UTMALDG.MULTICAST', 'UTCBAR', 'SYNCS', 'HMMA', 'UCGABAR', 'REDG']
+ops = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'UTMALDG', 'UTMALDG.MULTICAST', 'UBLKCP', 'UTCBAR', 'SYNCS', 'HMMA', 'UCGABAR', 'REDG']
 per = collections.OrderedDict()
 cur = None
 for line in out.splitlines():
@@ -36,6 +37,8 @@ for line in out.splitlines():
         c['UTMALDG'] += 1
         if 'MULTICAST' in op:
             c['UTMALDG.MULTICAST'] += 1
+    elif op.startswith('UBLKCP'):
+        c['UBLKCP'] += 1
     elif op.startswith('UTCBAR'):
         c['UTCBAR'] += 1
     elif op.startswith('SYNCS'):
@@ -50,7 +53,7 @@ demangle = subprocess.run(['c++filt'], input='\n'.join(per), capture_output=True
 tot = collections.Counter()
 rows = []
 for (name, c), dn in zip(per.items(), demangle):
-    if not (c['UTCHMMA'] or c['LDTM'] or c['UTMALDG'] or c['HMMA']):
+    if not (c['UTCHMMA'] or c['LDTM'] or c['UTMALDG'] or c['HMMA'] or c['UBLKCP']):
         continue
     dn = re.sub(r'\(.*', '', dn).replace('void ', '')
     rows.append((dn, c))
