@@ -2,17 +2,20 @@
 //
 // The path's only exchange step is the sum of the flat fp32 gradient block (+ aux slots) over the ranks once per iteration
 // (trainer.allreduce_gradients).  NCCL does it in 0.39 ms for 127 MB on 8 B200.  Here every rank maps the other ranks' state
-// blocks (CUDA IPC) and ONE kernel per rank does the whole exchange with plain loads over NVLink:
+// blocks (CUDA IPC) and ONE cooperative kernel per rank does the whole exchange with ordinary addresses over NVLink.
+//
+// peer_allreduce_kernel (all-reduce):
 //   barrier A   every rank's backward pass is complete (the kernel is stream-ordered behind it)
-//   phase 1     rank r sums slice r of all W gradient blocks in rank order 0..W-1 (W-1 of them read from peer memory, 8 independent
-//               128-bit loads in flight per thread) and stores it into its own block: a reduce-scatter by pulling
-//               ... and writes the sum straight from its registers into ALL W blocks (W-1 of them remote stores): the all-gather by pushing,
-//               in the same loop, no second pass (measured on 8 B200: pulling the reduced slices in a second phase 0.47 ms, NCCL 0.39 ms)
+//   phase 1     rank r sums slice r of all W gradient blocks in rank order 0..W-1 (a reduce-scatter by pulling: cp.async.bulk pieces of every block
+//               into shared memory, reduce_slice_tma; or 128-bit loads, reduce_slice) and writes the sum into ALL W blocks in the same loop (the
+//               all-gather by pushing; measured on 8 B200: pulling the reduced slices in a second phase 0.47 ms, pushing 0.42, bulk copies 0.37)
 //   barrier B   every rank's sums have landed everywhere; nobody reads or writes this rank's block any more
+// peer_step_kernel (the exchange fused with the optimiser step):
+//   barrier A, phase 1 without the push but with sum g^2 of the slice -> barrier B carries the partial sums to every rank -> clip + TF Adam on the
+//   own slice, the updated PARAMETERS written into all W parameter blocks -> barrier C.
 // A slice is summed by exactly one rank in a fixed order, so every rank ends up with the same bits and the result does not depend on
 // timing.  The barriers are flags in a small exported block per rank: st.release.sys into every peer's block, ld.acquire.sys polls on
-// the own one, epochs instead of resets; a watchdog traps instead of hanging.  The kernel is launched cooperatively (grid.sync between
-// the local phases).
+// the own one, epochs instead of resets; a watchdog traps instead of hanging.  grid.sync between the local phases.
 #pragma once
 #include <cooperative_groups.h>
 #include "gemm_tcgen05.cuh"      // mbarrier helpers
