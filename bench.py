@@ -597,6 +597,9 @@ def run_b200(args):
                       'value': args.videos * args.steps / (ms_s / 1e3), 'unit': 'videos/s',
                       'note': 'BASELINE config 2 literally: global batch %d split over %d GPUs; the per-GPU work shrinks to %d rows, the %d sequential '
                               'recurrent steps and the all-reduce do not' % (args.videos, world, K * Bs, 3 * (Tv + 35) + 2 * 35)}
+            if getattr(m2, 'peer_world', 0):      # unmap the peers' blocks on every rank BEFORE any rank frees its own (CUDA IPC rule)
+                m2.peer_disconnect()
+            barrier()
             del t2, m2
             torch.cuda.empty_cache()
     run_e2e(2)

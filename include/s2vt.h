@@ -186,7 +186,8 @@ int s2vt_grad_segment_ready(s2vt_handle* h, int segment, s2vt_stream stream, int
  * gradient block (+ aux slots) over the ranks with ONE kernel per rank: slice r is summed by rank r in rank order from all blocks
  * (reduce-scatter by 128-bit loads over NVLink) and written from the registers into every rank's block (all-gather by remote stores), one
  * flag barrier before and one behind -- identical bits on every rank, independent of timing.  Collective: every rank makes the call, in the same order.  Errors:
- * S2VT_ECUDA when the memory cannot be shared or mapped (the caller keeps NCCL), S2VT_ESTATE before connect. */
+ * S2VT_ECUDA when the memory cannot be shared or mapped (the caller keeps NCCL), S2VT_ESTATE before connect.  Teardown: every rank calls
+ * s2vt_peer_disconnect (or destroys its handle) BEFORE any rank frees its state block -- CUDA IPC forbids freeing memory a peer still maps. */
 #define S2VT_PEER_HANDLE_BYTES 64
 int s2vt_peer_export(s2vt_handle* h, unsigned char* state_handle, int64_t* state_offset, unsigned char* comm_handle);
 int s2vt_peer_connect(s2vt_handle* h, int rank, int world, const unsigned char* state_handles, const int64_t* state_offsets, const unsigned char* comm_handles);
