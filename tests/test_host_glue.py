@@ -192,3 +192,75 @@ def test_restore_brings_adam_state_and_matching_step_counter(tmp_path):
     e = _FakeModel(4)
     ck.optimistic_restore(e, str(tmp_path / 'tf_like.npz'), with_optimizer=True)
     assert e.adam_step == 7
+
+
+class _FakeModel(object):
+    """Records what ReinforceTrainer.step asks of the library (host logic only; CPU tensors)."""
+
+    def __init__(self, rank):
+        self.device = torch.device('cpu')
+        self.grads = torch.zeros(16 + 8)
+        self.calls = []
+        self.rank = rank
+
+    def set_reuse_frontend(self, enable=True):
+        self.calls.append(('reuse', enable))
+
+    def rollout(self, v, K, seed, row_base=0):
+        self.calls.append(('rollout', K, seed, row_base))
+        B = v.shape[0]
+        return torch.full((K * B, 35), 3, dtype=torch.int32), torch.full((B, 35), 4, dtype=torch.int32)
+
+    def caption_masks(self, ids):
+        return torch.ones(ids.shape, dtype=torch.float32), None
+
+    def rl_backward(self, v, samp, mask, r, b, norm=0.0, drop_seed=0, row_base=0):
+        self.calls.append(('backward', norm, drop_seed, row_base, float(r.sum()), float(b.sum())))
+        self.grads[:16] = float(self.rank + 1)
+        self.grads[16 + 2] = float(mask.sum())              # aux slot: local sum(mask)
+
+    def optimizer_step(self, lr, clip, wemb_slice_norm=True, normalize=False):
+        self.calls.append(('adam', lr, clip, wemb_slice_norm, normalize, self.grads.clone()))
+        return torch.zeros(2)
+
+
+class _FakeScorer(object):
+    def score_ids(self, ids, vi):
+        return torch.arange(ids.shape[0], dtype=torch.float64) * 0.01
+
+
+def _trainer_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from s2vt_b200 import trainer
+    m = _FakeModel(rank)
+    tr = trainer.ReinforceTrainer(m, _FakeScorer(), n_samples=3, start_learning_rate=1e-3, decay_steps=2, clip_norm=5.0, seed=7)
+    assert tr.peer_exchange is False                             # host tensors: the collective path
+    for _ in range(3):
+        tr.step(np.zeros((2, 4, 8), np.float32), np.array([0, 1], np.int32))
+    if rank == 1:
+        torch.save(m.calls, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reinforce_trainer_step_host_logic_world_size_2_gloo(tmp_path):
+    """Rank 1 of 2: Philox row base = rank * K * B, per-iteration seeds, norm deferred to the optimiser (normalize=True), gradients and the
+    sum(mask) aux slot summed over the ranks before the optimiser step, staircase learning-rate decay."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'calls.pt')
+    mp.spawn(_trainer_worker, args=(2, 29617, out), nprocs=2, join=True)
+    calls = torch.load(out, weights_only=False)
+    assert calls[0] == ('reuse', True)
+    K, B = 3, 2
+    steps = [calls[1 + 3 * i: 4 + 3 * i] for i in range(3)]
+    for it, (ro, bw, ad) in enumerate(steps):
+        assert ro == ('rollout', K, 7 + it, 1 * K * B)
+        assert bw[:4] == ('backward', 1.0, 7 * 7919 + it + 1, 1 * K * B)
+        assert abs(bw[4] - sum(0.01 * j for j in range(K * B))) < 1e-6                       # rewards: scores of the K * B sampled rows
+        assert abs(bw[5] - K * sum(0.01 * (K * B + j) for j in range(B))) < 1e-6             # baseline: the greedy scores, repeated K times
+        assert ad[0] == 'adam' and abs(ad[1] - 1e-3 * 0.5 ** (it // 2)) < 1e-12 and ad[2] == 5.0 and ad[3] is True and ad[4] is True
+        g = ad[5]
+        assert torch.equal(g[:16], torch.full((16,), 3.0))                                  # 1 + 2 over the two ranks
+        assert g[18].item() == 2 * K * B * 35                                                # global sum(mask)
