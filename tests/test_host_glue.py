@@ -264,3 +264,54 @@ def test_reinforce_trainer_step_host_logic_world_size_2_gloo(tmp_path):
         g = ad[5]
         assert torch.equal(g[:16], torch.full((16,), 3.0))                                  # 1 + 2 over the two ranks
         assert g[18].item() == 2 * K * B * 35                                                # global sum(mask)
+
+
+class _FakeXEModel(object):
+    def __init__(self, rank):
+        self.device = torch.device('cpu')
+        self.grads = torch.zeros(8 + 8)
+        self.rank, self.calls = rank, []
+
+    def _f32(self, x):
+        return torch.as_tensor(x, dtype=torch.float32)
+
+    def xe_backward_sharded(self, video, captions, mask, colsum, n_global, norm, decay=None, drop_seed=0, row_base=0):
+        self.calls.append(('xe', colsum.clone(), n_global, norm, decay, drop_seed, row_base))
+        self.grads[:8] = float(10 * (self.rank + 1))
+        return torch.tensor([1.0 + self.rank, 0.5 if decay is None else 0.0])
+
+    def optimizer_step(self, lr, clip, wemb_slice_norm=True, normalize=False):
+        self.calls.append(('adam', lr, clip, wemb_slice_norm, normalize, self.grads.clone()))
+
+
+def _xe_trainer_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from s2vt_b200 import trainer
+    m = _FakeXEModel(rank)
+    tr = trainer.XETrainer(m, start_learning_rate=1e-3, decay_steps=5000, clip_norm=10.0, seed=3)
+    n = 2 + rank                                                  # ragged shards: 2 rows on rank 0, 3 on rank 1
+    mask = np.zeros((n, 6), np.float32); mask[:, :2 + rank] = 1
+    loss = tr.step(np.zeros((n, 4, 8), np.float32), np.zeros((n, 6), np.int32), mask)
+    torch.save((m.calls, loss), out + str(rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_xe_trainer_step_host_logic_world_size_2_gloo(tmp_path):
+    """Q3 couples the rows of a batch: the ranks exchange the per-step mask sums and the row count FIRST, back-propagate with the global
+    statistics (weight decay on rank 0 only), then sum gradients and loss parts."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'xe')
+    mp.spawn(_xe_trainer_worker, args=(2, 29619, out), nprocs=2, join=True)
+    for rank in range(2):
+        calls, loss = torch.load(out + str(rank), weights_only=False)
+        xe, ad = calls
+        colsum = torch.tensor([5., 5., 3., 0., 0., 0.])           # 2 rows with 2 ones + 3 rows with 3 ones
+        assert xe[0] == 'xe' and torch.equal(xe[1], colsum) and xe[2] == 5 and xe[3] == 13.0
+        assert xe[4] == (None if rank == 0 else 0.0)
+        assert xe[5] == 3 * 7919 + 1 and xe[6] == rank * (2 + rank)
+        assert ad[0] == 'adam' and ad[1] == 1e-3 and ad[2] == 10.0 and ad[3] is False
+        assert torch.equal(ad[5][:8], torch.full((8,), 30.0))
+        assert torch.equal(loss, torch.tensor([3.0, 0.5]))        # CE parts add up, the decay part comes from rank 0 alone
