@@ -194,7 +194,7 @@ def test_restore_brings_adam_state_and_matching_step_counter(tmp_path):
     assert e.adam_step == 7
 
 
-class _FakeModel(object):
+class _FakeRLModel(object):
     """Records what ReinforceTrainer.step asks of the library (host logic only; CPU tensors)."""
 
     def __init__(self, rank):
@@ -234,7 +234,7 @@ def _trainer_worker(rank, world, port, out):
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from s2vt_b200 import trainer
-    m = _FakeModel(rank)
+    m = _FakeRLModel(rank)
     tr = trainer.ReinforceTrainer(m, _FakeScorer(), n_samples=3, start_learning_rate=1e-3, decay_steps=2, clip_norm=5.0, seed=7)
     assert tr.peer_exchange is False                             # host tensors: the collective path
     for _ in range(3):
